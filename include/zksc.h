@@ -1,0 +1,184 @@
+/* zksc -- B200-native sumcheck prover: the drop-in C ABI.
+ *
+ * The reference (aagbotemi/zk-cryptography) is pure Rust with no FFI seam of its own; the seam this
+ * library replaces is the Rust API of its `polynomial`, `sumcheck` and `fiat_shamir` crates
+ * (SURVEY.md section 8b).  Every entry point below names the reference item it stands in for
+ * (paths relative to the reference root).  A `build.rs`-built Rust shim (rust/, source only -- there
+ * is no Rust toolchain in this image) binds exactly these symbols; see INTEGRATION.md.
+ *
+ * Conventions
+ *  - A field element is BLS12-381 Fr in ark-ff 0.4.2's in-memory form: 4 x uint64_t little-endian
+ *    limbs, Montgomery form (R = 2^256) -- a `&[Fr]` can be passed as `const uint64_t*` unchanged.
+ *  - Every function returns 0 (ZKSC_OK) or a negative ZKSC_ERR_* code; zksc_last_error() gives text.
+ *    Nothing unwinds across the boundary.  Shape errors that `assert!`/`panic!` in the reference
+ *    (evaluation_form.rs:16-20, composed_multilinear.rs:15) come back as ZKSC_ERR_SHAPE.
+ *  - A context is bound to one CUDA device and one host thread at a time.  There is NO CPU fallback:
+ *    without a usable CUDA device every compute entry point fails with ZKSC_ERR_NO_DEVICE.
+ */
+#ifndef ZKSC_H
+#define ZKSC_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZKSC_OK 0
+#define ZKSC_ERR_NO_DEVICE (-1)
+#define ZKSC_ERR_CUDA (-2)
+#define ZKSC_ERR_SHAPE (-3)
+#define ZKSC_ERR_STATE (-4)
+#define ZKSC_ERR_UNSUPPORTED (-5)
+#define ZKSC_ERR_OOM (-6)
+#define ZKSC_ERR_VERIFY (-7) /* the reference's Err("Verification failed"), multi_composed_sumcheck.rs:170 */
+#define ZKSC_ERR_COMM (-8)
+
+#define ZKSC_MAX_DEGREE 8    /* factors per product */
+#define ZKSC_MAX_PRODUCTS 8
+
+typedef struct zksc_ctx zksc_ctx;
+typedef struct zksc_tables zksc_tables;
+
+/* ---- library / context ----------------------------------------------------------------------- */
+const char* zksc_version(void);
+/* Number of usable CUDA devices (0 when none; never fails). */
+int zksc_device_count(void);
+/* Create a context on CUDA device `device`.  Fails with ZKSC_ERR_NO_DEVICE when there is none. */
+int zksc_ctx_create(int device, zksc_ctx** out);
+int zksc_ctx_destroy(zksc_ctx* ctx);
+/* Last error text of this context (or of the failed zksc_ctx_create when ctx == NULL). */
+const char* zksc_last_error(const zksc_ctx* ctx);
+/* Multi-GPU: one process per GPU.  `unique_id` is the 128-byte ncclUniqueId made by rank 0
+ * (zksc_comm_unique_id) and distributed by the caller (torch.distributed / MPI / files). */
+int zksc_comm_unique_id(uint8_t out_id[128]);
+int zksc_comm_init(zksc_ctx* ctx, int n_ranks, int rank, const uint8_t unique_id[128]);
+int zksc_ctx_rank(const zksc_ctx* ctx, int* rank, int* n_ranks);
+int zksc_ctx_synchronize(zksc_ctx* ctx);
+
+/* ---- device-resident evaluation tables --------------------------------------------------------
+ * A `zksc_tables` is `n_proofs` independent instances of  sum_p prod_k f_{p,k}  : for each proof,
+ * `n_products` products (Vec<ComposedMultilinear<F>>, multi_composed_sumcheck.rs:47-50), product p
+ * having degree[p] factor tables (ComposedMultilinear.polys, composed_multilinear.rs:7-18) of 2^n_vars
+ * entries each (Multilinear.evaluations, evaluation_form.rs:5-9).  Variable 0 is the most significant
+ * index bit.  Tables are ordered proof-major, then product, then factor.
+ *
+ * Sharding (contexts with a communicator of G ranks): every rank holds the entries i with
+ * i mod G == rank of every table, as a table of 2^n_vars / G entries ("local" tables); n_vars is always
+ * the GLOBAL number of variables.                                                                 */
+
+/* Copy host tables to the device.  host_tables[t] -> 2^n_vars elements (full table, also when
+ * sharded: the rank picks out its own entries). */
+int zksc_tables_upload(zksc_ctx* ctx, uint32_t n_vars, uint32_t n_proofs, uint32_t n_products, const uint32_t* degree,
+                       const uint64_t* const* host_tables, zksc_tables** out);
+/* Fill tables on the device with the seeded synthetic generator (entry = f(seed + proof, table, i);
+ * DESIGN.md "Synthetic inputs"); each rank generates only its shard. */
+int zksc_tables_synth(zksc_ctx* ctx, uint32_t n_vars, uint32_t n_proofs, uint32_t n_products, const uint32_t* degree, uint64_t seed,
+                      zksc_tables** out);
+int zksc_tables_free(zksc_tables* t);
+/* Forget all bound challenges: back to the tables as uploaded (the input is never modified). */
+int zksc_tables_reset(zksc_tables* t);
+/* Number of variables still unbound (global). */
+int zksc_tables_vars_left(const zksc_tables* t, uint32_t* out);
+
+/* The round-evaluation idiom  p.partial_evaluation(F::from(i),0).element_wise_product().sum(), i = 0..=d
+ * (multi_composed_sumcheck.rs:81-89, composed_sumcheck.rs:41-49; for degree 1 this is
+ * split_poly_into_two_and_sum_each_part, evaluation_form.rs:68-74), for every proof and product, with
+ * any pending zksc_bind fused into the same pass.
+ * out: n_proofs x (sum_p degree[p]+1) elements; proof-major, product-major, i-minor.  All ranks of a
+ * sharded context receive the full (reduced) values. */
+int zksc_round_evals(zksc_tables* t, uint64_t* out);
+/* Bind variable 0 of every table to a challenge: Multilinear::partial_evaluation(r, 0)
+ * (evaluation_form.rs:123-141, as used at multi_composed_sumcheck.rs:103-105).  challenges: n_proofs
+ * elements.  The fold is deferred and fused into the next zksc_round_evals / zksc_residual. */
+int zksc_bind(zksc_tables* t, const uint64_t* challenges);
+/* Current contents of the tables (after all binds): n_proofs x n_tables x 2^vars_left elements.
+ * On a sharded context the shards are gathered (ncclAllGather) and every rank gets the full tables. */
+int zksc_residual(zksc_tables* t, uint64_t* out);
+/* sum over the hypercube of sum_p prod_k f_{p,k}: MultiComposedSumcheckProver::calculate_poly_sum
+ * (multi_composed_sumcheck.rs:37-45) / Sumcheck::poly_sum (sumcheck.rs:25-27).  out: n_proofs elements.
+ * Must be called on unbound tables. */
+int zksc_poly_sum(zksc_tables* t, uint64_t* out);
+/* Multilinear::to_bytes / composed_poly_to_bytes (evaluation_form.rs:54-62, sumcheck/src/utils.rs:53-59)
+ * of proof `proof`: n_tables x 2^n_vars x 32 canonical big-endian bytes.  Single-rank contexts only. */
+int zksc_tables_to_bytes(zksc_tables* t, uint32_t proof, uint8_t* out);
+
+/* ---- the provers (host round loop + SHA-256 transcript inside the library) ---------------------
+ * Protocol selector: which reference prover's transcript/message format to follow. */
+#define ZKSC_PROTO_SUMCHECK 0       /* Sumcheck::prove            sumcheck/src/sumcheck.rs:29-61  (1 product, degree 1) */
+#define ZKSC_PROTO_COMPOSED 1       /* ComposedSumcheck::prove    composed/composed_sumcheck.rs:32-67 (1 product)       */
+#define ZKSC_PROTO_MULTI_PARTIAL 2  /* MultiComposedSumcheckProver::prove_partial  multi_composed_sumcheck.rs:56-62     */
+#define ZKSC_PROTO_MULTI_FULL 3     /* MultiComposedSumcheckProver::prove (absorbs every table first)  :47-54          */
+
+/* Prove all n_proofs instances (independent transcripts).  `sums`: n_proofs claimed sums (ignored for
+ * ZKSC_PROTO_COMPOSED, which absorbs no sum).  Outputs, per proof and round:
+ *   round_msgs   : n_proofs x n_vars x msg_stride elements -- SUMCHECK: [h0,h1]; COMPOSED: evals at 0..d;
+ *                  MULTI_*: monomials as (coeff, pow) pairs, `round_len` of them (sparse polynomial,
+ *                  sparse_univariate.rs:11-20).  msg_stride = zksc_msg_stride(...) elements.
+ *   round_len    : n_proofs x n_vars -- number of elements (SUMCHECK/COMPOSED) or monomials (MULTI_*)
+ *   challenges   : n_proofs x n_vars elements
+ * The tables end fully bound except for the last challenge; call zksc_tables_reset to reuse them. */
+int zksc_prove(zksc_tables* t, int protocol, const uint64_t* sums, uint64_t* round_msgs, uint32_t* round_len, uint64_t* challenges);
+uint32_t zksc_msg_stride(int protocol, uint32_t n_products, const uint32_t* degree);
+/* Serialise one proof's round messages exactly as the reference feeds them to its transcripts:
+ * ComposedSumcheckProof::to_bytes (multi_composed_sumcheck.rs:24-32) for MULTI_*, vec_to_bytes per
+ * round otherwise.  Returns the byte count in *out_len (out may be NULL to query). */
+int zksc_proof_to_bytes(int protocol, uint32_t n_vars, uint32_t msg_stride, const uint64_t* round_msgs, const uint32_t* round_len,
+                        uint8_t* out, size_t* out_len);
+
+/* MultiComposedSumcheckVerifier::verify_partial (multi_composed_sumcheck.rs:143-181) and the transcript
+ * half of Sumcheck::verify / ComposedSumcheck::verify: replay the transcript, check p(0)+p(1) against
+ * the running claim, return the sub-claim.  Host only (no device work).  ZKSC_ERR_VERIFY on mismatch. */
+int zksc_verify_rounds(int protocol, uint32_t n_vars, uint32_t msg_stride, const uint64_t* sum, const uint64_t* round_msgs,
+                       const uint32_t* round_len, const uint8_t* absorbed_prefix, size_t prefix_len, uint64_t* subclaim_sum,
+                       uint64_t* challenges);
+/* The oracle check of MultiComposedSumcheckVerifier::verify (:135-141) / Sumcheck::verify (:94) /
+ * ComposedSumcheck::verify (:94): sum_p prod_k f_{p,k}(points), by n successive folds on the device.
+ * points: n_proofs x n_vars elements; out: n_proofs elements.  Resets the tables first and after. */
+int zksc_evaluate(zksc_tables* t, const uint64_t* points, uint64_t* out);
+
+/* ---- stand-alone Multilinear operations on caller-owned host vectors (device compute) -----------
+ * Each copies its inputs to the device, runs the CUDA kernel and copies the result back. */
+/* Multilinear::partial_evaluation(r, variable_index)  evaluation_form.rs:123-141; n = 2^k entries in, n/2 out */
+int zksc_ml_partial_evaluation(zksc_ctx* ctx, const uint64_t* evals, uint64_t n, const uint64_t* r, uint32_t variable_index, uint64_t* out);
+/* Multilinear::evaluation(points)  evaluation_form.rs:162-175 */
+int zksc_ml_evaluation(zksc_ctx* ctx, const uint64_t* evals, uint64_t n, const uint64_t* points, uint32_t n_points, uint64_t* out);
+/* add_distinct / mul_distinct  evaluation_form.rs:28-52 : out[i*nb+j] = a[i] (+|*) b[j] */
+int zksc_ml_outer(zksc_ctx* ctx, int mul, const uint64_t* a, uint64_t na, const uint64_t* b, uint64_t nb, uint64_t* out);
+/* impl Add / Sub / Mul<F> for Multilinear (evaluation_form.rs:178-251) and element_wise_product of two
+ * tables (composed_multilinear.rs:105-111): op 0 add, 1 sub, 2 mul, 3 scale by b[0] */
+int zksc_ml_elementwise(zksc_ctx* ctx, int op, const uint64_t* a, const uint64_t* b, uint64_t n, uint64_t* out);
+
+/* ---- host helpers (no device) -------------------------------------------------------------------- */
+/* F::from(u64) in Montgomery form; canonical <-> Montgomery; be32 (sumcheck/src/utils.rs:7-9) */
+void zksc_fr_from_u64(uint64_t x, uint64_t out[4]);
+void zksc_fr_from_canonical(const uint64_t canonical[4], uint64_t out[4]);
+void zksc_fr_to_canonical(const uint64_t mont[4], uint64_t out[4]);
+void zksc_fr_from_canonical_batch(const uint64_t* canonical, uint64_t n, uint64_t* out);
+void zksc_fr_to_canonical_batch(const uint64_t* mont, uint64_t n, uint64_t* out);
+void zksc_fr_to_be_bytes(const uint64_t mont[4], uint8_t out[32]);
+void zksc_fr_from_be_bytes_mod_order(const uint8_t in[32], uint64_t out[4]);
+void zksc_fr_add(const uint64_t a[4], const uint64_t b[4], uint64_t out[4]);
+void zksc_fr_sub(const uint64_t a[4], const uint64_t b[4], uint64_t out[4]);
+void zksc_fr_mul(const uint64_t a[4], const uint64_t b[4], uint64_t out[4]);
+/* FiatShamirTranscript (transcripts/fiat-shamir/src/fiat_shamir.rs:5-40) */
+typedef struct zksc_transcript zksc_transcript;
+zksc_transcript* zksc_transcript_new(void);
+void zksc_transcript_free(zksc_transcript* t);
+void zksc_transcript_commit(zksc_transcript* t, const uint8_t* data, size_t len);
+void zksc_transcript_challenge(zksc_transcript* t, uint8_t out[32]);
+void zksc_transcript_challenge_field(zksc_transcript* t, uint64_t out[4]);
+/* SparseUnivariatePolynomial::interpolation over x = 0..n-1 (sparse_univariate.rs:40-63): returns the
+ * number of monomials written to out_mono as (coeff, pow) pairs (zero coefficients dropped). */
+uint32_t zksc_sparse_interpolate(const uint64_t* ys, uint32_t n, uint64_t* out_mono);
+/* impl Add for SparseUnivariatePolynomial (sparse_univariate.rs:159-203); returns monomial count */
+uint32_t zksc_sparse_add(const uint64_t* a_mono, uint32_t na, const uint64_t* b_mono, uint32_t nb, uint64_t* out_mono);
+/* SparseUnivariatePolynomial::evaluate (sparse_univariate.rs:90-106) */
+void zksc_sparse_evaluate(const uint64_t* mono, uint32_t n, const uint64_t point[4], uint64_t out[4]);
+/* Seeded synthetic table entry (canonical value -> Montgomery), same convention as the device generator */
+void zksc_synth_entry(uint64_t seed, uint64_t table, uint64_t index, uint64_t out[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZKSC_H */

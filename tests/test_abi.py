@@ -1,0 +1,33 @@
+"""The C-ABI library loads and exports every symbol include/zksc.h declares (no compute calls)."""
+import ctypes
+import os
+import re
+
+import zk_cryptography_b200 as zk
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "zksc.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(zksc_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported(built):
+    L = ctypes.CDLL(zk._lib.lib_path())
+    names = declared_symbols()
+    assert len(names) >= 45
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+
+
+def test_python_binding_covers_the_header(built):
+    bound = set(zk.lib()._zksc_signatures)
+    assert set(declared_symbols()) == bound
+
+
+def test_version_and_device_count(built):
+    L = zk.lib()
+    assert b"sm_100a" in L.zksc_version()
+    assert L.zksc_device_count() >= 0

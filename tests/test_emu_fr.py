@@ -1,0 +1,92 @@
+"""The limb / carry-chain algorithms of zk_cryptography_b200/csrc/fr.cuh, compiled for the host with the
+PTX extended-precision instructions emulated (tests/emu/fr_emu.cpp), against Python big integers.  This
+checks on a CPU-only box the exact algorithms the GPU executes (the -m gpu tests check the real thing)."""
+import ctypes
+import os
+import random
+import subprocess
+
+import pytest
+
+R = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+RR = 1 << 256
+RINV = pow(RR, -1, R)
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def emu():
+    out = os.path.join(HERE, "emu", "libfr_emu.so")
+    src = os.path.join(HERE, "emu", "fr_emu.cpp")
+    hdr = os.path.join(HERE, "..", "zk_cryptography_b200", "csrc", "fr.cuh")
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", out, src])
+    return ctypes.CDLL(out)
+
+
+def arr(x, n):
+    return (ctypes.c_uint32 * n)(*[(x >> (32 * i)) & 0xFFFFFFFF for i in range(n)])
+
+
+def val(a):
+    return sum(int(v) << (32 * i) for i, v in enumerate(a))
+
+
+EDGE = [0, 1, R - 1, R - 2, 2**256 - 1, 2**255, (1 << 32) - 1, R + 1, 2**256 - 2**32, 0xFFFFFFFF << 224, R // 2, 2 * R - 1]
+
+
+def rnd(rng, lim):
+    if rng.random() < 0.25:
+        return rng.choice(EDGE) % lim
+    return rng.randrange(lim)
+
+
+def test_constants(emu):
+    one, r2 = (ctypes.c_uint32 * 8)(), (ctypes.c_uint32 * 8)()
+    emu.emu_consts(one, r2)
+    assert val(one) == RR % R and val(r2) == RR * RR % R
+
+
+def test_limb_algorithms(emu):
+    rng = random.Random(11)
+    o8, o9, o16 = (ctypes.c_uint32 * 8)(), (ctypes.c_uint32 * 9)(), (ctypes.c_uint32 * 16)()
+    for it in range(6000):
+        a, b = rnd(rng, 2**256), rnd(rng, 2**256)
+        emu.emu_mul_wide(arr(a, 8), arr(b, 8), o16)
+        assert val(o16) == a * b
+        emu.emu_mont_mul_raw(arr(a, 8), arr(b, 8), o9)
+        v = val(o9)
+        assert v % R == a * b * RINV % R and v < 2**256 + R
+        T = rnd(rng, 2**512)
+        emu.emu_redc(arr(T, 16), o9)
+        v = val(o9)
+        assert v % R == T * RINV % R and v < 2**256 + R
+        a %= R
+        b %= R
+        emu.emu_fr_mul(arr(a, 8), arr(b, 8), o8); assert val(o8) == a * b * RINV % R
+        emu.emu_fr_add(arr(a, 8), arr(b, 8), o8); assert val(o8) == (a + b) % R
+        emu.emu_fr_sub(arr(a, 8), arr(b, 8), o8); assert val(o8) == (a - b) % R
+        x = rnd(rng, 2**256)
+        emu.emu_fr_canon(arr(x, 8), o8); assert val(o8) == x % R
+        c = rnd(rng, R)
+        emu.emu_fr_fold(arr(a, 8), arr(b, 8), arr(c, 8), o8); assert val(o8) == (a + c * (b - a) * RINV) % R
+        A = rnd(rng, 2**288)
+        emu.emu_acc9_reduce(arr(A, 9), o8); assert val(o8) == A % R
+        A = rnd(rng, 2**544)
+        emu.emu_acc17_reduce(arr(A, 17), o8); assert val(o8) == A * RINV % R
+
+
+def test_lazy_accumulation_of_many_products(emu):
+    """sum of unreduced 512-bit products in a 17-limb accumulator, one reduction at the end"""
+    rng = random.Random(12)
+    acc = (ctypes.c_uint32 * 17)()
+    total = 0
+    o16, o8 = (ctypes.c_uint32 * 16)(), (ctypes.c_uint32 * 8)()
+    for _ in range(500):
+        a, b = rnd(rng, 2**256), rnd(rng, 2**256)   # operands need not be canonical
+        emu.emu_mul_wide(arr(a, 8), arr(b, 8), o16)
+        emu.emu_acc17_add(acc, o16)
+        total += a * b
+    assert val(acc) == total
+    emu.emu_acc17_reduce(acc, o8)
+    assert val(o8) == total * RINV % R

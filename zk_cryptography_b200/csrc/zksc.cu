@@ -1,0 +1,977 @@
+// zksc engine: C ABI of include/zksc.h over the sm_100a kernels of kernels.cuh.
+//
+// Data layout in HBM: the reference's own element layout (32-byte Montgomery elements, array of
+// elements per table) -- one LDG.E.256 / STG.E.256 per element per thread, 1 KiB contiguous per warp.
+//   orig : [proof][table][N_local]     the caller's tables, never modified
+//   work : [proof][table][N_local/2]   round >= 1 tables, folded in place from then on
+// Round j >= 1 reads T_{j-1} once and writes T_j once (fold fused with the next round's evaluation).
+#include "../../include/zksc.h"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "host_field.hpp"
+#include "aux_kernels.cuh"
+#include "kernels.cuh"
+
+#if __has_include(<nccl.h>)
+#include <nccl.h>
+#define ZKSC_HAVE_NCCL_H 1
+#else
+#define ZKSC_HAVE_NCCL_H 0
+#endif
+
+using namespace zksc;
+using zksc::host::FrH;
+
+static_assert(kMaxDegree == ZKSC_MAX_DEGREE, "header / kernel limits differ");
+
+static thread_local std::string g_create_error;
+
+// ------------------------------------------------------------------------------------------------
+// NCCL, loaded at run time (single-GPU use must not depend on libnccl being present)
+// ------------------------------------------------------------------------------------------------
+#if ZKSC_HAVE_NCCL_H
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool load(std::string& err) {
+        if (lib) return true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) {
+            lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (lib) break;
+        }
+        if (!lib) { err = std::string("cannot load libnccl: ") + dlerror(); return false; }
+        GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+        CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
+        CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+        AllGather = (decltype(AllGather))dlsym(lib, "ncclAllGather");
+        GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+        if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllGather || !GetErrorString) { err = "libnccl lacks required symbols"; return false; }
+        return true;
+    }
+};
+static NcclApi g_nccl;
+#endif
+
+// ------------------------------------------------------------------------------------------------
+struct zksc_ctx {
+    int device = 0;
+    int sms = 0;
+    cudaStream_t stream = nullptr;
+    Fr* partials = nullptr;
+    size_t partials_cap = 0;
+    unsigned int* counters = nullptr;
+    Fr* results_dev = nullptr;   // [n_ranks][kMaxBatch * kMaxEvals] (allgather target)
+    Fr* results_send = nullptr;  // [kMaxBatch * kMaxEvals]
+    Fr* results_host = nullptr;  // pinned mirror of results_dev
+    size_t results_cap = 0;      // elements per rank slot
+    int occ[kMaxDegree + 1][2];
+    std::string err;
+    int rank = 0, n_ranks = 1;
+#if ZKSC_HAVE_NCCL_H
+    ncclComm_t comm = nullptr;
+#endif
+};
+
+struct zksc_tables {
+    zksc_ctx* ctx;
+    uint32_t n_vars, B, P, Dtot, E;
+    uint32_t deg[ZKSC_MAX_PRODUCTS], koff[ZKSC_MAX_PRODUCTS], eoff[ZKSC_MAX_PRODUCTS];
+    uint64_t n_local0;       // entries per table held by this rank at round 0
+    Fr* orig = nullptr;      // [B][Dtot][n_local0]
+    Fr* work = nullptr;      // [B][Dtot][max(n_local0/2,1)]
+    Fr* tail = nullptr;      // [B][Dtot][n_ranks]   gathered residual (sharded contexts)
+    // state
+    uint32_t vars_left;
+    uint64_t cur_n;          // entries per table in the current buffer
+    int where;               // 0 orig, 1 work, 2 tail
+    bool pending;
+    std::vector<Fr> pending_chal;
+};
+
+#define CK(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess) {                                                                          \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                \
+            return (e_ == cudaErrorMemoryAllocation) ? ZKSC_ERR_OOM : ZKSC_ERR_CUDA;                      \
+        }                                                                                                 \
+    } while (0)
+#define FAIL(code, msg)       \
+    do {                      \
+        ctx->err = (msg);     \
+        return (code);        \
+    } while (0)
+#define TRY(expr)              \
+    do {                       \
+        int rc_ = (expr);      \
+        if (rc_ != ZKSC_OK) return rc_; \
+    } while (0)
+
+static inline FrH to_host(const Fr& f) { FrH h; memcpy(h.v, f.l, 32); return h; }
+static inline FrH load_h(const uint64_t* p) { FrH h; memcpy(h.v, p, 32); return h; }
+static inline void store_h(uint64_t* p, const FrH& h) { memcpy(p, h.v, 32); }
+
+// ------------------------------------------------------------------------------------------------
+// library / context
+// ------------------------------------------------------------------------------------------------
+extern "C" const char* zksc_version(void) { return "zksc 0.1 (sm_100a)"; }
+
+extern "C" int zksc_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+// per-degree launchers live in round_inst.cu (one object per degree, compiled in parallel)
+#define ZKSC_DECL_ROUND(D)                                                                   \
+    void zksc_launch_round_##D(bool fold, dim3 grid, cudaStream_t s, const RoundArgs& a);     \
+    int zksc_occ_round_##D(bool fold);
+ZKSC_DECL_ROUND(1) ZKSC_DECL_ROUND(2) ZKSC_DECL_ROUND(3) ZKSC_DECL_ROUND(4)
+ZKSC_DECL_ROUND(5) ZKSC_DECL_ROUND(6) ZKSC_DECL_ROUND(7) ZKSC_DECL_ROUND(8)
+
+extern "C" int zksc_ctx_create(int device, zksc_ctx** out) {
+    if (!out) return ZKSC_ERR_SHAPE;
+    *out = nullptr;
+    int n = zksc_device_count();
+    if (n <= 0 || device < 0 || device >= n) {
+        g_create_error = "no usable CUDA device (zksc has no CPU fallback)";
+        return ZKSC_ERR_NO_DEVICE;
+    }
+    zksc_ctx* ctx = new zksc_ctx();
+    ctx->device = device;
+    auto fail = [&](cudaError_t e, const char* what) {
+        g_create_error = std::string(what) + ": " + cudaGetErrorString(e);
+        delete ctx;
+        return ZKSC_ERR_CUDA;
+    };
+    cudaError_t e;
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(e, "cudaSetDevice");
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail(e, "cudaGetDeviceProperties");
+    ctx->sms = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
+    if ((e = cudaMalloc(&ctx->counters, (kMaxBatch + 1) * sizeof(unsigned int))) != cudaSuccess) return fail(e, "cudaMalloc");
+    if ((e = cudaMemset(ctx->counters, 0, (kMaxBatch + 1) * sizeof(unsigned int))) != cudaSuccess) return fail(e, "cudaMemset");
+#define ZKSC_OCC(D) ctx->occ[D][0] = zksc_occ_round_##D(false); ctx->occ[D][1] = zksc_occ_round_##D(true);
+    ZKSC_OCC(1) ZKSC_OCC(2) ZKSC_OCC(3) ZKSC_OCC(4) ZKSC_OCC(5) ZKSC_OCC(6) ZKSC_OCC(7) ZKSC_OCC(8)
+    if ((e = cudaGetLastError()) != cudaSuccess) return fail(e, "occupancy query (is this an sm_100a device?)");
+    *out = ctx;
+    return ZKSC_OK;
+}
+
+extern "C" int zksc_ctx_destroy(zksc_ctx* ctx) {
+    if (!ctx) return ZKSC_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+#if ZKSC_HAVE_NCCL_H
+    if (ctx->comm) g_nccl.CommDestroy(ctx->comm);
+#endif
+    cudaFree(ctx->partials);
+    cudaFree(ctx->counters);
+    cudaFree(ctx->results_dev);
+    cudaFree(ctx->results_send);
+    cudaFreeHost(ctx->results_host);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return ZKSC_OK;
+}
+
+extern "C" const char* zksc_last_error(const zksc_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int zksc_ctx_synchronize(zksc_ctx* ctx) {
+    if (!ctx) return ZKSC_ERR_STATE;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return ZKSC_OK;
+}
+
+extern "C" int zksc_ctx_rank(const zksc_ctx* ctx, int* rank, int* n_ranks) {
+    if (!ctx) return ZKSC_ERR_STATE;
+    if (rank) *rank = ctx->rank;
+    if (n_ranks) *n_ranks = ctx->n_ranks;
+    return ZKSC_OK;
+}
+
+extern "C" int zksc_comm_unique_id(uint8_t out_id[128]) {
+#if ZKSC_HAVE_NCCL_H
+    std::string err;
+    if (!g_nccl.load(err)) { g_create_error = err; return ZKSC_ERR_COMM; }
+    ncclUniqueId id;
+    static_assert(sizeof(id) == 128, "ncclUniqueId size");
+    if (g_nccl.GetUniqueId(&id) != ncclSuccess) { g_create_error = "ncclGetUniqueId failed"; return ZKSC_ERR_COMM; }
+    memcpy(out_id, &id, 128);
+    return ZKSC_OK;
+#else
+    g_create_error = "built without nccl.h";
+    return ZKSC_ERR_COMM;
+#endif
+}
+
+extern "C" int zksc_comm_init(zksc_ctx* ctx, int n_ranks, int rank, const uint8_t unique_id[128]) {
+    if (!ctx) return ZKSC_ERR_STATE;
+    if (n_ranks < 1 || (n_ranks & (n_ranks - 1)) || rank < 0 || rank >= n_ranks) FAIL(ZKSC_ERR_SHAPE, "n_ranks must be a power of two and 0 <= rank < n_ranks");
+    if (n_ranks == 1) { ctx->rank = 0; ctx->n_ranks = 1; return ZKSC_OK; }
+#if ZKSC_HAVE_NCCL_H
+    if (!g_nccl.load(ctx->err)) return ZKSC_ERR_COMM;
+    CK(cudaSetDevice(ctx->device));
+    ncclUniqueId id;
+    memcpy(&id, unique_id, 128);
+    ncclResult_t r = g_nccl.CommInitRank(&ctx->comm, n_ranks, id, rank);
+    if (r != ncclSuccess) FAIL(ZKSC_ERR_COMM, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r));
+    ctx->rank = rank;
+    ctx->n_ranks = n_ranks;
+    // result buffers are sized per rank count: drop them so the next use re-allocates
+    cudaFree(ctx->results_dev); cudaFree(ctx->results_send); cudaFreeHost(ctx->results_host);
+    ctx->results_dev = nullptr; ctx->results_send = nullptr; ctx->results_host = nullptr; ctx->results_cap = 0;
+    return ZKSC_OK;
+#else
+    FAIL(ZKSC_ERR_COMM, "built without nccl.h");
+#endif
+}
+
+static int ensure_results(zksc_ctx* ctx, size_t elems) {
+    if (elems <= ctx->results_cap) return ZKSC_OK;
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->results_dev); cudaFree(ctx->results_send); cudaFreeHost(ctx->results_host);
+    ctx->results_dev = nullptr; ctx->results_send = nullptr; ctx->results_host = nullptr; ctx->results_cap = 0;
+    CK(cudaMalloc(&ctx->results_dev, elems * ctx->n_ranks * sizeof(Fr)));
+    CK(cudaMalloc(&ctx->results_send, elems * sizeof(Fr)));
+    CK(cudaHostAlloc(&ctx->results_host, elems * ctx->n_ranks * sizeof(Fr), cudaHostAllocDefault));
+    ctx->results_cap = elems;
+    return ZKSC_OK;
+}
+static int ensure_partials(zksc_ctx* ctx, size_t elems) {
+    if (elems <= ctx->partials_cap) return ZKSC_OK;
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->partials);
+    ctx->partials = nullptr; ctx->partials_cap = 0;
+    CK(cudaMalloc(&ctx->partials, elems * sizeof(Fr)));
+    ctx->partials_cap = elems;
+    return ZKSC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// tables
+// ------------------------------------------------------------------------------------------------
+static int tables_alloc(zksc_ctx* ctx, uint32_t n_vars, uint32_t B, uint32_t P, const uint32_t* degree, zksc_tables** out) {
+    if (!ctx || !out || !degree) return ZKSC_ERR_SHAPE;
+    *out = nullptr;
+    if (B < 1 || P < 1 || P > ZKSC_MAX_PRODUCTS) FAIL(ZKSC_ERR_SHAPE, "need 1 <= n_products <= ZKSC_MAX_PRODUCTS and n_proofs >= 1");
+    if (n_vars > 40) FAIL(ZKSC_ERR_SHAPE, "n_vars too large");
+    int lg = 0;
+    while ((1 << lg) < ctx->n_ranks) lg++;
+    if ((int)n_vars < lg) FAIL(ZKSC_ERR_SHAPE, "tables have fewer entries than there are ranks");
+    zksc_tables* t = new zksc_tables();
+    t->ctx = ctx; t->n_vars = n_vars; t->B = B; t->P = P; t->Dtot = 0; t->E = 0;
+    for (uint32_t p = 0; p < P; p++) {
+        if (degree[p] < 1 || degree[p] > ZKSC_MAX_DEGREE) { delete t; FAIL(ZKSC_ERR_UNSUPPORTED, "product degree must be in 1..ZKSC_MAX_DEGREE"); }
+        t->deg[p] = degree[p]; t->koff[p] = t->Dtot; t->eoff[p] = t->E;
+        t->Dtot += degree[p]; t->E += degree[p] + 1;
+    }
+    t->n_local0 = (1ull << n_vars) / ctx->n_ranks;
+    CK(cudaSetDevice(ctx->device));
+    size_t n_orig = (size_t)B * t->Dtot * t->n_local0;
+    size_t n_work = (size_t)B * t->Dtot * (t->n_local0 > 1 ? t->n_local0 / 2 : 1);
+    cudaError_t e = cudaMalloc(&t->orig, n_orig * sizeof(Fr));
+    if (e == cudaSuccess) e = cudaMalloc(&t->work, n_work * sizeof(Fr));
+    if (e == cudaSuccess && ctx->n_ranks > 1) e = cudaMalloc(&t->tail, (size_t)B * t->Dtot * ctx->n_ranks * sizeof(Fr));
+    if (e != cudaSuccess) {
+        cudaFree(t->orig); cudaFree(t->work); cudaFree(t->tail);
+        delete t;
+        ctx->err = std::string("cudaMalloc(tables): ") + cudaGetErrorString(e);
+        cudaGetLastError();
+        return ZKSC_ERR_OOM;
+    }
+    {
+        size_t need = (size_t)B * t->E, need2 = (size_t)B * t->Dtot;
+        int rc = ensure_results(ctx, need > need2 ? need : need2);
+        if (rc != ZKSC_OK) { cudaFree(t->orig); cudaFree(t->work); cudaFree(t->tail); delete t; return rc; }
+    }
+    zksc_tables_reset(t);
+    *out = t;
+    return ZKSC_OK;
+}
+
+extern "C" int zksc_tables_reset(zksc_tables* t) {
+    if (!t) return ZKSC_ERR_STATE;
+    t->vars_left = t->n_vars;
+    t->cur_n = t->n_local0;
+    t->where = 0;
+    t->pending = false;
+    t->pending_chal.clear();
+    return ZKSC_OK;
+}
+
+extern "C" int zksc_tables_free(zksc_tables* t) {
+    if (!t) return ZKSC_OK;
+    cudaSetDevice(t->ctx->device);
+    cudaStreamSynchronize(t->ctx->stream);
+    cudaFree(t->orig); cudaFree(t->work); cudaFree(t->tail);
+    delete t;
+    return ZKSC_OK;
+}
+
+extern "C" int zksc_tables_vars_left(const zksc_tables* t, uint32_t* out) {
+    if (!t || !out) return ZKSC_ERR_STATE;
+    *out = t->vars_left;
+    return ZKSC_OK;
+}
+
+__global__ void __launch_bounds__(256) pick_shard_kernel(const Fr* full, Fr* out, unsigned long long n_local, unsigned long long G, unsigned long long g) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_local; i += stride) st256(out + i, ld256(full + i * G + g));
+}
+
+static inline int grid_for(const zksc_ctx* ctx, unsigned long long n, int threads, int per_sm) {
+    unsigned long long blocks = (n + threads - 1) / threads;
+    unsigned long long cap = (unsigned long long)ctx->sms * per_sm;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+extern "C" int zksc_tables_upload(zksc_ctx* ctx, uint32_t n_vars, uint32_t n_proofs, uint32_t n_products, const uint32_t* degree,
+                                  const uint64_t* const* host_tables, zksc_tables** out) {
+    if (!ctx) return ZKSC_ERR_STATE;
+    if (!host_tables) FAIL(ZKSC_ERR_SHAPE, "host_tables is NULL");
+    zksc_tables* t = nullptr;
+    TRY(tables_alloc(ctx, n_vars, n_proofs, n_products, degree, &t));
+    const uint64_t N = 1ull << n_vars;
+    const size_t n_tabs = (size_t)t->B * t->Dtot;
+    if (ctx->n_ranks == 1) {
+        for (size_t i = 0; i < n_tabs; i++) {
+            cudaError_t e = cudaMemcpyAsync(t->orig + i * N, host_tables[i], N * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream);
+            if (e != cudaSuccess) { zksc_tables_free(t); ctx->err = std::string("H2D: ") + cudaGetErrorString(e); return ZKSC_ERR_CUDA; }
+        }
+    } else {
+        Fr* stage = nullptr;
+        cudaError_t e = cudaMalloc(&stage, N * sizeof(Fr));
+        if (e != cudaSuccess) { zksc_tables_free(t); ctx->err = "cudaMalloc(upload staging)"; cudaGetLastError(); return ZKSC_ERR_OOM; }
+        for (size_t i = 0; i < n_tabs && e == cudaSuccess; i++) {
+            e = cudaMemcpyAsync(stage, host_tables[i], N * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream);
+            if (e != cudaSuccess) break;
+            pick_shard_kernel<<<grid_for(ctx, t->n_local0, 256, 8), 256, 0, ctx->stream>>>(stage, t->orig + i * t->n_local0, t->n_local0, ctx->n_ranks, ctx->rank);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        cudaFree(stage);
+        if (e != cudaSuccess) { zksc_tables_free(t); ctx->err = std::string("sharded upload: ") + cudaGetErrorString(e); return ZKSC_ERR_CUDA; }
+    }
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);  // host buffers are only borrowed for the call
+    if (e != cudaSuccess) { zksc_tables_free(t); ctx->err = std::string("upload: ") + cudaGetErrorString(e); return ZKSC_ERR_CUDA; }
+    *out = t;
+    return ZKSC_OK;
+}
+
+extern "C" int zksc_tables_synth(zksc_ctx* ctx, uint32_t n_vars, uint32_t n_proofs, uint32_t n_products, const uint32_t* degree, uint64_t seed,
+                                 zksc_tables** out) {
+    if (!ctx) return ZKSC_ERR_STATE;
+    zksc_tables* t = nullptr;
+    TRY(tables_alloc(ctx, n_vars, n_proofs, n_products, degree, &t));
+    for (uint32_t b = 0; b < t->B; b++)
+        for (uint32_t k = 0; k < t->Dtot; k++) {
+            synth_kernel<<<grid_for(ctx, t->n_local0, 256, 8), 256, 0, ctx->stream>>>(t->orig + ((size_t)b * t->Dtot + k) * t->n_local0, t->n_local0,
+                                                                                        seed + b, k, ctx->rank, ctx->n_ranks);
+        }
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { zksc_tables_free(t); ctx->err = std::string("synth: ") + cudaGetErrorString(e); return ZKSC_ERR_CUDA; }
+    *out = t;
+    return ZKSC_OK;
+}
+
+// current buffer geometry
+struct Geo {
+    Fr* base;
+    unsigned long long tab_stride, proof_stride;
+};
+static Geo geo_of(const zksc_tables* t, int where) {
+    Geo g;
+    if (where == 0) { g.base = t->orig; g.tab_stride = t->n_local0; }
+    else if (where == 1) { g.base = t->work; g.tab_stride = t->n_local0 > 1 ? t->n_local0 / 2 : 1; }
+    else { g.base = t->tail; g.tab_stride = t->ctx->n_ranks; }
+    g.proof_stride = g.tab_stride * t->Dtot;
+    return g;
+}
+
+// Apply the pending challenge with the stand-alone fold kernel (no evaluation).
+static int flush_pending(zksc_tables* t) {
+    zksc_ctx* ctx = t->ctx;
+    if (!t->pending) return ZKSC_OK;
+    if (t->cur_n < 2) FAIL(ZKSC_ERR_STATE, "no variable left to bind");
+    Geo gi = geo_of(t, t->where);
+    int to = (t->where == 0) ? 1 : t->where;
+    Geo go = geo_of(t, to);
+    for (uint32_t b0 = 0; b0 < t->B; b0 += kMaxBatch) {
+        uint32_t nb = t->B - b0 < (uint32_t)kMaxBatch ? t->B - b0 : kMaxBatch;
+        FoldArgs a;
+        a.in = gi.base + (size_t)b0 * gi.proof_stride;
+        a.out = go.base + (size_t)b0 * go.proof_stride;
+        a.in_tab_stride = gi.tab_stride; a.in_proof_stride = gi.proof_stride;
+        a.out_tab_stride = go.tab_stride; a.out_proof_stride = go.proof_stride;
+        a.n_out = t->cur_n / 2; a.s = t->cur_n / 2; a.n_tabs = t->Dtot;
+        for (uint32_t b = 0; b < nb; b++) a.chal[b] = t->pending_chal[b0 + b];
+        dim3 grid(grid_for(ctx, a.n_out, 256, 8), nb);
+        fold_kernel<<<grid, 256, 0, ctx->stream>>>(a);
+    }
+    CK(cudaGetLastError());
+    t->where = to;
+    t->cur_n /= 2;
+    t->pending = false;
+    return ZKSC_OK;
+}
+
+#if ZKSC_HAVE_NCCL_H
+#define NCCLCK(call)                                                                       \
+    do {                                                                                   \
+        ncclResult_t r_ = (call);                                                          \
+        if (r_ != ncclSuccess) FAIL(ZKSC_ERR_COMM, std::string(#call) + ": " + g_nccl.GetErrorString(r_)); \
+    } while (0)
+#endif
+
+__global__ void tail_scatter_kernel(const Fr* gathered, Fr* tail, unsigned int n_tabs_total, unsigned int G) {
+    // gathered: [rank][tab] -> tail: [tab][rank]
+    unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_tabs_total * G) {
+        unsigned int tab = i / G, g = i % G;
+        st256(tail + i, ld256(gathered + (size_t)g * n_tabs_total + tab));
+    }
+}
+__global__ void tail_collect_kernel(const Fr* base, unsigned long long tab_stride, Fr* out, unsigned int n_tabs_total) {
+    unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_tabs_total) st256(out + i, ld256(base + (size_t)i * tab_stride));
+}
+
+// Sharded contexts: once every rank is down to one entry per table, gather the G entries of every
+// table on every rank (entry index == rank) and continue replicated.
+static int gather_tail(zksc_tables* t) {
+    zksc_ctx* ctx = t->ctx;
+#if ZKSC_HAVE_NCCL_H
+    TRY(flush_pending(t));
+    if (t->cur_n != 1) FAIL(ZKSC_ERR_STATE, "gather_tail: local tables not exhausted");
+    const unsigned int nt = t->B * t->Dtot;
+    TRY(ensure_results(ctx, nt));
+    Geo g = geo_of(t, t->where);
+    tail_collect_kernel<<<(nt + 127) / 128, 128, 0, ctx->stream>>>(g.base, g.tab_stride, ctx->results_send, nt);
+    CK(cudaGetLastError());
+    NCCLCK(g_nccl.AllGather(ctx->results_send, ctx->results_dev, (size_t)nt * sizeof(Fr), ncclUint8, ctx->comm, ctx->stream));
+    tail_scatter_kernel<<<(nt * ctx->n_ranks + 127) / 128, 128, 0, ctx->stream>>>(ctx->results_dev, t->tail, nt, ctx->n_ranks);
+    CK(cudaGetLastError());
+    t->where = 2;
+    t->cur_n = ctx->n_ranks;
+    return ZKSC_OK;
+#else
+    FAIL(ZKSC_ERR_COMM, "built without nccl.h");
+#endif
+}
+
+// One round: evaluations of every product of every proof at 0..npts_cap-1 (capped by degree+1).
+static int round_evals_impl(zksc_tables* t, uint64_t* out, uint32_t npts_cap) {
+    zksc_ctx* ctx = t->ctx;
+    CK(cudaSetDevice(ctx->device));
+    if (t->vars_left == 0) FAIL(ZKSC_ERR_STATE, "all variables are bound");
+    const bool sharded_phase = (ctx->n_ranks > 1 && t->where != 2);
+    if (sharded_phase) {
+        uint64_t n_after = t->pending ? t->cur_n / 2 : t->cur_n;
+        if (n_after == 1) TRY(gather_tail(t));
+    }
+    const bool reduce_ranks = (ctx->n_ranks > 1 && t->where != 2);
+    uint64_t n_eval = t->pending ? t->cur_n / 2 : t->cur_n;  // table size of the round being evaluated
+    if (n_eval < 2) FAIL(ZKSC_ERR_STATE, "no variable left to evaluate");
+    const bool fold = t->pending;
+    Geo gi = geo_of(t, t->where);
+    int to = fold ? ((t->where == 0) ? 1 : t->where) : t->where;
+    Geo go = geo_of(t, to);
+    const unsigned long long half = n_eval / 2;
+    Fr* res = reduce_ranks ? ctx->results_send : ctx->results_dev;
+
+    for (uint32_t b0 = 0; b0 < t->B; b0 += kMaxBatch) {
+        uint32_t nb = t->B - b0 < (uint32_t)kMaxBatch ? t->B - b0 : kMaxBatch;
+        for (uint32_t p = 0; p < t->P; p++) {
+            const int D = t->deg[p];
+            int gx = grid_for(ctx, half, kThreads, ctx->occ[D][fold ? 1 : 0]);
+            TRY(ensure_partials(ctx, (size_t)nb * gx * (D + 1)));
+            RoundArgs a;
+            a.in = gi.base + (size_t)b0 * gi.proof_stride + (size_t)t->koff[p] * gi.tab_stride;
+            a.out = go.base + (size_t)b0 * go.proof_stride + (size_t)t->koff[p] * go.tab_stride;
+            a.in_tab_stride = gi.tab_stride; a.in_proof_stride = gi.proof_stride;
+            a.out_tab_stride = go.tab_stride; a.out_proof_stride = go.proof_stride;
+            a.half = half;
+            a.partials = ctx->partials; a.counters = ctx->counters;
+            a.result = res + (size_t)b0 * t->E + t->eoff[p];
+            a.res_stride = t->E;
+            a.npts = (uint32_t)(D + 1) < npts_cap ? (D + 1) : npts_cap;
+            a.flag = nullptr; a.flag_value = 0;
+            if (fold) for (uint32_t b = 0; b < nb; b++) a.chal[b] = t->pending_chal[b0 + b];
+            dim3 grid(gx, nb);
+            switch (D) {
+                case 1: zksc_launch_round_1(fold, grid, ctx->stream, a); break;
+                case 2: zksc_launch_round_2(fold, grid, ctx->stream, a); break;
+                case 3: zksc_launch_round_3(fold, grid, ctx->stream, a); break;
+                case 4: zksc_launch_round_4(fold, grid, ctx->stream, a); break;
+                case 5: zksc_launch_round_5(fold, grid, ctx->stream, a); break;
+                case 6: zksc_launch_round_6(fold, grid, ctx->stream, a); break;
+                case 7: zksc_launch_round_7(fold, grid, ctx->stream, a); break;
+                case 8: zksc_launch_round_8(fold, grid, ctx->stream, a); break;
+                default: FAIL(ZKSC_ERR_UNSUPPORTED, "degree");
+            }
+            CK(cudaGetLastError());
+        }
+    }
+    if (fold) { t->where = to; t->cur_n /= 2; t->pending = false; }
+
+    const size_t n_res = (size_t)t->B * t->E;
+    if (!reduce_ranks) {
+        CK(cudaMemcpyAsync(ctx->results_host, ctx->results_dev, n_res * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        memcpy(out, ctx->results_host, n_res * sizeof(Fr));
+    } else {
+#if ZKSC_HAVE_NCCL_H
+        // the only per-round exchange: every rank's partial evaluations (n_res elements of 32 bytes).
+        // NCCL has no modular sum, so gather and add mod r on the host, identically on every rank.
+        NCCLCK(g_nccl.AllGather(ctx->results_send, ctx->results_dev, n_res * sizeof(Fr), ncclUint8, ctx->comm, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->results_host, ctx->results_dev, n_res * ctx->n_ranks * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (size_t i = 0; i < n_res; i++) {
+            FrH acc = to_host(ctx->results_host[i]);
+            for (int g = 1; g < ctx->n_ranks; g++) acc = host::add(acc, to_host(ctx->results_host[(size_t)g * n_res + i]));
+            store_h(out + 4 * i, acc);
+        }
+#endif
+    }
+    return ZKSC_OK;
+}
+
+extern "C" int zksc_round_evals(zksc_tables* t, uint64_t* out) {
+    if (!t || !out) return ZKSC_ERR_STATE;
+    return round_evals_impl(t, out, ZKSC_MAX_DEGREE + 1);
+}
+
+extern "C" int zksc_bind(zksc_tables* t, const uint64_t* challenges) {
+    if (!t || !challenges) return ZKSC_ERR_STATE;
+    zksc_ctx* ctx = t->ctx;
+    CK(cudaSetDevice(ctx->device));
+    if (t->vars_left == 0) FAIL(ZKSC_ERR_STATE, "all variables are bound");
+    if (t->pending) {
+        if (ctx->n_ranks > 1 && t->where != 2 && t->cur_n / 2 == 1) TRY(gather_tail(t));
+        else TRY(flush_pending(t));
+    }
+    if (ctx->n_ranks > 1 && t->where != 2 && t->cur_n == 1) TRY(gather_tail(t));
+    t->pending_chal.resize(t->B);
+    for (uint32_t b = 0; b < t->B; b++) memcpy(t->pending_chal[b].l, challenges + 4 * b, 32);
+    t->pending = true;
+    t->vars_left--;
+    return ZKSC_OK;
+}
+
+extern "C" int zksc_residual(zksc_tables* t, uint64_t* out) {
+    if (!t || !out) return ZKSC_ERR_STATE;
+    zksc_ctx* ctx = t->ctx;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->n_ranks > 1 && t->where != 2) {
+        uint64_t n_after = t->pending ? t->cur_n / 2 : t->cur_n;
+        if (n_after != 1) FAIL(ZKSC_ERR_UNSUPPORTED, "sharded residual is only available once each rank holds one entry per table");
+        TRY(gather_tail(t));
+    }
+    TRY(flush_pending(t));
+    Geo g = geo_of(t, t->where);
+    const size_t nt = (size_t)t->B * t->Dtot;
+    for (size_t i = 0; i < nt; i++)
+        CK(cudaMemcpyAsync(out + 4 * i * t->cur_n, g.base + i * g.tab_stride, t->cur_n * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return ZKSC_OK;
+}
+
+extern "C" int zksc_poly_sum(zksc_tables* t, uint64_t* out) {
+    if (!t || !out) return ZKSC_ERR_STATE;
+    zksc_ctx* ctx = t->ctx;
+    if (t->vars_left != t->n_vars || t->pending) FAIL(ZKSC_ERR_STATE, "zksc_poly_sum needs unbound tables");
+    std::vector<uint64_t> ev((size_t)t->B * t->E * 4);
+    if (t->n_vars == 0) {
+        // a single entry per table: the sum is the product itself
+        std::vector<uint64_t> resid((size_t)t->B * t->Dtot * 4);
+        TRY(zksc_residual(t, resid.data()));
+        for (uint32_t b = 0; b < t->B; b++) {
+            FrH s = host::kZero;
+            for (uint32_t p = 0; p < t->P; p++) {
+                FrH prod = host::kOne;
+                for (uint32_t k = 0; k < t->deg[p]; k++) prod = host::mul(prod, load_h(&resid[((size_t)b * t->Dtot + t->koff[p] + k) * 4]));
+                s = host::add(s, prod);
+            }
+            store_h(out + 4 * b, s);
+        }
+        return ZKSC_OK;
+    }
+    TRY(round_evals_impl(t, ev.data(), 2));
+    for (uint32_t b = 0; b < t->B; b++) {
+        FrH s = host::kZero;
+        for (uint32_t p = 0; p < t->P; p++) {
+            const uint64_t* e = &ev[((size_t)b * t->E + t->eoff[p]) * 4];
+            s = host::add(s, host::add(load_h(e), load_h(e + 4)));
+        }
+        store_h(out + 4 * b, s);
+    }
+    zksc_tables_reset(t);
+    return ZKSC_OK;
+}
+
+extern "C" int zksc_tables_to_bytes(zksc_tables* t, uint32_t proof, uint8_t* out) {
+    if (!t || !out) return ZKSC_ERR_STATE;
+    zksc_ctx* ctx = t->ctx;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->n_ranks != 1) FAIL(ZKSC_ERR_UNSUPPORTED, "zksc_tables_to_bytes: single-rank contexts only");
+    if (proof >= t->B) FAIL(ZKSC_ERR_SHAPE, "proof index");
+    const uint64_t N = t->n_local0;
+    const uint64_t chunk = N < (1ull << 22) ? N : (1ull << 22);
+    Fr* tmp = nullptr;
+    CK(cudaMalloc(&tmp, chunk * sizeof(Fr)));
+    for (uint32_t k = 0; k < t->Dtot; k++) {
+        const Fr* src = t->orig + ((size_t)proof * t->Dtot + k) * N;
+        for (uint64_t off = 0; off < N; off += chunk) {
+            to_bytes_kernel<<<grid_for(ctx, chunk, 256, 8), 256, 0, ctx->stream>>>(src + off, tmp, chunk);
+            cudaError_t e = cudaMemcpyAsync(out + ((size_t)k * N + off) * 32, tmp, chunk * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+            if (e != cudaSuccess) { cudaFree(tmp); ctx->err = std::string("to_bytes: ") + cudaGetErrorString(e); return ZKSC_ERR_CUDA; }
+        }
+    }
+    cudaFree(tmp);
+    return ZKSC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// provers: host round loop + transcript (sumcheck.rs:29-61, composed_sumcheck.rs:32-67,
+// multi_composed_sumcheck.rs:47-120)
+// ------------------------------------------------------------------------------------------------
+extern "C" uint32_t zksc_msg_stride(int protocol, uint32_t n_products, const uint32_t* degree) {
+    uint32_t dmax = 0;
+    for (uint32_t p = 0; p < n_products; p++) dmax = degree[p] > dmax ? degree[p] : dmax;
+    if (protocol == ZKSC_PROTO_SUMCHECK) return 2;
+    if (protocol == ZKSC_PROTO_COMPOSED) return dmax + 1;
+    return 2 * (dmax + 1);
+}
+
+extern "C" int zksc_prove(zksc_tables* t, int protocol, const uint64_t* sums, uint64_t* round_msgs, uint32_t* round_len, uint64_t* challenges) {
+    if (!t || !round_msgs || !round_len || !challenges) return ZKSC_ERR_STATE;
+    zksc_ctx* ctx = t->ctx;
+    if (protocol < ZKSC_PROTO_SUMCHECK || protocol > ZKSC_PROTO_MULTI_FULL) FAIL(ZKSC_ERR_SHAPE, "unknown protocol");
+    if (protocol == ZKSC_PROTO_SUMCHECK && (t->P != 1 || t->deg[0] != 1)) FAIL(ZKSC_ERR_SHAPE, "Sumcheck::prove takes one multilinear table");
+    if (protocol == ZKSC_PROTO_COMPOSED && t->P != 1) FAIL(ZKSC_ERR_SHAPE, "ComposedSumcheck::prove takes one product");
+    if (protocol != ZKSC_PROTO_COMPOSED && !sums) FAIL(ZKSC_ERR_SHAPE, "sums is NULL");
+    if (t->vars_left != t->n_vars || t->pending) FAIL(ZKSC_ERR_STATE, "tables are partially bound; call zksc_tables_reset first");
+    const uint32_t stride = zksc_msg_stride(protocol, t->P, t->deg);
+    const uint32_t B = t->B, n = t->n_vars;
+    std::vector<host::FiatShamirTranscript> tr(B);
+    if (protocol == ZKSC_PROTO_MULTI_FULL) {
+        // transcript.commit(&composed_poly_to_bytes(&poly))  multi_composed_sumcheck.rs:52
+        if (ctx->n_ranks != 1) FAIL(ZKSC_ERR_UNSUPPORTED, "MULTI_FULL (absorbs every table entry) is single-rank only; use MULTI_PARTIAL");
+        std::vector<uint8_t> bytes((size_t)t->Dtot * t->n_local0 * 32);
+        for (uint32_t b = 0; b < B; b++) {
+            TRY(zksc_tables_to_bytes(t, b, bytes.data()));
+            tr[b].commit(bytes);
+        }
+    }
+    if (protocol != ZKSC_PROTO_COMPOSED)
+        for (uint32_t b = 0; b < B; b++) tr[b].commit_field(load_h(sums + 4 * b));  // :70 / sumcheck.rs:34-35
+
+    std::vector<uint64_t> ev((size_t)B * t->E * 4), chal((size_t)B * 4);
+    std::vector<uint8_t> bytes;
+    memset(round_msgs, 0, (size_t)B * n * stride * 32);
+    for (uint32_t round = 0; round < n; round++) {
+        TRY(round_evals_impl(t, ev.data(), ZKSC_MAX_DEGREE + 1));
+        for (uint32_t b = 0; b < B; b++) {
+            uint64_t* msg = round_msgs + ((size_t)b * n + round) * stride * 4;
+            uint32_t* len = round_len + (size_t)b * n + round;
+            const uint64_t* e = &ev[(size_t)b * t->E * 4];
+            bytes.clear();
+            if (protocol == ZKSC_PROTO_SUMCHECK || protocol == ZKSC_PROTO_COMPOSED) {
+                const uint32_t cnt = t->deg[0] + 1;
+                memcpy(msg, e, (size_t)cnt * 32);
+                *len = cnt;
+                for (uint32_t i = 0; i < cnt; i++) {
+                    uint8_t be[32];
+                    host::to_be_bytes(load_h(e + 4 * i), be);
+                    bytes.insert(bytes.end(), be, be + 32);
+                }
+            } else {
+                host::SparseUnivariatePolynomial round_poly = host::SparseUnivariatePolynomial::zero();  // :77
+                for (uint32_t p = 0; p < t->P; p++) {
+                    std::vector<FrH> ys;
+                    for (uint32_t i = 0; i <= t->deg[p]; i++) ys.push_back(load_h(e + 4 * (t->eoff[p] + i)));
+                    round_poly = round_poly + host::SparseUnivariatePolynomial::interpolate_evals(ys);  // :91-94
+                }
+                *len = (uint32_t)round_poly.monomial.size();
+                for (size_t m = 0; m < round_poly.monomial.size(); m++) {
+                    store_h(msg + 8 * m, round_poly.monomial[m].coeff);
+                    store_h(msg + 8 * m + 4, round_poly.monomial[m].pow);
+                }
+                round_poly.to_bytes(bytes);
+            }
+            tr[b].commit(bytes);                                      // :97
+            FrH r = tr[b].evaluate_challenge_into_field();            // :99
+            store_h(&chal[4 * b], r);
+            store_h(challenges + ((size_t)b * n + round) * 4, r);
+        }
+        TRY(zksc_bind(t, chal.data()));                               // :103-105 (deferred, fused)
+    }
+    return ZKSC_OK;
+}
+
+extern "C" int zksc_proof_to_bytes(int protocol, uint32_t n_vars, uint32_t msg_stride, const uint64_t* round_msgs, const uint32_t* round_len,
+                                   uint8_t* out, size_t* out_len) {
+    if (!round_msgs || !round_len || !out_len) return ZKSC_ERR_SHAPE;
+    const uint32_t per = (protocol == ZKSC_PROTO_MULTI_PARTIAL || protocol == ZKSC_PROTO_MULTI_FULL) ? 2 : 1;
+    size_t n = 0;
+    for (uint32_t r = 0; r < n_vars; r++) {
+        for (uint32_t i = 0; i < round_len[r] * per; i++) {
+            if (out) host::to_be_bytes(load_h(round_msgs + ((size_t)r * msg_stride + i) * 4), out + n);
+            n += 32;
+        }
+    }
+    *out_len = n;
+    return ZKSC_OK;
+}
+
+extern "C" int zksc_verify_rounds(int protocol, uint32_t n_vars, uint32_t msg_stride, const uint64_t* sum, const uint64_t* round_msgs,
+                                  const uint32_t* round_len, const uint8_t* absorbed_prefix, size_t prefix_len, uint64_t* subclaim_sum,
+                                  uint64_t* challenges) {
+    if (!round_msgs || !round_len || !sum || !subclaim_sum || !challenges) return ZKSC_ERR_SHAPE;
+    host::FiatShamirTranscript tr;
+    if (absorbed_prefix && prefix_len) tr.commit(absorbed_prefix, prefix_len);
+    FrH claimed = load_h(sum);
+    if (protocol != ZKSC_PROTO_COMPOSED) tr.commit_field(claimed);
+    std::vector<uint8_t> bytes;
+    for (uint32_t r = 0; r < n_vars; r++) {
+        const uint64_t* msg = round_msgs + (size_t)r * msg_stride * 4;
+        bytes.clear();
+        FrH p0, p1, c;
+        if (protocol == ZKSC_PROTO_SUMCHECK) {
+            // sumcheck.rs:73-92: check, then commit, then challenge
+            if (round_len[r] != 2) return ZKSC_ERR_SHAPE;
+            FrH h0 = load_h(msg), h1 = load_h(msg + 4);
+            if (host::add(h0, h1) != claimed) return ZKSC_ERR_VERIFY;
+            uint8_t be[64];
+            host::to_be_bytes(h0, be); host::to_be_bytes(h1, be + 32);
+            tr.commit(be, 64);
+            c = tr.evaluate_challenge_into_field();
+            claimed = host::add(host::mul(c, h1), host::mul(host::sub(host::kOne, c), h0));  // uni_poly.evaluation(&[c])
+        } else {
+            host::SparseUnivariatePolynomial poly;
+            if (protocol == ZKSC_PROTO_COMPOSED) {
+                std::vector<FrH> ys;
+                for (uint32_t i = 0; i < round_len[r]; i++) {
+                    ys.push_back(load_h(msg + 4 * i));
+                    uint8_t be[32];
+                    host::to_be_bytes(ys.back(), be);
+                    bytes.insert(bytes.end(), be, be + 32);
+                }
+                poly = host::SparseUnivariatePolynomial::interpolate_evals(ys);  // composed_sumcheck.rs:81-83
+            } else {
+                for (uint32_t i = 0; i < round_len[r]; i++) poly.monomial.push_back({load_h(msg + 8 * i), load_h(msg + 8 * i + 4)});
+                poly.to_bytes(bytes);
+            }
+            tr.commit(bytes);
+            c = tr.evaluate_challenge_into_field();
+            p0 = poly.evaluate(host::kZero);
+            p1 = poly.evaluate(host::kOne);
+            if (host::add(p0, p1) != claimed) return ZKSC_ERR_VERIFY;
+            claimed = poly.evaluate(c);
+        }
+        store_h(challenges + 4 * r, c);
+    }
+    store_h(subclaim_sum, claimed);
+    return ZKSC_OK;
+}
+
+extern "C" int zksc_evaluate(zksc_tables* t, const uint64_t* points, uint64_t* out) {
+    if (!t || !points || !out) return ZKSC_ERR_STATE;
+    zksc_tables_reset(t);
+    std::vector<uint64_t> chal((size_t)t->B * 4);
+    for (uint32_t j = 0; j < t->n_vars; j++) {
+        for (uint32_t b = 0; b < t->B; b++) memcpy(&chal[4 * b], points + ((size_t)b * t->n_vars + j) * 4, 32);
+        TRY(zksc_bind(t, chal.data()));
+    }
+    std::vector<uint64_t> resid((size_t)t->B * t->Dtot * 4);
+    TRY(zksc_residual(t, resid.data()));
+    for (uint32_t b = 0; b < t->B; b++) {
+        FrH s = host::kZero;
+        for (uint32_t p = 0; p < t->P; p++) {
+            FrH prod = host::kOne;  // ComposedMultilinear::evaluation  composed_multilinear.rs:52-61
+            for (uint32_t k = 0; k < t->deg[p]; k++) prod = host::mul(prod, load_h(&resid[((size_t)b * t->Dtot + t->koff[p] + k) * 4]));
+            s = host::add(s, prod);
+        }
+        store_h(out + 4 * b, s);
+    }
+    zksc_tables_reset(t);
+    return ZKSC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stand-alone Multilinear operations
+// ------------------------------------------------------------------------------------------------
+struct DevBuf {
+    Fr* p = nullptr;
+    ~DevBuf() { cudaFree(p); }
+};
+
+extern "C" int zksc_ml_partial_evaluation(zksc_ctx* ctx, const uint64_t* evals, uint64_t n, const uint64_t* r, uint32_t variable_index, uint64_t* out) {
+    if (!ctx) return ZKSC_ERR_STATE;
+    if (!evals || !r || !out) FAIL(ZKSC_ERR_SHAPE, "NULL argument");
+    if (n < 2 || (n & (n - 1))) FAIL(ZKSC_ERR_SHAPE, "Number of evaluations must be a power of 2 (and at least 2 to bind a variable)");
+    if (n % 2 != 0 || variable_index >= n / 2 || (n >> (variable_index + 1)) == 0) FAIL(ZKSC_ERR_SHAPE, "variable_index must be less than n/2 and name an existing variable");
+    CK(cudaSetDevice(ctx->device));
+    DevBuf in, o;
+    CK(cudaMalloc(&in.p, n * sizeof(Fr)));
+    CK(cudaMalloc(&o.p, n / 2 * sizeof(Fr)));
+    CK(cudaMemcpyAsync(in.p, evals, n * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    FoldArgs a;
+    a.in = in.p; a.out = o.p;
+    a.in_tab_stride = a.in_proof_stride = a.out_tab_stride = a.out_proof_stride = 0;
+    a.n_out = n / 2; a.s = n >> (variable_index + 1); a.n_tabs = 1;
+    memcpy(a.chal[0].l, r, 32);
+    fold_kernel<<<dim3(grid_for(ctx, a.n_out, 256, 8), 1), 256, 0, ctx->stream>>>(a);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, o.p, n / 2 * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return ZKSC_OK;
+}
+
+extern "C" int zksc_ml_evaluation(zksc_ctx* ctx, const uint64_t* evals, uint64_t n, const uint64_t* points, uint32_t n_points, uint64_t* out) {
+    if (!ctx) return ZKSC_ERR_STATE;
+    if (!evals || !out || (n_points && !points)) FAIL(ZKSC_ERR_SHAPE, "NULL argument");
+    if (n < 1 || (n & (n - 1))) FAIL(ZKSC_ERR_SHAPE, "Number of evaluations must be a power of 2");
+    if ((1ull << n_points) != n) FAIL(ZKSC_ERR_SHAPE, "Number of evaluation points must match the number of variables");
+    CK(cudaSetDevice(ctx->device));
+    DevBuf buf;
+    CK(cudaMalloc(&buf.p, n * sizeof(Fr)));
+    CK(cudaMemcpyAsync(buf.p, evals, n * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    uint64_t cur = n;
+    for (uint32_t j = 0; j < n_points; j++) {
+        FoldArgs a;
+        a.in = buf.p; a.out = buf.p;  // variable 0, in place
+        a.in_tab_stride = a.in_proof_stride = a.out_tab_stride = a.out_proof_stride = 0;
+        a.n_out = cur / 2; a.s = cur / 2; a.n_tabs = 1;
+        memcpy(a.chal[0].l, points + 4 * j, 32);
+        fold_kernel<<<dim3(grid_for(ctx, a.n_out, 256, 8), 1), 256, 0, ctx->stream>>>(a);
+        cur /= 2;
+    }
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, buf.p, sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return ZKSC_OK;
+}
+
+extern "C" int zksc_ml_outer(zksc_ctx* ctx, int mul, const uint64_t* a, uint64_t na, const uint64_t* b, uint64_t nb, uint64_t* out) {
+    if (!ctx) return ZKSC_ERR_STATE;
+    if (!a || !b || !out || !na || !nb) FAIL(ZKSC_ERR_SHAPE, "empty operand");
+    uint64_t n = na * nb;
+    if (n & (n - 1)) FAIL(ZKSC_ERR_SHAPE, "Number of evaluations must be a power of 2");
+    CK(cudaSetDevice(ctx->device));
+    DevBuf da, db, dout;
+    CK(cudaMalloc(&da.p, na * sizeof(Fr)));
+    CK(cudaMalloc(&db.p, nb * sizeof(Fr)));
+    CK(cudaMalloc(&dout.p, n * sizeof(Fr)));
+    CK(cudaMemcpyAsync(da.p, a, na * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(db.p, b, nb * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    outer_kernel<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(mul, da.p, na, db.p, nb, dout.p);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, dout.p, n * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return ZKSC_OK;
+}
+
+extern "C" int zksc_ml_elementwise(zksc_ctx* ctx, int op, const uint64_t* a, const uint64_t* b, uint64_t n, uint64_t* out) {
+    if (!ctx) return ZKSC_ERR_STATE;
+    if (!a || !b || !out || !n) FAIL(ZKSC_ERR_SHAPE, "empty operand");
+    if (op < 0 || op > 3) FAIL(ZKSC_ERR_SHAPE, "op");
+    CK(cudaSetDevice(ctx->device));
+    DevBuf da, db, dout;
+    const uint64_t nb = (op == EW_SCALE) ? 1 : n;
+    CK(cudaMalloc(&da.p, n * sizeof(Fr)));
+    CK(cudaMalloc(&db.p, nb * sizeof(Fr)));
+    CK(cudaMalloc(&dout.p, n * sizeof(Fr)));
+    CK(cudaMemcpyAsync(da.p, a, n * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(db.p, b, nb * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    ew_kernel<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(op, da.p, db.p, dout.p, n);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, dout.p, n * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return ZKSC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host helpers
+// ------------------------------------------------------------------------------------------------
+extern "C" void zksc_fr_from_u64(uint64_t x, uint64_t out[4]) { store_h(out, host::from_u64(x)); }
+extern "C" void zksc_fr_from_canonical(const uint64_t c[4], uint64_t out[4]) { store_h(out, host::from_canonical(c)); }
+extern "C" void zksc_fr_to_canonical(const uint64_t m[4], uint64_t out[4]) { host::to_canonical(load_h(m), out); }
+extern "C" void zksc_fr_from_canonical_batch(const uint64_t* c, uint64_t n, uint64_t* out) {
+    for (uint64_t i = 0; i < n; i++) store_h(out + 4 * i, host::from_canonical(c + 4 * i));
+}
+extern "C" void zksc_fr_to_canonical_batch(const uint64_t* m, uint64_t n, uint64_t* out) {
+    for (uint64_t i = 0; i < n; i++) host::to_canonical(load_h(m + 4 * i), out + 4 * i);
+}
+extern "C" void zksc_fr_to_be_bytes(const uint64_t m[4], uint8_t out[32]) { host::to_be_bytes(load_h(m), out); }
+extern "C" void zksc_fr_from_be_bytes_mod_order(const uint8_t in[32], uint64_t out[4]) { store_h(out, host::from_be_bytes_mod_order(in)); }
+extern "C" void zksc_fr_add(const uint64_t a[4], const uint64_t b[4], uint64_t out[4]) { store_h(out, host::add(load_h(a), load_h(b))); }
+extern "C" void zksc_fr_sub(const uint64_t a[4], const uint64_t b[4], uint64_t out[4]) { store_h(out, host::sub(load_h(a), load_h(b))); }
+extern "C" void zksc_fr_mul(const uint64_t a[4], const uint64_t b[4], uint64_t out[4]) { store_h(out, host::mul(load_h(a), load_h(b))); }
+
+struct zksc_transcript {
+    host::FiatShamirTranscript t;
+};
+extern "C" zksc_transcript* zksc_transcript_new(void) { return new zksc_transcript(); }
+extern "C" void zksc_transcript_free(zksc_transcript* t) { delete t; }
+extern "C" void zksc_transcript_commit(zksc_transcript* t, const uint8_t* data, size_t len) { t->t.commit(data, len); }
+extern "C" void zksc_transcript_challenge(zksc_transcript* t, uint8_t out[32]) { t->t.challenge(out); }
+extern "C" void zksc_transcript_challenge_field(zksc_transcript* t, uint64_t out[4]) { store_h(out, t->t.evaluate_challenge_into_field()); }
+
+static uint32_t store_poly(const host::SparseUnivariatePolynomial& p, uint64_t* out) {
+    for (size_t m = 0; m < p.monomial.size(); m++) {
+        store_h(out + 8 * m, p.monomial[m].coeff);
+        store_h(out + 8 * m + 4, p.monomial[m].pow);
+    }
+    return (uint32_t)p.monomial.size();
+}
+static host::SparseUnivariatePolynomial load_poly(const uint64_t* mono, uint32_t n) {
+    host::SparseUnivariatePolynomial p;
+    for (uint32_t i = 0; i < n; i++) p.monomial.push_back({load_h(mono + 8 * i), load_h(mono + 8 * i + 4)});
+    return p;
+}
+extern "C" uint32_t zksc_sparse_interpolate(const uint64_t* ys, uint32_t n, uint64_t* out_mono) {
+    std::vector<FrH> y;
+    for (uint32_t i = 0; i < n; i++) y.push_back(load_h(ys + 4 * i));
+    return store_poly(host::SparseUnivariatePolynomial::interpolate_evals(y), out_mono);
+}
+extern "C" uint32_t zksc_sparse_add(const uint64_t* a, uint32_t na, const uint64_t* b, uint32_t nb, uint64_t* out_mono) {
+    return store_poly(load_poly(a, na) + load_poly(b, nb), out_mono);
+}
+extern "C" void zksc_sparse_evaluate(const uint64_t* mono, uint32_t n, const uint64_t point[4], uint64_t out[4]) {
+    store_h(out, load_poly(mono, n).evaluate(load_h(point)));
+}
+
+static uint64_t h_splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    uint64_t z = x;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+extern "C" void zksc_synth_entry(uint64_t seed, uint64_t table, uint64_t index, uint64_t out[4]) {
+    const uint64_t base = h_splitmix64(seed ^ h_splitmix64(table * 0xD1342543DE82EF95ull + 0x632BE59BD9B4E019ull));
+    uint64_t c[4];
+    for (int limb = 0; limb < 4; limb++) c[limb] = h_splitmix64(base + (index * 4 + limb) * 0x9E3779B97F4A7C15ull);
+    store_h(out, host::from_canonical(c));
+}
