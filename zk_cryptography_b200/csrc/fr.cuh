@@ -186,8 +186,11 @@ static const uint32_t kModulus[8] = {ZKSC_P0, ZKSC_P1, ZKSC_P2, ZKSC_P3, ZKSC_P4
 // in uniform registers (no vector registers spent) and every pair fuses (checked in SASS).
 ZKSC_DEV void load_modulus(uint32_t& m0, uint32_t& m1, uint32_t& m2, uint32_t& m3, uint32_t& m4, uint32_t& m5, uint32_t& m6, uint32_t& m7) {
 #ifndef ZKSC_HOST_EMU
-    asm volatile("ld.const.u32 %0, [%8]; ld.const.u32 %1, [%8+4]; ld.const.u32 %2, [%8+8]; ld.const.u32 %3, [%8+12];\n\t"
-                 "ld.const.u32 %4, [%8+16]; ld.const.u32 %5, [%8+20]; ld.const.u32 %6, [%8+24]; ld.const.u32 %7, [%8+28];"
+    // &kModulus is a GENERIC address in device code: convert it to a .const-space address first
+    // (an ld.const on the generic address reads garbage).
+    asm volatile("{\n\t.reg .u64 cp;\n\tcvta.to.const.u64 cp, %8;\n\t"
+                 "ld.const.u32 %0, [cp]; ld.const.u32 %1, [cp+4]; ld.const.u32 %2, [cp+8]; ld.const.u32 %3, [cp+12];\n\t"
+                 "ld.const.u32 %4, [cp+16]; ld.const.u32 %5, [cp+20]; ld.const.u32 %6, [cp+24]; ld.const.u32 %7, [cp+28];\n\t}"
                  : "=r"(m0), "=r"(m1), "=r"(m2), "=r"(m3), "=r"(m4), "=r"(m5), "=r"(m6), "=r"(m7)
                  : "l"(kModulus));
 #else
