@@ -1,0 +1,404 @@
+#!/usr/bin/env python
+"""bench.py -- sumcheck prover throughput (hypercube evals/s) on N B200s, or the CPU reference arm.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c1|c5] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One step = what the reference's `multi_composed_sumcheck_with_prove_partial_benchmark` times
+(sumcheck/benches/multi_composed_sumcheck_benchmark.rs:138-146):
+    sum = MultiComposedSumcheckProver::calculate_poly_sum(&poly);  prove_partial(&poly, &sum)
+on synthetic seeded tables.  Workloads (BASELINE.json configs):
+    c2 (default)  one degree-2 product, 2^24 entries per GPU (2^(24+log2 N) sharded over N GPUs: weak scaling)
+    c3            one degree-3 product, 2^28 entries in total, sharded over the N GPUs (strong scaling)
+    c1            Sumcheck::prove on one 2^20-entry multilinear (replicated on every GPU)
+    c5            64 independent degree-2 proofs of 2^22 entries, 64/N per GPU (replicas, batched launches)
+`value`   : tables resident in HBM when the clock starts (generated on the device).
+`e2e`     : the same step through the public API with HOST tables: pinned host -> device copy of every
+            table and device -> host copy of the proof inside the timed region.
+`--impl reference` : the CPU restatement of the reference (oracle/zkref.c; the Rust reference cannot be
+            built in this image) on all host threads, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "sumcheck prover hypercube evals/sec"
+UNIT = "evals/s"
+SEED = 20261017
+
+# name -> (n_vars at N=1, degrees, protocol name, proofs, scaling)
+WORKLOADS = {
+    "c2": dict(n=24, degs=[2], proto="multi_partial", proofs=1, scaling="weak",
+               desc="MultiComposedSumcheckProver: calculate_poly_sum + prove_partial, one degree-2 product, 2^24 entries per GPU"),
+    "c3": dict(n=28, degs=[3], proto="multi_partial", proofs=1, scaling="strong",
+               desc="MultiComposedSumcheckProver: calculate_poly_sum + prove_partial, one degree-3 product, 2^28 entries in total"),
+    "c1": dict(n=20, degs=[1], proto="sumcheck", proofs=1, scaling="replicas",
+               desc="Sumcheck: poly_sum + prove, one 2^20-entry multilinear per GPU"),
+    "c5": dict(n=22, degs=[2], proto="multi_partial", proofs=64, scaling="strong",
+               desc="64 independent prove_partial (degree-2 product, 2^22 entries each), 64/N proofs per GPU, batched launches"),
+}
+
+
+def read_peaks():
+    """HBM peak from MEASURED_PEAKS.json (driver-written) else the profiling guide's fallback; the integer
+    peak from profiles/int_peak.json (our own IMAD microbenchmark on this pool's B200, tools/ubench.cu)."""
+    hbm, src = 6650.0, "fallback"
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            hbm, src = float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        pass
+    ip = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "int_peak.json")) as f:
+            ip = json.load(f)
+    except Exception:
+        pass
+    return hbm, src, ip
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz = index, False, [], set(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def algorithmic_bytes(rec):
+    """HBM bytes one round-kernel launch must move (DESIGN.md "Algorithmic bytes"): 32 B per element;
+    an evaluate-only launch reads both halves of every table (2 * pairs entries); a fused fold+evaluate launch
+    reads the previous table (4 * pairs entries) and writes the folded one (2 * pairs)."""
+    per_table = (6 if rec["fold"] else 2) * rec["pairs"] * 32
+    return per_table * rec["degree"] * rec["proofs"]
+
+
+def algorithmic_modmuls(rec):
+    """Field multiplications one launch needs: (d+1)(d-1) per pair for the d+1 evaluation points (points 0 and 1
+    cost d-1 each, as do points 2..d) plus, when the fold is fused in, 2d per pair (both entries of the pair of
+    each of the d tables are folded)."""
+    d = rec["degree"]
+    return ((d + 1) * (d - 1) + (2 * d if rec["fold"] else 0)) * rec["pairs"] * rec["proofs"]
+
+
+def run_b200(args):
+    import numpy as np
+    import torch
+
+    import zk_cryptography_b200 as zk
+    from zk_cryptography_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    wl = dict(WORKLOADS[args.workload])
+    G = world
+    lgG = int(math.log2(G))
+    ctx = zk.Context(local_rank)
+    sharded = wl["scaling"] in ("weak", "strong") and wl["proofs"] == 1 and G > 1
+    if sharded:
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(zk.Context.unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        ctx.comm_init(G, rank, bytes(uid.cpu().numpy().tobytes()))
+    n = wl["n"] + (lgG if wl["scaling"] == "weak" else 0)
+    proofs_total = wl["proofs"]
+    proofs_local = proofs_total // G if (wl["proofs"] > 1) else 1
+    if wl["proofs"] > 1 and proofs_total % G:
+        raise SystemExit("proof count must divide by the GPU count")
+    proto = {"multi_partial": zk.PROTO_MULTI_PARTIAL, "sumcheck": zk.PROTO_SUMCHECK}[wl["proto"]]
+    seed = SEED + (rank * proofs_local if wl["proofs"] > 1 else 0)
+    tables = zk.Tables.synth(ctx, n, wl["degs"], seed, n_proofs=proofs_local)
+
+    stream = torch.cuda.ExternalStream(ctx.stream_handle(), device=torch.device("cuda", local_rank))
+
+    def step():
+        tables.reset()
+        s = tables.poly_sum()                     # calculate_poly_sum (round-0 pass; its evaluations are reused by prove)
+        return tables.prove(proto, s)             # prove_partial: n rounds, transcript on the host
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # units per step for the whole job
+    if wl["scaling"] == "replicas":
+        evals_per_step = (1 << n) * G
+    elif wl["proofs"] > 1:
+        evals_per_step = (1 << n) * proofs_total
+    else:
+        evals_per_step = 1 << n
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    ctx.timing(True)
+    launches0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.start()
+    e0.record(stream)
+    for _ in range(args.steps):
+        msgs, lens, chal = step()
+    e1.record(stream)
+    barrier()
+    sampler.stop_flag = True
+    ms = e0.elapsed_time(e1)
+    launches = ctx.launch_count() - launches0
+    recs = ctx.timing_read(cap=1 << 16)
+    ctx.timing(False)
+    if dist is not None:
+        tms = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    sampler.join(timeout=1.0)
+    value = evals_per_step * args.steps / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (live CUDA events around every launch of the timed region) ----
+    hbm_peak, peak_src, int_peak = read_peaks()
+    groups = {}
+    for r in recs:
+        g = groups.setdefault((r["degree"], r["fold"]), dict(ms=0.0, bytes=0, modmuls=0, launches=0, largest=None))
+        g["ms"] += r["ms"]; g["bytes"] += algorithmic_bytes(r); g["modmuls"] += algorithmic_modmuls(r); g["launches"] += 1
+        if g["largest"] is None or r["pairs"] * r["proofs"] > g["largest"]["pairs"] * g["largest"]["proofs"]:
+            g["largest"] = r
+    (kd, kf), top = max(groups.items(), key=lambda kv: kv[1]["ms"])
+    big = top["largest"]
+    big_n = sum(1 for r in recs if (r["degree"], r["fold"]) == (kd, kf) and r["pairs"] == big["pairs"])
+    big_ms = sum(r["ms"] for r in recs if (r["degree"], r["fold"]) == (kd, kf) and r["pairs"] == big["pairs"]) / big_n
+    achieved = algorithmic_bytes(big) / (big_ms * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm", "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(achieved / hbm_peak, 4),
+        "traffic": None, "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)" if peak_src == "measured" else "fallback 6650 GB/s (B200_PROFILING.md)",
+        "kernel": "round_kernel<D=%d,FOLD=%s>" % (kd, "true" if kf else "false"),
+        "launch": {"pairs_per_table": big["pairs"], "proofs": big["proofs"], "algorithmic_bytes": algorithmic_bytes(big), "avg_ms": round(big_ms, 5),
+                   "launches_averaged": big_n},
+        "all_launches_of_kernel": {"launches": top["launches"], "ms_per_step": round(top["ms"] / args.steps, 5),
+                                   "GBps": round(top["bytes"] / (top["ms"] * 1e-3) / 1e9, 1)},
+        "kernel_share_of_step": round(top["ms"] / ms, 4),
+    }
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tr = json.load(f).get(roofline["kernel"])
+            if tr and tr.get("pairs_per_table") == big["pairs"]:
+                roofline["traffic"] = tr["dram_bytes"]
+    except Exception:
+        pass
+    int_roofline = None
+    if int_peak:
+        # 136 32x32->64 limb products per 256-bit CIOS Montgomery multiplication
+        prods = algorithmic_modmuls(big) * 136 / (big_ms * 1e-3) / 1e12
+        int_roofline = {"bound": "int32-multiply", "achieved": round(prods, 3), "peak": int_peak["imad_wide_Tops"], "unit": "T limb-products/s",
+                        "frac": round(prods / int_peak["imad_wide_Tops"], 4), "peak_source": int_peak.get("source", "tools/ubench.cu")}
+
+    # ---- e2e: host tables in pinned memory -> upload -> poly_sum + prove -> proof on the host ----
+    e2e = None
+    if not args.no_e2e:
+        host = torch.empty((proofs_local * tables.n_tables, (1 << n) // (G if sharded else 1), 4), dtype=torch.int64).pin_memory()
+        hnp = host.numpy().view(np.uint64)
+        hnp[...] = tables.read_local().reshape(hnp.shape)
+        views = [hnp[i] for i in range(hnp.shape[0])]
+        h2d = hnp.nbytes
+
+        def e2e_step():
+            tables.reupload(views, local=sharded)
+            s = tables.poly_sum()
+            return tables.prove(proto, s)
+
+        for _ in range(max(1, min(args.warmup, 3))):
+            e2e_step()
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(stream)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            m2, l2, c2 = e2e_step()
+        f1.record(stream)
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        ms2 = max(f0.elapsed_time(f1), 0.0)
+        if dist is not None:
+            tms = torch.tensor([ms2], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            ms2 = float(tms.item())
+        assert np.array_equal(m2, msgs) and np.array_equal(c2, chal), "e2e proof differs from the resident-table proof"
+        d2h = int(m2.nbytes + c2.nbytes + l2.nbytes + 32 * proofs_local)
+        e2e = {"value": evals_per_step * args.steps / (ms2 * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h,
+               "ms_per_step": round(ms2 / args.steps, 4), "host_wall_ms_per_step": round(wall_ms / args.steps, 4),
+               "api": "Tables.reupload(host tables) + Tables.poly_sum() + Tables.prove() = zksc_tables_reupload + zksc_poly_sum + zksc_prove (C ABI, host buffers)"}
+
+    if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- CPU baseline (oracle port; N=1 only) ----
+    cpu = None
+    if G == 1 and not args.no_cpu:
+        cpu = cpu_baseline(args.workload, sample_n=args.cpu_n)
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": G, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": wl["scaling"] if wl["scaling"] != "replicas" else "weak",
+        "vs_baseline": None, "dtype": "u32 limbs (256-bit modular integer, BLS12-381 Fr, Montgomery)", "data": "synthetic (seeded splitmix64 tables generated on the device)",
+        "config": {"workload": "%s: %s" % (args.workload, wl["desc"]), "n_vars": n, "degrees": wl["degs"], "proofs": proofs_total,
+                   "table_bytes_per_gpu": int(proofs_local * tables.n_tables * ((1 << n) // (G if sharded else 1)) * 32),
+                   "l2_policy": "inputs_exceed_l2" if proofs_local * tables.n_tables * ((1 << n) // (G if sharded else 1)) * 32 > 126e6 * 2 else "inputs_fit_l2_no_flush",
+                   "sharding": ("index mod %d (last-bound variables), per-round ncclAllGather of %d field elements" % (G, tables.n_evals)) if sharded else
+                               ("replicas" if G > 1 else "single GPU"),
+                   "proof_bytes": len(_lib.proof_to_bytes(proto, msgs[0], lens[0]))},
+        "clocks": sampler.summary(), "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline, "int_roofline": int_roofline,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(out))
+    sys.stdout.flush()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_workload(workload, sample_n):
+    import numpy as np
+    from oracle import cref
+    wl = WORKLOADS[workload]
+    n = min(wl["n"], sample_n)
+    D = sum(wl["degs"])
+    tabs = np.concatenate([cref.synth_table(SEED, k, n) for k in range(D)])
+    proto = {"multi_partial": 2, "sumcheck": 0}[wl["proto"]]
+    return cref, wl, n, tabs, proto
+
+
+def cpu_baseline(workload, sample_n):
+    """The oracle port on the host cores: one bounded sample of the same workload at a smaller n
+    (cost is linear in 2^n), all OpenMP threads, plus the single-thread figure (the reference itself is
+    single-threaded)."""
+    cref, wl, n, tabs, proto = cpu_workload(workload, sample_n)
+    res = {}
+    for label, th in (("all", cref.max_threads()), ("one", 1)):
+        cref.set_threads(th)
+        nn = n if label == "all" else max(10, n - 3)
+        tt = tabs if nn == n else __import__("numpy").concatenate([cref.synth_table(SEED, k, nn) for k in range(sum(wl["degs"]))])
+        t0 = time.perf_counter()
+        s = cref.poly_sum(nn, wl["degs"], tt)
+        cref.prove(proto, nn, wl["degs"], tt, s)
+        dt = time.perf_counter() - t0
+        res[label] = ((1 << nn) / dt, nn, dt, th)
+    return {"value": res["all"][0], "unit": UNIT, "cores": res["all"][3], "kind": "port",
+            "sample": "oracle/zkref.c (C restatement with the reference's loop structure), same workload at n_vars=%d (%.2f s), OpenMP over %d threads"
+                      % (res["all"][1], res["all"][2], res["all"][3]),
+            "single_thread": {"value": res["one"][0], "n_vars": res["one"][1], "seconds": round(res["one"][2], 3)}}
+
+
+def run_reference(args):
+    """The reference's CPU implementation of the path on the host cores.  The reference is Rust and cannot be
+    compiled in this image (no cargo/rustc, crates not vendored), so this is the oracle port (`kind: port`)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cref, wl, n, tabs, proto = cpu_workload(args.workload, args.cpu_n)
+    th = cref.max_threads()
+    cref.set_threads(th)
+
+    def step():
+        s = cref.poly_sum(n, wl["degs"], tabs)
+        cref.prove(proto, n, wl["degs"], tabs, s)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = (1 << n) * args.steps / dt
+    sample = "oracle/zkref.c on %d OpenMP threads; each step = calculate_poly_sum + prove at n_vars=%d (bounded sample of %s; cost is linear in 2^n)" % (th, n, args.workload)
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt * 1e3 / args.steps, "higher_is_better": True, "scaling": WORKLOADS[args.workload]["scaling"] if WORKLOADS[args.workload]["scaling"] != "replicas" else "weak",
+        "vs_baseline": None, "dtype": "u64 limbs (256-bit modular integer, BLS12-381 Fr, Montgomery)", "data": "synthetic (same seeded tables)",
+        "config": {"workload": "%s: %s" % (args.workload, WORKLOADS[args.workload]["desc"]), "n_vars": n, "degrees": wl["degs"]},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": th, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-n", type=int, default=22, help="n_vars of the bounded CPU sample")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -55,6 +55,17 @@ int zksc_comm_unique_id(uint8_t out_id[128]);
 int zksc_comm_init(zksc_ctx* ctx, int n_ranks, int rank, const uint8_t unique_id[128]);
 int zksc_ctx_rank(const zksc_ctx* ctx, int* rank, int* n_ranks);
 int zksc_ctx_synchronize(zksc_ctx* ctx);
+/* Measurement hooks (bench.py; no reference counterpart).  zksc_ctx_stream: the cudaStream_t every kernel
+ * of this context is launched on (so callers can record their own events on it).  zksc_ctx_launch_count:
+ * kernels launched by this context so far.  zksc_ctx_timing(ctx, 1) brackets every round-kernel launch
+ * with CUDA events from then on; zksc_ctx_timing_read drains the records (per launch: duration in ms,
+ * product degree, whether the previous challenge's fold was fused in, pairs per table processed, proofs
+ * in the launch) and returns how many were written (at most cap). */
+void* zksc_ctx_stream(zksc_ctx* ctx);
+unsigned long long zksc_ctx_launch_count(const zksc_ctx* ctx);
+int zksc_ctx_timing(zksc_ctx* ctx, int enable);
+int zksc_ctx_timing_read(zksc_ctx* ctx, uint32_t cap, uint32_t* n_out, float* ms, uint32_t* degree, uint32_t* fold, uint64_t* pairs,
+                         uint64_t* proofs);
 
 /* ---- device-resident evaluation tables --------------------------------------------------------
  * A `zksc_tables` is `n_proofs` independent instances of  sum_p prod_k f_{p,k}  : for each proof,
@@ -71,6 +82,16 @@ int zksc_ctx_synchronize(zksc_ctx* ctx);
  * sharded: the rank picks out its own entries). */
 int zksc_tables_upload(zksc_ctx* ctx, uint32_t n_vars, uint32_t n_proofs, uint32_t n_products, const uint32_t* degree,
                        const uint64_t* const* host_tables, zksc_tables** out);
+/* Sharded contexts: as zksc_tables_upload, but host_local_tables[t] -> this rank's 2^n_vars / n_ranks
+ * entries (those with index = rank mod n_ranks, in order), so no rank touches data it does not own. */
+int zksc_tables_upload_local(zksc_ctx* ctx, uint32_t n_vars, uint32_t n_proofs, uint32_t n_products, const uint32_t* degree,
+                             const uint64_t* const* host_local_tables, zksc_tables** out);
+/* Copy new host tables into an existing handle of the same shape (and reset it): the steady-state form of
+ * zksc_tables_upload (local == 0) / zksc_tables_upload_local (local != 0) for callers that prove many
+ * instances of one shape. */
+int zksc_tables_reupload(zksc_tables* t, const uint64_t* const* host_tables, int local);
+/* This rank's copy of the tables as uploaded (n_proofs x n_tables x 2^n_vars / n_ranks elements). */
+int zksc_tables_read_local(zksc_tables* t, uint64_t* out);
 /* Fill tables on the device with the seeded synthetic generator (entry = f(seed + proof, table, i);
  * DESIGN.md "Synthetic inputs"); each rank generates only its shard. */
 int zksc_tables_synth(zksc_ctx* ctx, uint32_t n_vars, uint32_t n_proofs, uint32_t n_products, const uint32_t* degree, uint64_t seed,

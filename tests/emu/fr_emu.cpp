@@ -27,7 +27,11 @@ void emu_acc17_reduce(const uint32_t* a17, uint32_t* o) { Acc<17> a; memcpy(a.l,
 void emu_acc17_add(uint32_t* a17, const uint32_t* t16) { Acc<17> a; memcpy(a.l, a17, 68); uint32_t T[16]; memcpy(T, t16, 64); acc_add<17, 16>(a, T); memcpy(a17, a.l, 68); }
 void emu_consts(uint32_t* one, uint32_t* r2) { Fr a = fr_one(), b = fr_r2(); memcpy(one, a.l, 32); memcpy(r2, b.l, 32); }
 }
-extern "C" void emu_mont_mul_raw(const uint32_t* a, const uint32_t* b, uint32_t* out9) {
+extern "C" void emu_mul_ps_wide(const uint32_t* a, const uint32_t* b, uint32_t* out16) {
     Fr x, y; memcpy(x.l, a, 32); memcpy(y.l, b, 32);
-    uint32_t res[8], top; mont_mul_raw(res, top, x, y); memcpy(out9, res, 32); out9[8] = top;
+    uint32_t T[16]; (void)mul_ps<false>(T, x, y); memcpy(out16, T, 64);
+}
+extern "C" void emu_mul_ps_mont(const uint32_t* a, const uint32_t* b, uint32_t* out9) {
+    Fr x, y; memcpy(x.l, a, 32); memcpy(y.l, b, 32);
+    uint32_t res[8]; uint32_t top = mul_ps<true>(res, x, y); memcpy(out9, res, 32); out9[8] = top;
 }

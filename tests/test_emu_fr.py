@@ -54,7 +54,9 @@ def test_limb_algorithms(emu):
         a, b = rnd(rng, 2**256), rnd(rng, 2**256)
         emu.emu_mul_wide(arr(a, 8), arr(b, 8), o16)
         assert val(o16) == a * b
-        emu.emu_mont_mul_raw(arr(a, 8), arr(b, 8), o9)
+        emu.emu_mul_ps_wide(arr(a, 8), arr(b, 8), o16)
+        assert val(o16) == a * b
+        emu.emu_mul_ps_mont(arr(a, 8), arr(b, 8), o9)
         v = val(o9)
         assert v % R == a * b * RINV % R and v < 2**256 + R
         T = rnd(rng, 2**512)

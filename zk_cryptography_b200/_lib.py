@@ -48,6 +48,13 @@ def lib():
         "zksc_comm_init": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, _u8p]),
         "zksc_ctx_rank": (ctypes.c_int, [vp, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
         "zksc_ctx_synchronize": (ctypes.c_int, [vp]),
+        "zksc_ctx_stream": (vp, [vp]),
+        "zksc_ctx_launch_count": (ctypes.c_ulonglong, [vp]),
+        "zksc_ctx_timing": (ctypes.c_int, [vp, ctypes.c_int]),
+        "zksc_ctx_timing_read": (ctypes.c_int, [vp, ctypes.c_uint32, _u32p, ctypes.POINTER(ctypes.c_float), _u32p, _u32p, _u64p, _u64p]),
+        "zksc_tables_reupload": (ctypes.c_int, [vp, ctypes.POINTER(_u64p), ctypes.c_int]),
+        "zksc_tables_upload_local": (ctypes.c_int, [vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, _u32p, ctypes.POINTER(_u64p), ctypes.POINTER(vp)]),
+        "zksc_tables_read_local": (ctypes.c_int, [vp, _u64p]),
         "zksc_tables_upload": (ctypes.c_int, [vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, _u32p, ctypes.POINTER(_u64p), ctypes.POINTER(vp)]),
         "zksc_tables_synth": (ctypes.c_int, [vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, _u32p, ctypes.c_uint64, ctypes.POINTER(vp)]),
         "zksc_tables_free": (ctypes.c_int, [vp]),
@@ -173,6 +180,28 @@ class Context:
     def synchronize(self):
         self.check(lib().zksc_ctx_synchronize(self._h))
 
+    def stream_handle(self):
+        """The cudaStream_t (as int) all kernels of this context run on."""
+        return int(lib().zksc_ctx_stream(self._h) or 0)
+
+    def launch_count(self):
+        return int(lib().zksc_ctx_launch_count(self._h))
+
+    def timing(self, enable):
+        self.check(lib().zksc_ctx_timing(self._h, 1 if enable else 0))
+
+    def timing_read(self, cap=4096):
+        """-> list of dicts {ms, degree, fold, pairs, proofs}, one per round-kernel launch since the last read."""
+        n = ctypes.c_uint32()
+        ms = np.zeros(cap, dtype=np.float32)
+        deg = np.zeros(cap, dtype=np.uint32)
+        fold = np.zeros(cap, dtype=np.uint32)
+        pairs = np.zeros(cap, dtype=np.uint64)
+        proofs = np.zeros(cap, dtype=np.uint64)
+        self.check(lib().zksc_ctx_timing_read(self._h, cap, ctypes.byref(n), ms.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), p32(deg), p32(fold),
+                                              p64(pairs), p64(proofs)))
+        return [dict(ms=float(ms[i]), degree=int(deg[i]), fold=int(fold[i]), pairs=int(pairs[i]), proofs=int(proofs[i])) for i in range(n.value)]
+
     def close(self):
         if self._h:
             lib().zksc_ctx_destroy(self._h)
@@ -207,6 +236,35 @@ class Tables:
         h = ctypes.c_void_p()
         ctx.check(lib().zksc_tables_upload(ctx._h, n_vars, n_proofs, len(deg), p32(deg), ptrs, ctypes.byref(h)))
         return Tables(ctx, n_vars, degrees, h, n_proofs)
+
+    def reupload(self, tables, local=False):
+        """Copy new host tables (same shapes) into this handle and reset it.  local: the arrays are this
+        rank's shards (2^n_vars / n_ranks entries each) instead of full tables."""
+        arrs = [np.ascontiguousarray(t, dtype=np.uint64) for t in tables]
+        n = (1 << self.n_vars) // (self.ctx.n_ranks if local else 1)
+        if len(arrs) != self.n_proofs * self.n_tables or any(a.shape != (n, 4) for a in arrs):
+            raise ZkscError(-3, "tables do not match the shape this handle was created with")
+        ptrs = (_u64p * len(arrs))(*[p64(a) for a in arrs])
+        self.ctx.check(lib().zksc_tables_reupload(self._h, ptrs, 1 if local else 0))
+
+    @staticmethod
+    def upload_local(ctx, n_vars, degrees, local_tables, n_proofs=1):
+        """Sharded contexts: local_tables[t] holds this rank's entries (index = rank mod n_ranks) of table t."""
+        deg = np.asarray(degrees, dtype=np.uint32)
+        arrs = [np.ascontiguousarray(t, dtype=np.uint64) for t in local_tables]
+        n = (1 << n_vars) // ctx.n_ranks
+        if len(arrs) != n_proofs * int(deg.sum()) or any(a.shape != (n, 4) for a in arrs):
+            raise ZkscError(-3, "local tables must hold 2^n_vars / n_ranks entries each")
+        ptrs = (_u64p * len(arrs))(*[p64(a) for a in arrs])
+        h = ctypes.c_void_p()
+        ctx.check(lib().zksc_tables_upload_local(ctx._h, n_vars, n_proofs, len(deg), p32(deg), ptrs, ctypes.byref(h)))
+        return Tables(ctx, n_vars, degrees, h, n_proofs)
+
+    def read_local(self):
+        """-> (n_proofs, n_tables, 2^n_vars / n_ranks, 4): this rank's copy of the tables as uploaded."""
+        out = np.zeros((self.n_proofs, self.n_tables, (1 << self.n_vars) // self.ctx.n_ranks, 4), dtype=np.uint64)
+        self.ctx.check(lib().zksc_tables_read_local(self._h, p64(out)))
+        return out
 
     @staticmethod
     def synth(ctx, n_vars, degrees, seed, n_proofs=1):

@@ -6,14 +6,16 @@
 // The in-memory element is bit-identical to ark-ff's: 4 x u64 little-endian limbs == 8 x u32
 // little-endian limbs, Montgomery form, 32 bytes, so a `&[Fr]` can be copied to the device verbatim.
 //
-// Design notes (see DESIGN.md "Kernels"):
-//  * all multi-limb products are carry chains of mad.lo.cc / madc.hi.cc pairs; ptxas fuses each pair
-//    into one IMAD.WIDE.U32(.X) with a predicate carry (checked with cuobjdump -sass);
-//  * the 512-bit product is built "even/odd": for one multiplier limb b_i the products with
-//    a0,a2,a4,a6 form one clean carry chain and those with a1,a3,a5,a7 a second one, so no
-//    instruction is spent on per-product carry fix-up;
-//  * the modulus is r = 1 + 2^32*q, so -r^-1 mod 2^32 = 0xffffffff and the Montgomery quotient
-//    limb is just m = -T[i];
+// Design notes (see DESIGN.md "Kernels"; measurements in profiles/r01_ubench*.jsonl):
+//  * the multiplier pipe is the roof: IMAD.WIDE.U32 issues at ~31 per clock per SM on B200 (half the IMAD
+//    rate), IMAD.HI.U32 at ~25, and FP64 DFMA shares the same pipe (no gain from mixing), so the aim is
+//    ONE IMAD.WIDE per 32x32 limb product and nothing else on that pipe;
+//  * multiplication is product scanning (column-wise) with a 96-bit accumulator: each partial product is
+//    mad.lo.cc + madc.hi.cc, which ptxas fuses into one IMAD.WIDE.U32 with carry-out, plus an IADD3.X on
+//    the ALU pipe that counts carries;
+//  * the modulus is r = 1 + 2^32*u with r_1 = 2^32 - 1: the Montgomery digit needs no multiplication, the
+//    digit * r_0 product is a carry, digit * r_1 is a shift and a subtraction (112 products in all), and
+//    the digit is formed as a COMPLEMENT (~lo), never a negation -- see mul_ps;
 //  * sums of products are accumulated UNREDUCED (17 limbs) and reduced once per block.
 #pragma once
 #include <cstdint>
@@ -168,123 +170,98 @@ ZKSC_DEV Fr fr_canon(const Fr& x) {
     return y;
 }
 
-// ---- multi-limb products --------------------------------------------------------------------------
-// IMAD.WIDE needs its 64-bit accumulator in an aligned register pair, so partial products whose low
-// limb sits at an EVEN position accumulate in E[] and those at an ODD position in O[] (index =
-// absolute limb position).  For one multiplier limb x at base position i the products with
-// a0,a2,a4,a6 form one carry chain in the array of i's parity and those with a1,a3,a5,a7 a second
-// chain in the other array; the carry out of a chain lands on a limb that is still fresh (small).
-#ifndef ZKSC_HOST_EMU
-static __device__ __constant__ uint32_t kModulus[8] = {ZKSC_P0, ZKSC_P1, ZKSC_P2, ZKSC_P3, ZKSC_P4, ZKSC_P5, ZKSC_P6, ZKSC_P7};
-#else
-static const uint32_t kModulus[8] = {ZKSC_P0, ZKSC_P1, ZKSC_P2, ZKSC_P3, ZKSC_P4, ZKSC_P5, ZKSC_P6, ZKSC_P7};
-#endif
-
-// The modulus limbs are fetched with a volatile ld.const so that ptxas sees opaque values: with
-// immediates (or a constant bank whose contents it knows) it strength-reduces the multiplications by
-// 1 and 0xffffffff and no longer fuses the lo/hi pair into one IMAD.WIDE; as opaque values they live
-// in uniform registers (no vector registers spent) and every pair fuses (checked in SASS).
-ZKSC_DEV void load_modulus(uint32_t& m0, uint32_t& m1, uint32_t& m2, uint32_t& m3, uint32_t& m4, uint32_t& m5, uint32_t& m6, uint32_t& m7) {
-#ifndef ZKSC_HOST_EMU
-    // &kModulus is a GENERIC address in device code: convert it to a .const-space address first
-    // (an ld.const on the generic address reads garbage).
-    asm volatile("{\n\t.reg .u64 cp;\n\tcvta.to.const.u64 cp, %8;\n\t"
-                 "ld.const.u32 %0, [cp]; ld.const.u32 %1, [cp+4]; ld.const.u32 %2, [cp+8]; ld.const.u32 %3, [cp+12];\n\t"
-                 "ld.const.u32 %4, [cp+16]; ld.const.u32 %5, [cp+20]; ld.const.u32 %6, [cp+24]; ld.const.u32 %7, [cp+28];\n\t}"
-                 : "=r"(m0), "=r"(m1), "=r"(m2), "=r"(m3), "=r"(m4), "=r"(m5), "=r"(m6), "=r"(m7)
-                 : "l"(kModulus));
-#else
-    m0 = kModulus[0]; m1 = kModulus[1]; m2 = kModulus[2]; m3 = kModulus[3];
-    m4 = kModulus[4]; m5 = kModulus[5]; m6 = kModulus[6]; m7 = kModulus[7];
-#endif
+// ---- product scanning (column-wise) multiplication ---------------------------------------------------
+// One 96-bit column accumulator (lo, hi, cn).  Every partial product is ONE IMAD.WIDE.U32 with carry-OUT
+// only (mad.lo.cc + madc.hi.cc, fused by ptxas) plus an IADD3.X that counts the carry (ptxas merges two
+// carries into one IADD3.X); no IMAD.WIDE takes a carry-IN.
+// REDUCE: Montgomery reduction interleaved (FIPS).  The textbook quotient digit is q_k = -lo_k (because
+// -p^-1 = -1 mod 2^32), but ptxas folds a negation into the multiplier's operand modifiers and then
+// splits every q*p product into IMAD + IMAD.HI.U32 -- 7 multiplier-pipe cycles instead of 4 (SASS +
+// tools/ubench3.cu).  So the digit is taken as q'_k = ~lo_k and the row added is (q'_k + 1) * p:
+//   * the q'_k * p_j products (j >= 1) are ordinary fused IMAD.WIDEs,
+//   * the "+1" parts add the constant sum_i p * 2^(32 i), i.e. c_k = sum of the p_j that fall in column k,
+//   * column k's own term lo_k + q'_k * p_0 + p_0 = lo_k + ~lo_k + 1 = 2^32 exactly: the low limb
+//     clears and a carry of one moves up, whatever lo_k is (q'_k + 1 ranges over 1..2^32).
+// The total added is < 2^256 * p * (1 + 2^-31), so for a*b < p * 2^256 the result is < 2p + 1 (and
+// since it is congruent to a*b/2^256 and 2p is not reachable... see cond_sub_r: one conditional subtract
+// of p brings any value < 2p to canonical form; the value 2p itself cannot occur because the result
+// is < (p^2 + 2^256 p (1 + 2^-31)) / 2^256 < 2p for p < 2^255).
+// Inputs as for mont_mul_raw.  REDUCE: out[0..7] (+ top limb returned); else out[0..15] = a * b.
+ZKSC_DEV constexpr unsigned long long mod_limb(int j) {
+    return j == 0 ? ZKSC_P0 : j == 1 ? ZKSC_P1 : j == 2 ? ZKSC_P2 : j == 3 ? ZKSC_P3 : j == 4 ? ZKSC_P4 : j == 5 ? ZKSC_P5 : j == 6 ? ZKSC_P6 : ZKSC_P7;
 }
-
-// X[pos .. pos+7] += (v0, v2, v4, v6 as limbs 0,2,4,6) * x ; carry into X[pos+8].
-// CARRY_IN: the chain starts with the pending CC.CF.
-template <bool CARRY_IN>
-ZKSC_DEV void chain4(uint32_t* X, int pos, uint32_t v0, uint32_t v2, uint32_t v4, uint32_t v6, uint32_t x) {
+// sum of the modulus limbs p_j, j >= 1, that the "+1" parts put into column k
+ZKSC_DEV constexpr unsigned long long mod_column_constant(int k) {
+    unsigned long long c = 0;
+    for (int i = (k > 7 ? k - 7 : 0); i <= (k < 8 ? k - 1 : 7); i++) c += mod_limb(k - i);
+    return c;
+}
+template <bool REDUCE>
+ZKSC_DEV uint32_t mul_ps(uint32_t* out, const Fr& a, const Fr& b) {
     using namespace ptx;
-    X[pos + 0] = CARRY_IN ? madc_lo_cc(x, v0, X[pos + 0]) : mad_lo_cc(x, v0, X[pos + 0]);
-    X[pos + 1] = madc_hi_cc(x, v0, X[pos + 1]);
-    X[pos + 2] = madc_lo_cc(x, v2, X[pos + 2]); X[pos + 3] = madc_hi_cc(x, v2, X[pos + 3]);
-    X[pos + 4] = madc_lo_cc(x, v4, X[pos + 4]); X[pos + 5] = madc_hi_cc(x, v4, X[pos + 5]);
-    X[pos + 6] = madc_lo_cc(x, v6, X[pos + 6]); X[pos + 7] = madc_hi_cc(x, v6, X[pos + 7]);
-    X[pos + 8] = addc(X[pos + 8], 0u);
-}
-
-// 512-bit product a*b, any a, b < 2^256, as E + O (O[p] has weight 2^(32p), O[0] unused = 0).
-ZKSC_DEV void mul_wide_eo(uint32_t (&E)[17], uint32_t (&O)[17], const Fr& a, const Fr& b) {
+    // modulus limbs as immediates: IMAD.WIDE.U32 takes an immediate operand, no registers spent
+    const uint32_t p[8] = {ZKSC_P0, ZKSC_P1, ZKSC_P2, ZKSC_P3, ZKSC_P4, ZKSC_P5, ZKSC_P6, ZKSC_P7};
+    uint32_t q[8];
+    uint32_t lo = 0, hi = 0, cn = 0;
 #pragma unroll
-    for (int i = 0; i < 17; i++) { E[i] = 0; O[i] = 0; }
+    for (int k = 0; k < 15; k++) {
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-        uint32_t* A = (i & 1) ? O : E;
-        uint32_t* B = (i & 1) ? E : O;
-        chain4<false>(A, i, a.l[0], a.l[2], a.l[4], a.l[6], b.l[i]);
-        chain4<false>(B, i + 1, a.l[1], a.l[3], a.l[5], a.l[7], b.l[i]);
-    }
-}
-// T = E + (O) merged into 16 limbs (the product fits 512 bits)
-ZKSC_DEV void merge_eo(uint32_t (&T)[16], const uint32_t (&E)[17], const uint32_t (&O)[17]) {
-    T[0] = E[0];
-    T[1] = ptx::add_cc(E[1], O[1]);
-#pragma unroll
-    for (int i = 2; i < 15; i++) T[i] = ptx::addc_cc(E[i], O[i]);
-    T[15] = ptx::addc(E[15], O[15]);
-}
-ZKSC_DEV void mul_wide(uint32_t (&T)[16], const Fr& a, const Fr& b) {
-    uint32_t E[17], O[17];
-    mul_wide_eo(E, O, a, b);
-    merge_eo(T, E, O);
-}
-
-// ---- Montgomery multiplication (CIOS, even/odd) --------------------------------------------------
-// Row i adds a*b_i and then m_i*r at base position i, with m_i = -(limb i of the running total)
-// because -r^-1 = -1 mod 2^32.  Limb i of the total is E[i] + O[i] + k, k being the carry produced
-// when limb i-1 was cancelled; k enters the m*r chain as its carry-in.
-// Inputs: a < 2^256 arbitrary, b < 2^256 arbitrary with a*b < r*2^256 for a result < 2r.
-// Returns the (up to) 9-limb result a*b*2^-256 + (multiple of r), limbs 8..16 of the total.
-ZKSC_DEV void mont_mul_raw(uint32_t (&res)[8], uint32_t& top, const Fr& a, const Fr& b) {
-    using namespace ptx;
-    uint32_t E[18], O[18];
-#pragma unroll
-    for (int i = 0; i < 18; i++) { E[i] = 0; O[i] = 0; }
-    // The modulus limbs must sit in ordinary registers: with immediates or uniform registers ptxas
-    // does not fuse the lo/hi pair into IMAD.WIDE (checked in SASS), which doubles the multiplies.
-    uint32_t m0, m1, m2, m3, m4, m5, m6, m7;
-    load_modulus(m0, m1, m2, m3, m4, m5, m6, m7);
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        uint32_t* A = (i & 1) ? O : E;
-        uint32_t* B = (i & 1) ? E : O;
-        chain4<false>(A, i, a.l[0], a.l[2], a.l[4], a.l[6], b.l[i]);
-        chain4<false>(B, i + 1, a.l[1], a.l[3], a.l[5], a.l[7], b.l[i]);
-        if (i == 0) {
-            const uint32_t m = 0u - E[0];
-            chain4<false>(A, i, m0, m2, m4, m6, m);
-            chain4<false>(B, i + 1, m1, m3, m5, m7, m);
-        } else {
-            (void)add_cc(E[i - 1], O[i - 1]);           // limb i-1 is 0 mod 2^32; CF = k_{i-1}
-            const uint32_t t = addc(E[i], O[i]);
-            const uint32_t m = 0u - t;
-            chain4<true>(A, i, m0, m2, m4, m6, m);      // k_{i-1} enters here
-            chain4<false>(B, i + 1, m1, m3, m5, m7, m);
+        for (int i = (k > 7 ? k - 7 : 0); i <= (k < 7 ? k : 7); i++) {
+            lo = mad_lo_cc(a.l[i], b.l[k - i], lo);
+            hi = madc_hi_cc(a.l[i], b.l[k - i], hi);
+            cn = addc(cn, 0u);
         }
-    }
-    (void)add_cc(O[7], E[7]);                           // k_7
+        if (REDUCE) {
 #pragma unroll
-    for (int i = 0; i < 8; i++) res[i] = addc_cc(E[8 + i], O[8 + i]);
-    top = addc(E[16], O[16]);
+            for (int i = (k > 7 ? k - 7 : 0); i <= (k < 8 ? k - 1 : 7); i++) {
+#ifndef ZKSC_NO_P1_TRICK
+                if (k - i == 1) {
+                    // p_1 = 2^32 - 1:  q * p_1 = (q << 32) - q, five adds on the (idle) ALU pipe instead of
+                    // one more IMAD.WIDE on the multiplier pipe that bounds the kernel
+                    hi = add_cc(hi, q[i]);
+                    cn = addc(cn, 0u);
+                    lo = sub_cc(lo, q[i]);
+                    hi = subc_cc(hi, 0u);
+                    cn = subc(cn, 0u);
+                    continue;
+                }
+#endif
+                lo = mad_lo_cc(q[i], p[k - i], lo);
+                hi = madc_hi_cc(q[i], p[k - i], hi);
+                cn = addc(cn, 0u);
+            }
+            if (k > 0) {
+                const unsigned long long c = mod_column_constant(k);
+                lo = add_cc(lo, (uint32_t)c);
+                hi = addc_cc(hi, (uint32_t)(c >> 32));
+                cn = addc(cn, 0u);
+            }
+            if (k < 8) {
+                q[k] = ~lo;                 // lo + q + 1 == 2^32: limb cleared, carry one
+                hi = add_cc(hi, 1u);
+                cn = addc(cn, 0u);
+            } else {
+                out[k - 8] = lo;
+            }
+        } else {
+            out[k] = lo;
+        }
+        lo = hi; hi = cn; cn = 0;
+    }
+    if (REDUCE) { out[7] = lo; return hi; }
+    out[15] = lo;
+    return 0;
 }
 
 // Montgomery product, canonical result.  a, b < r.
 ZKSC_DEV Fr fr_mul(const Fr& a, const Fr& b) {
     Fr o;
-    uint32_t top;
-    mont_mul_raw(o.l, top, a, b);   // < 2r < 2^256: top == 0
+    (void)mul_ps<true>(o.l, a, b);   // < 2r < 2^256: top == 0
     cond_sub_r(o.l);
     return o;
 }
+// 512-bit product a*b, any a, b < 2^256
+ZKSC_DEV void mul_wide(uint32_t (&T)[16], const Fr& a, const Fr& b) { (void)mul_ps<false>(T, a, b); }
 
 // Montgomery reduction of a 16-limb T (any T < 2^512): (T + M r) / 2^256, 8 limbs + top.
 // Only used on the once-per-block slow path and in tests.
@@ -298,7 +275,7 @@ ZKSC_DEV void redc_rows(uint32_t (&T)[16], uint32_t& top) {
 #pragma unroll
         for (int j = 0; j < 8; j++) {
             // T[i+j] += lo, T[i+j+1] += hi  (plain 64-bit accumulation; clarity over speed)
-            unsigned long long w = (unsigned long long)m * kModulus[j] + T[i + j] + c;
+            unsigned long long w = (unsigned long long)m * mod_limb(j) + T[i + j] + c;
             T[i + j] = (uint32_t)w;
             c = (uint32_t)(w >> 32);
         }

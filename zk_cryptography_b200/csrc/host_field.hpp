@@ -294,11 +294,65 @@ struct SparseUnivariatePolynomial {
             if (result[k] != kZero) p.monomial.push_back({result[k], from_u64(k)});
         return p;
     }
-    // evaluations at x = 0..d  (sumcheck/src/utils.rs:29-35 convert_round_poly_to_uni_poly_format)
+    // Dense coefficients of the interpolant through (0, ys[0]) .. (d, ys[d]).  Same field values as
+    // `interpolation` (the interpolant is unique); the d+1 inverse denominators prod_{j != i}(i - j) depend
+    // on d only and are computed once (the general routine pays one Fermat inversion per basis polynomial,
+    // ~10 us each -- too slow for a per-round host step).
+    static std::vector<FrH> dense_interpolate_evals(const std::vector<FrH>& ys) {
+        const size_t n = ys.size();
+        static std::vector<std::vector<FrH>> inv_denoms(64);
+        if (n >= inv_denoms.size()) {
+            std::vector<FrH> xs;
+            for (size_t i = 0; i < n; i++) xs.push_back(from_u64(i));
+            SparseUnivariatePolynomial sp = interpolation(xs, ys);
+            std::vector<FrH> dense(n, kZero);
+            for (const auto& m : sp.monomial) { uint64_t e[4]; to_canonical(m.pow, e); dense[e[0]] = m.coeff; }
+            return dense;
+        }
+        std::vector<FrH>& inv = inv_denoms[n];
+        if (inv.size() != n) {
+            inv.assign(n, kOne);
+            for (size_t i = 0; i < n; i++) {
+                FrH denom = kOne;
+                for (size_t j = 0; j < n; j++)
+                    if (j != i) denom = mul(denom, sub(from_u64(i), from_u64(j)));
+                inv[i] = inverse(denom);
+            }
+        }
+        std::vector<FrH> result(n, kZero);
+        std::vector<FrH> l, nl;
+        for (size_t i = 0; i < n; i++) {
+            l.assign(1, kOne);
+            for (size_t j = 0; j < n; j++) {
+                if (j == i) continue;
+                const FrH xj = from_u64(j);
+                nl.assign(l.size() + 1, kZero);
+                for (size_t k = 0; k < l.size(); k++) {
+                    nl[k] = sub(nl[k], mul(l[k], xj));
+                    nl[k + 1] = add(nl[k + 1], l[k]);
+                }
+                l.swap(nl);
+            }
+            FrH scale = mul(inv[i], ys[i]);
+            for (size_t k = 0; k < l.size(); k++) result[k] = add(result[k], mul(l[k], scale));
+        }
+        return result;
+    }
+    // evaluations at x = 0..d  (sumcheck/src/utils.rs:29-35 convert_round_poly_to_uni_poly_format) ->
+    // SparseUnivariatePolynomial::interpolation (:40-63): monomials with a zero coefficient are dropped (:52-60)
     static SparseUnivariatePolynomial interpolate_evals(const std::vector<FrH>& ys) {
-        std::vector<FrH> xs;
-        for (size_t i = 0; i < ys.size(); i++) xs.push_back(from_u64(i));
-        return interpolation(xs, ys);
+        std::vector<FrH> dense = dense_interpolate_evals(ys);
+        SparseUnivariatePolynomial p;
+        for (size_t k = 0; k < dense.size(); k++)
+            if (dense[k] != kZero) p.monomial.push_back({dense[k], from_u64(k)});
+        return p;
+    }
+    // value at `point` of the interpolant through (i, ys[i]): Horner on the dense coefficients
+    static FrH evaluate_evals_at(const std::vector<FrH>& ys, const FrH& point) {
+        std::vector<FrH> c = dense_interpolate_evals(ys);
+        FrH acc = kZero;
+        for (size_t k = c.size(); k-- > 0;) acc = add(mul(acc, point), c[k]);
+        return acc;
     }
 
     // :90-106  sum coeff * point^pow (pow is a field element used as a 256-bit exponent)

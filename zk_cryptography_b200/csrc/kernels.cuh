@@ -10,6 +10,10 @@
 // so that every round is ONE pass over HBM: read T_{j-1} (4 entries per table per thread), write
 // T_j (2 entries), and accumulate the d+1 evaluations of round j from the two freshly folded entries.
 //
+// SKIP1: evaluation point 1 is not computed: the host derives it as h(1) = claim - h(0), where claim is
+// the previous round polynomial at the previous challenge (the identity the verifier checks), which is
+// exact field arithmetic and therefore bit-identical -- one product fewer per pair.
+//
 // Variable 0 is the most significant index bit (polynomial/src/utils.rs:26-53 with index 0): round j
 // pairs entry x with x + N_j/2.
 #pragma once
@@ -32,7 +36,7 @@ struct RoundArgs {
     unsigned int* counters;    // [proof], zero on entry, zero on exit
     Fr* result;                // [proof][res_stride]: npts Montgomery elements each
     unsigned int res_stride;
-    unsigned int npts;         // number of evaluation points wanted (<= D+1)
+    unsigned int npts;         // evaluation points 0..npts-1 are wanted (<= D+1); SKIP1 kernels leave point 1 untouched
     volatile unsigned int* flag;  // optional: set to flag_value (system scope) after the results
     unsigned int flag_value;
     Fr chal[kMaxBatch];        // FOLD: challenge of the previous round, Montgomery form, per proof
@@ -72,8 +76,10 @@ ZKSC_DEV Fr acc_finish(const Acc<NL>& a) {
 
 // Block-level reduction of NP accumulators, publication of the block partial, and -- in the last
 // block of each proof to arrive -- the final cross-block sum.
-template <int NL, int NP>
+// Accumulator slot s holds evaluation point s, or with SKIP1 point (s == 0 ? 0 : s + 1).
+template <int NL, int NP, bool SKIP1>
 ZKSC_DEV void reduce_and_publish(Acc<NL> (&acc)[NP], const RoundArgs& args, int npts) {
+    auto point_of = [](int slot) { return (SKIP1 && slot > 0) ? slot + 1 : slot; };
     __shared__ Acc<NL> s_warp[kWarps][NP];
     __shared__ bool s_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -92,7 +98,7 @@ ZKSC_DEV void reduce_and_publish(Acc<NL> (&acc)[NP], const RoundArgs& args, int 
             if (lane < kWarps) a = s_warp[lane][p];
             else acc_zero(a);
             acc_warp_reduce(a);
-            if (lane == 0 && p < npts) {
+            if (lane == 0 && point_of(p) < npts) {
                 Fr v = acc_finish<NL>(a);
                 st256(my_partials + p, v);
             }
@@ -108,7 +114,8 @@ ZKSC_DEV void reduce_and_publish(Acc<NL> (&acc)[NP], const RoundArgs& args, int 
     __threadfence();
     // last block of this proof: sum the per-block partials (canonical Montgomery elements)
     const Fr* all = args.partials + (size_t)proof * gridDim.x * NP;
-    for (int p = warp; p < npts; p += kWarps) {
+    for (int p = warp; p < NP; p += kWarps) {
+        if (point_of(p) >= npts) continue;
         Acc<9> a;
         acc_zero(a);
         for (unsigned int blk = lane; blk < gridDim.x; blk += 32) {
@@ -118,7 +125,7 @@ ZKSC_DEV void reduce_and_publish(Acc<NL> (&acc)[NP], const RoundArgs& args, int 
         acc_warp_reduce(a);
         if (lane == 0) {
             Fr v = acc9_reduce(a);
-            st256(args.result + (size_t)proof * args.res_stride + p, v);
+            st256(args.result + (size_t)proof * args.res_stride + point_of(p), v);
         }
     }
     __syncthreads();
@@ -139,10 +146,10 @@ ZKSC_DEV void reduce_and_publish(Acc<NL> (&acc)[NP], const RoundArgs& args, int 
 
 // FOLD = false : evaluate the round polynomial of the tables as they are (first round).
 // FOLD = true  : bind the previous challenge (in -> out), then evaluate the next round on the result.
-template <int D, bool FOLD>
+template <int D, bool FOLD, bool SKIP1>
 __global__ void __launch_bounds__(kThreads) round_kernel(const __grid_constant__ RoundArgs args) {
     constexpr int NL = Lazy<D>::NL;
-    constexpr int NP = D + 1;
+    constexpr int NP = SKIP1 ? D : D + 1;   // accumulators
     const int proof = blockIdx.y;
     const Fr* in = args.in + (size_t)proof * args.in_proof_stride;
     Fr* out = args.out + (size_t)proof * args.out_proof_stride;
@@ -178,21 +185,21 @@ __global__ void __launch_bounds__(kThreads) round_kernel(const __grid_constant__
         }
         // evaluation points 0 and 1 are the two halves themselves
         accumulate_product<D>(acc[0], a);
-        if (npts > 1) accumulate_product<D>(acc[1], b);
-        if (npts > 2) {
+        if (!SKIP1 && npts > 1) accumulate_product<D>(acc[1], b);
+        if (D >= 2 && npts > 2) {
             // f_k(t) = a_k + t (b_k - a_k): walk t = 2..D by repeated addition of the difference
             Fr delta[D];
 #pragma unroll
             for (int k = 0; k < D; k++) delta[k] = fr_sub(b[k], a[k]);
 #pragma unroll
-            for (int p = 2; p < NP; p++) {
+            for (int p = 2; p <= D; p++) {
 #pragma unroll
                 for (int k = 0; k < D; k++) b[k] = fr_add(b[k], delta[k]);
-                if (p < npts) accumulate_product<D>(acc[p], b);
+                if (p < npts) accumulate_product<D>(acc[SKIP1 ? p - 1 : p], b);
             }
         }
     }
-    reduce_and_publish<NL, NP>(acc, args, npts);
+    reduce_and_publish<NL, NP, SKIP1>(acc, args, npts);
 }
 
 }  // namespace zksc

@@ -77,12 +77,18 @@ struct zksc_ctx {
     Fr* results_send = nullptr;  // [kMaxBatch * kMaxEvals]
     Fr* results_host = nullptr;  // pinned mirror of results_dev
     size_t results_cap = 0;      // elements per rank slot
-    int occ[kMaxDegree + 1][2];
+    int occ[kMaxDegree + 1][3];   // resident CTAs per SM of round_kernel<D, variant>
     std::string err;
     int rank = 0, n_ranks = 1;
 #if ZKSC_HAVE_NCCL_H
     ncclComm_t comm = nullptr;
 #endif
+    // measurement (bench.py): kernels launched so far, and optional per-launch CUDA-event timing
+    unsigned long long launches = 0;
+    bool timing = false;
+    struct LaunchRec { cudaEvent_t e0, e1; unsigned int degree, fold; unsigned long long pairs, proofs; };
+    std::vector<LaunchRec> recs;       // used entries: [0, n_recs)
+    size_t n_recs = 0;
 };
 
 struct zksc_tables {
@@ -99,6 +105,17 @@ struct zksc_tables {
     int where;               // 0 orig, 1 work, 2 tail
     bool pending;
     std::vector<Fr> pending_chal;
+    // round-0 evaluations computed by zksc_poly_sum, handed to the next round-0 zksc_round_evals once
+    // (calculate_poly_sum followed by prove is the reference's calling pattern; the input is immutable)
+    std::vector<uint64_t> r0_cache;
+    bool r0_valid = false;
+    // The evaluations returned by the latest zksc_round_evals (valid until the next bind) and, after a
+    // bind that followed them, the per-product claims h_p(r) = h_p,next(0) + h_p,next(1): with a claim the
+    // next round's kernel skips evaluation point 1 and the host fills in h(1) = claim - h(0).
+    std::vector<uint64_t> last_evals;   // [B][E][4]
+    bool last_evals_valid = false;
+    std::vector<FrH> claim;             // [B][P]
+    bool claim_valid = false;
 };
 
 #define CK(call)                                                                                          \
@@ -137,8 +154,8 @@ extern "C" int zksc_device_count(void) {
 
 // per-degree launchers live in round_inst.cu (one object per degree, compiled in parallel)
 #define ZKSC_DECL_ROUND(D)                                                                   \
-    void zksc_launch_round_##D(bool fold, dim3 grid, cudaStream_t s, const RoundArgs& a);     \
-    int zksc_occ_round_##D(bool fold);
+    void zksc_launch_round_##D(int variant, dim3 grid, cudaStream_t s, const RoundArgs& a);   \
+    int zksc_occ_round_##D(int variant);
 ZKSC_DECL_ROUND(1) ZKSC_DECL_ROUND(2) ZKSC_DECL_ROUND(3) ZKSC_DECL_ROUND(4)
 ZKSC_DECL_ROUND(5) ZKSC_DECL_ROUND(6) ZKSC_DECL_ROUND(7) ZKSC_DECL_ROUND(8)
 
@@ -165,7 +182,7 @@ extern "C" int zksc_ctx_create(int device, zksc_ctx** out) {
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
     if ((e = cudaMalloc(&ctx->counters, (kMaxBatch + 1) * sizeof(unsigned int))) != cudaSuccess) return fail(e, "cudaMalloc");
     if ((e = cudaMemset(ctx->counters, 0, (kMaxBatch + 1) * sizeof(unsigned int))) != cudaSuccess) return fail(e, "cudaMemset");
-#define ZKSC_OCC(D) ctx->occ[D][0] = zksc_occ_round_##D(false); ctx->occ[D][1] = zksc_occ_round_##D(true);
+#define ZKSC_OCC(D) for (int v = 0; v < 3; v++) ctx->occ[D][v] = zksc_occ_round_##D(v);
     ZKSC_OCC(1) ZKSC_OCC(2) ZKSC_OCC(3) ZKSC_OCC(4) ZKSC_OCC(5) ZKSC_OCC(6) ZKSC_OCC(7) ZKSC_OCC(8)
     if ((e = cudaGetLastError()) != cudaSuccess) return fail(e, "occupancy query (is this an sm_100a device?)");
     *out = ctx;
@@ -179,6 +196,7 @@ extern "C" int zksc_ctx_destroy(zksc_ctx* ctx) {
 #if ZKSC_HAVE_NCCL_H
     if (ctx->comm) g_nccl.CommDestroy(ctx->comm);
 #endif
+    for (auto& r : ctx->recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     cudaFree(ctx->partials);
     cudaFree(ctx->counters);
     cudaFree(ctx->results_dev);
@@ -202,6 +220,59 @@ extern "C" int zksc_ctx_rank(const zksc_ctx* ctx, int* rank, int* n_ranks) {
     if (!ctx) return ZKSC_ERR_STATE;
     if (rank) *rank = ctx->rank;
     if (n_ranks) *n_ranks = ctx->n_ranks;
+    return ZKSC_OK;
+}
+
+extern "C" void* zksc_ctx_stream(zksc_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+extern "C" unsigned long long zksc_ctx_launch_count(const zksc_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int zksc_ctx_timing(zksc_ctx* ctx, int enable) {
+    if (!ctx) return ZKSC_ERR_STATE;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->timing = enable != 0;
+    ctx->n_recs = 0;
+    return ZKSC_OK;
+}
+
+extern "C" int zksc_ctx_timing_read(zksc_ctx* ctx, uint32_t cap, uint32_t* n_out, float* ms, uint32_t* degree, uint32_t* fold, uint64_t* pairs,
+                                    uint64_t* proofs) {
+    if (!ctx || !n_out) return ZKSC_ERR_STATE;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    uint32_t n = 0;
+    for (size_t i = 0; i < ctx->n_recs && n < cap; i++, n++) {
+        const auto& r = ctx->recs[i];
+        if (ms) CK(cudaEventElapsedTime(ms + n, r.e0, r.e1));
+        if (degree) degree[n] = r.degree;
+        if (fold) fold[n] = r.fold;
+        if (pairs) pairs[n] = r.pairs;
+        if (proofs) proofs[n] = r.proofs;
+    }
+    *n_out = n;
+    ctx->n_recs = 0;
+    return ZKSC_OK;
+}
+
+// bracket one round-kernel launch with events when timing is on
+static int timing_open(zksc_ctx* ctx, unsigned int degree, bool fold, unsigned long long pairs, unsigned long long proofs) {
+    if (!ctx->timing) return ZKSC_OK;
+    if (ctx->n_recs == ctx->recs.size()) {
+        zksc_ctx::LaunchRec r{};
+        CK(cudaEventCreate(&r.e0));
+        CK(cudaEventCreate(&r.e1));
+        ctx->recs.push_back(r);
+    }
+    auto& r = ctx->recs[ctx->n_recs];
+    r.degree = degree; r.fold = fold ? 1u : 0u; r.pairs = pairs; r.proofs = proofs;
+    CK(cudaEventRecord(r.e0, ctx->stream));
+    return ZKSC_OK;
+}
+static int timing_close(zksc_ctx* ctx) {
+    if (!ctx->timing) return ZKSC_OK;
+    CK(cudaEventRecord(ctx->recs[ctx->n_recs].e1, ctx->stream));
+    ctx->n_recs++;
     return ZKSC_OK;
 }
 
@@ -263,6 +334,11 @@ static int ensure_partials(zksc_ctx* ctx, size_t elems) {
     return ZKSC_OK;
 }
 
+struct DevBuf {
+    Fr* p = nullptr;
+    ~DevBuf() { cudaFree(p); }
+};
+
 // ------------------------------------------------------------------------------------------------
 // tables
 // ------------------------------------------------------------------------------------------------
@@ -312,6 +388,8 @@ extern "C" int zksc_tables_reset(zksc_tables* t) {
     t->where = 0;
     t->pending = false;
     t->pending_chal.clear();
+    t->last_evals_valid = false;
+    t->claim_valid = false;
     return ZKSC_OK;
 }
 
@@ -343,36 +421,71 @@ static inline int grid_for(const zksc_ctx* ctx, unsigned long long n, int thread
     return (int)blocks;
 }
 
+// copy (and, on a sharded context, stride-pick) the caller's full tables into t->orig
+static int upload_into(zksc_tables* t, const uint64_t* const* host_tables, bool local) {
+    zksc_ctx* ctx = t->ctx;
+    CK(cudaSetDevice(ctx->device));
+    t->r0_valid = false;
+    const uint64_t N = 1ull << t->n_vars;
+    const size_t n_tabs = (size_t)t->B * t->Dtot;
+    if (ctx->n_ranks == 1 || local) {
+        const uint64_t NL = t->n_local0;
+        for (size_t i = 0; i < n_tabs; i++) CK(cudaMemcpyAsync(t->orig + i * NL, host_tables[i], NL * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        // stage one full table at a time, keep the entries with index = rank (mod n_ranks)
+        DevBuf stage;
+        CK(cudaMalloc(&stage.p, N * sizeof(Fr)));
+        for (size_t i = 0; i < n_tabs; i++) {
+            CK(cudaMemcpyAsync(stage.p, host_tables[i], N * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+            pick_shard_kernel<<<grid_for(ctx, t->n_local0, 256, 8), 256, 0, ctx->stream>>>(stage.p, t->orig + i * t->n_local0, t->n_local0, ctx->n_ranks, ctx->rank);
+            ctx->launches++;
+            CK(cudaGetLastError());
+        }
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));  // host buffers are only borrowed for the call
+    return ZKSC_OK;
+}
+
 extern "C" int zksc_tables_upload(zksc_ctx* ctx, uint32_t n_vars, uint32_t n_proofs, uint32_t n_products, const uint32_t* degree,
                                   const uint64_t* const* host_tables, zksc_tables** out) {
     if (!ctx) return ZKSC_ERR_STATE;
     if (!host_tables) FAIL(ZKSC_ERR_SHAPE, "host_tables is NULL");
     zksc_tables* t = nullptr;
     TRY(tables_alloc(ctx, n_vars, n_proofs, n_products, degree, &t));
-    const uint64_t N = 1ull << n_vars;
-    const size_t n_tabs = (size_t)t->B * t->Dtot;
-    if (ctx->n_ranks == 1) {
-        for (size_t i = 0; i < n_tabs; i++) {
-            cudaError_t e = cudaMemcpyAsync(t->orig + i * N, host_tables[i], N * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream);
-            if (e != cudaSuccess) { zksc_tables_free(t); ctx->err = std::string("H2D: ") + cudaGetErrorString(e); return ZKSC_ERR_CUDA; }
-        }
-    } else {
-        Fr* stage = nullptr;
-        cudaError_t e = cudaMalloc(&stage, N * sizeof(Fr));
-        if (e != cudaSuccess) { zksc_tables_free(t); ctx->err = "cudaMalloc(upload staging)"; cudaGetLastError(); return ZKSC_ERR_OOM; }
-        for (size_t i = 0; i < n_tabs && e == cudaSuccess; i++) {
-            e = cudaMemcpyAsync(stage, host_tables[i], N * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream);
-            if (e != cudaSuccess) break;
-            pick_shard_kernel<<<grid_for(ctx, t->n_local0, 256, 8), 256, 0, ctx->stream>>>(stage, t->orig + i * t->n_local0, t->n_local0, ctx->n_ranks, ctx->rank);
-            e = cudaGetLastError();
-        }
-        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-        cudaFree(stage);
-        if (e != cudaSuccess) { zksc_tables_free(t); ctx->err = std::string("sharded upload: ") + cudaGetErrorString(e); return ZKSC_ERR_CUDA; }
-    }
-    cudaError_t e = cudaStreamSynchronize(ctx->stream);  // host buffers are only borrowed for the call
-    if (e != cudaSuccess) { zksc_tables_free(t); ctx->err = std::string("upload: ") + cudaGetErrorString(e); return ZKSC_ERR_CUDA; }
+    int rc = upload_into(t, host_tables, false);
+    if (rc != ZKSC_OK) { std::string keep = ctx->err; zksc_tables_free(t); ctx->err = keep; return rc; }
     *out = t;
+    return ZKSC_OK;
+}
+
+extern "C" int zksc_tables_upload_local(zksc_ctx* ctx, uint32_t n_vars, uint32_t n_proofs, uint32_t n_products, const uint32_t* degree,
+                                        const uint64_t* const* host_local_tables, zksc_tables** out) {
+    if (!ctx) return ZKSC_ERR_STATE;
+    if (!host_local_tables) FAIL(ZKSC_ERR_SHAPE, "host_local_tables is NULL");
+    zksc_tables* t = nullptr;
+    TRY(tables_alloc(ctx, n_vars, n_proofs, n_products, degree, &t));
+    int rc = upload_into(t, host_local_tables, true);
+    if (rc != ZKSC_OK) { std::string keep = ctx->err; zksc_tables_free(t); ctx->err = keep; return rc; }
+    *out = t;
+    return ZKSC_OK;
+}
+
+extern "C" int zksc_tables_reupload(zksc_tables* t, const uint64_t* const* host_tables, int local) {
+    if (!t) return ZKSC_ERR_STATE;
+    zksc_ctx* ctx = t->ctx;
+    if (!host_tables) FAIL(ZKSC_ERR_SHAPE, "host_tables is NULL");
+    zksc_tables_reset(t);
+    return upload_into(t, host_tables, local != 0);
+}
+
+extern "C" int zksc_tables_read_local(zksc_tables* t, uint64_t* out) {
+    if (!t || !out) return ZKSC_ERR_STATE;
+    zksc_ctx* ctx = t->ctx;
+    CK(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)t->B * t->Dtot * t->n_local0;
+    CK(cudaMemcpyAsync(out, t->orig, n * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return ZKSC_OK;
 }
 
@@ -385,6 +498,7 @@ extern "C" int zksc_tables_synth(zksc_ctx* ctx, uint32_t n_vars, uint32_t n_proo
         for (uint32_t k = 0; k < t->Dtot; k++) {
             synth_kernel<<<grid_for(ctx, t->n_local0, 256, 8), 256, 0, ctx->stream>>>(t->orig + ((size_t)b * t->Dtot + k) * t->n_local0, t->n_local0,
                                                                                         seed + b, k, ctx->rank, ctx->n_ranks);
+            ctx->launches++;
         }
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
@@ -426,6 +540,7 @@ static int flush_pending(zksc_tables* t) {
         for (uint32_t b = 0; b < nb; b++) a.chal[b] = t->pending_chal[b0 + b];
         dim3 grid(grid_for(ctx, a.n_out, 256, 8), nb);
         fold_kernel<<<grid, 256, 0, ctx->stream>>>(a);
+        ctx->launches++;
     }
     CK(cudaGetLastError());
     t->where = to;
@@ -466,9 +581,11 @@ static int gather_tail(zksc_tables* t) {
     TRY(ensure_results(ctx, nt));
     Geo g = geo_of(t, t->where);
     tail_collect_kernel<<<(nt + 127) / 128, 128, 0, ctx->stream>>>(g.base, g.tab_stride, ctx->results_send, nt);
+    ctx->launches++;
     CK(cudaGetLastError());
     NCCLCK(g_nccl.AllGather(ctx->results_send, ctx->results_dev, (size_t)nt * sizeof(Fr), ncclUint8, ctx->comm, ctx->stream));
     tail_scatter_kernel<<<(nt * ctx->n_ranks + 127) / 128, 128, 0, ctx->stream>>>(ctx->results_dev, t->tail, nt, ctx->n_ranks);
+    ctx->launches++;
     CK(cudaGetLastError());
     t->where = 2;
     t->cur_n = ctx->n_ranks;
@@ -483,6 +600,13 @@ static int round_evals_impl(zksc_tables* t, uint64_t* out, uint32_t npts_cap) {
     zksc_ctx* ctx = t->ctx;
     CK(cudaSetDevice(ctx->device));
     if (t->vars_left == 0) FAIL(ZKSC_ERR_STATE, "all variables are bound");
+    if (t->r0_valid && t->vars_left == t->n_vars && !t->pending && npts_cap > ZKSC_MAX_DEGREE) {
+        memcpy(out, t->r0_cache.data(), t->r0_cache.size() * sizeof(uint64_t));
+        t->r0_valid = false;
+        t->last_evals = t->r0_cache;
+        t->last_evals_valid = true;
+        return ZKSC_OK;
+    }
     const bool sharded_phase = (ctx->n_ranks > 1 && t->where != 2);
     if (sharded_phase) {
         uint64_t n_after = t->pending ? t->cur_n / 2 : t->cur_n;
@@ -492,6 +616,9 @@ static int round_evals_impl(zksc_tables* t, uint64_t* out, uint32_t npts_cap) {
     uint64_t n_eval = t->pending ? t->cur_n / 2 : t->cur_n;  // table size of the round being evaluated
     if (n_eval < 2) FAIL(ZKSC_ERR_STATE, "no variable left to evaluate");
     const bool fold = t->pending;
+    const bool full = npts_cap > ZKSC_MAX_DEGREE;
+    const bool skip1 = fold && full && t->claim_valid;      // point 1 comes from the claim
+    const int variant = skip1 ? 2 : (fold ? 1 : 0);
     Geo gi = geo_of(t, t->where);
     int to = fold ? ((t->where == 0) ? 1 : t->where) : t->where;
     Geo go = geo_of(t, to);
@@ -502,7 +629,7 @@ static int round_evals_impl(zksc_tables* t, uint64_t* out, uint32_t npts_cap) {
         uint32_t nb = t->B - b0 < (uint32_t)kMaxBatch ? t->B - b0 : kMaxBatch;
         for (uint32_t p = 0; p < t->P; p++) {
             const int D = t->deg[p];
-            int gx = grid_for(ctx, half, kThreads, ctx->occ[D][fold ? 1 : 0]);
+            int gx = grid_for(ctx, half, kThreads, ctx->occ[D][variant]);
             TRY(ensure_partials(ctx, (size_t)nb * gx * (D + 1)));
             RoundArgs a;
             a.in = gi.base + (size_t)b0 * gi.proof_stride + (size_t)t->koff[p] * gi.tab_stride;
@@ -517,17 +644,20 @@ static int round_evals_impl(zksc_tables* t, uint64_t* out, uint32_t npts_cap) {
             a.flag = nullptr; a.flag_value = 0;
             if (fold) for (uint32_t b = 0; b < nb; b++) a.chal[b] = t->pending_chal[b0 + b];
             dim3 grid(gx, nb);
+            TRY(timing_open(ctx, D, fold, half, nb));
             switch (D) {
-                case 1: zksc_launch_round_1(fold, grid, ctx->stream, a); break;
-                case 2: zksc_launch_round_2(fold, grid, ctx->stream, a); break;
-                case 3: zksc_launch_round_3(fold, grid, ctx->stream, a); break;
-                case 4: zksc_launch_round_4(fold, grid, ctx->stream, a); break;
-                case 5: zksc_launch_round_5(fold, grid, ctx->stream, a); break;
-                case 6: zksc_launch_round_6(fold, grid, ctx->stream, a); break;
-                case 7: zksc_launch_round_7(fold, grid, ctx->stream, a); break;
-                case 8: zksc_launch_round_8(fold, grid, ctx->stream, a); break;
+                case 1: zksc_launch_round_1(variant, grid, ctx->stream, a); break;
+                case 2: zksc_launch_round_2(variant, grid, ctx->stream, a); break;
+                case 3: zksc_launch_round_3(variant, grid, ctx->stream, a); break;
+                case 4: zksc_launch_round_4(variant, grid, ctx->stream, a); break;
+                case 5: zksc_launch_round_5(variant, grid, ctx->stream, a); break;
+                case 6: zksc_launch_round_6(variant, grid, ctx->stream, a); break;
+                case 7: zksc_launch_round_7(variant, grid, ctx->stream, a); break;
+                case 8: zksc_launch_round_8(variant, grid, ctx->stream, a); break;
                 default: FAIL(ZKSC_ERR_UNSUPPORTED, "degree");
             }
+            TRY(timing_close(ctx));
+            ctx->launches++;
             CK(cudaGetLastError());
         }
     }
@@ -552,6 +682,19 @@ static int round_evals_impl(zksc_tables* t, uint64_t* out, uint32_t npts_cap) {
         }
 #endif
     }
+    if (skip1) {
+        // h_p(1) = claim_p - h_p(0)   (what the verifier checks; exact in the field)
+        for (uint32_t b = 0; b < t->B; b++)
+            for (uint32_t p = 0; p < t->P; p++) {
+                uint64_t* e = out + ((size_t)b * t->E + t->eoff[p]) * 4;
+                store_h(e + 4, host::sub(t->claim[(size_t)b * t->P + p], load_h(e)));
+            }
+    }
+    t->claim_valid = false;
+    if (full) {
+        t->last_evals.assign(out, out + n_res * 4);
+        t->last_evals_valid = true;
+    }
     return ZKSC_OK;
 }
 
@@ -574,6 +717,20 @@ extern "C" int zksc_bind(zksc_tables* t, const uint64_t* challenges) {
     for (uint32_t b = 0; b < t->B; b++) memcpy(t->pending_chal[b].l, challenges + 4 * b, 32);
     t->pending = true;
     t->vars_left--;
+    // claim for the next round: this round's polynomial of every product at the challenge
+    t->claim_valid = false;
+    if (t->last_evals_valid) {
+        t->claim.resize((size_t)t->B * t->P);
+        std::vector<FrH> ys;
+        for (uint32_t b = 0; b < t->B; b++)
+            for (uint32_t p = 0; p < t->P; p++) {
+                ys.clear();
+                for (uint32_t i = 0; i <= t->deg[p]; i++) ys.push_back(load_h(&t->last_evals[((size_t)b * t->E + t->eoff[p] + i) * 4]));
+                t->claim[(size_t)b * t->P + p] = host::SparseUnivariatePolynomial::evaluate_evals_at(ys, load_h(challenges + 4 * b));
+            }
+        t->claim_valid = true;
+    }
+    t->last_evals_valid = false;
     return ZKSC_OK;
 }
 
@@ -615,7 +772,8 @@ extern "C" int zksc_poly_sum(zksc_tables* t, uint64_t* out) {
         }
         return ZKSC_OK;
     }
-    TRY(round_evals_impl(t, ev.data(), 2));
+    t->r0_valid = false;
+    TRY(round_evals_impl(t, ev.data(), ZKSC_MAX_DEGREE + 1));
     for (uint32_t b = 0; b < t->B; b++) {
         FrH s = host::kZero;
         for (uint32_t p = 0; p < t->P; p++) {
@@ -625,6 +783,8 @@ extern "C" int zksc_poly_sum(zksc_tables* t, uint64_t* out) {
         store_h(out + 4 * b, s);
     }
     zksc_tables_reset(t);
+    t->r0_cache = ev;
+    t->r0_valid = true;
     return ZKSC_OK;
 }
 
@@ -642,6 +802,7 @@ extern "C" int zksc_tables_to_bytes(zksc_tables* t, uint32_t proof, uint8_t* out
         const Fr* src = t->orig + ((size_t)proof * t->Dtot + k) * N;
         for (uint64_t off = 0; off < N; off += chunk) {
             to_bytes_kernel<<<grid_for(ctx, chunk, 256, 8), 256, 0, ctx->stream>>>(src + off, tmp, chunk);
+            ctx->launches++;
             cudaError_t e = cudaMemcpyAsync(out + ((size_t)k * N + off) * 32, tmp, chunk * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream);
             if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
             if (e != cudaSuccess) { cudaFree(tmp); ctx->err = std::string("to_bytes: ") + cudaGetErrorString(e); return ZKSC_ERR_CUDA; }
@@ -821,10 +982,6 @@ extern "C" int zksc_evaluate(zksc_tables* t, const uint64_t* points, uint64_t* o
 // ------------------------------------------------------------------------------------------------
 // stand-alone Multilinear operations
 // ------------------------------------------------------------------------------------------------
-struct DevBuf {
-    Fr* p = nullptr;
-    ~DevBuf() { cudaFree(p); }
-};
 
 extern "C" int zksc_ml_partial_evaluation(zksc_ctx* ctx, const uint64_t* evals, uint64_t n, const uint64_t* r, uint32_t variable_index, uint64_t* out) {
     if (!ctx) return ZKSC_ERR_STATE;
@@ -842,6 +999,7 @@ extern "C" int zksc_ml_partial_evaluation(zksc_ctx* ctx, const uint64_t* evals, 
     a.n_out = n / 2; a.s = n >> (variable_index + 1); a.n_tabs = 1;
     memcpy(a.chal[0].l, r, 32);
     fold_kernel<<<dim3(grid_for(ctx, a.n_out, 256, 8), 1), 256, 0, ctx->stream>>>(a);
+    ctx->launches++;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out, o.p, n / 2 * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -865,6 +1023,7 @@ extern "C" int zksc_ml_evaluation(zksc_ctx* ctx, const uint64_t* evals, uint64_t
         a.n_out = cur / 2; a.s = cur / 2; a.n_tabs = 1;
         memcpy(a.chal[0].l, points + 4 * j, 32);
         fold_kernel<<<dim3(grid_for(ctx, a.n_out, 256, 8), 1), 256, 0, ctx->stream>>>(a);
+        ctx->launches++;
         cur /= 2;
     }
     CK(cudaGetLastError());
@@ -886,6 +1045,7 @@ extern "C" int zksc_ml_outer(zksc_ctx* ctx, int mul, const uint64_t* a, uint64_t
     CK(cudaMemcpyAsync(da.p, a, na * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(db.p, b, nb * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
     outer_kernel<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(mul, da.p, na, db.p, nb, dout.p);
+    ctx->launches++;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out, dout.p, n * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -905,6 +1065,7 @@ extern "C" int zksc_ml_elementwise(zksc_ctx* ctx, int op, const uint64_t* a, con
     CK(cudaMemcpyAsync(da.p, a, n * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(db.p, b, nb * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
     ew_kernel<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(op, da.p, db.p, dout.p, n);
+    ctx->launches++;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out, dout.p, n * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
