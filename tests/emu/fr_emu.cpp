@@ -35,3 +35,8 @@ extern "C" void emu_mul_ps_mont(const uint32_t* a, const uint32_t* b, uint32_t* 
     Fr x, y; memcpy(x.l, a, 32); memcpy(y.l, b, 32);
     uint32_t res[8]; uint32_t top = mul_ps<true>(res, x, y); memcpy(out9, res, 32); out9[8] = top;
 }
+extern "C" void emu_mont_mul_rows(const uint32_t* a, const uint32_t* b, uint32_t* out9) {
+    Fr x, y; memcpy(x.l, a, 32); memcpy(y.l, b, 32);
+    uint32_t res[8], top; mont_mul_rows(res, top, x, y); memcpy(out9, res, 32); out9[8] = top;
+}
+extern "C" void emu_cstar(uint32_t* out17) { for (int i = 0; i < 17; i++) out17[i] = cstar_limb(i); }

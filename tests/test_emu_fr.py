@@ -47,6 +47,12 @@ def test_constants(emu):
     assert val(one) == RR % R and val(r2) == RR * RR % R
 
 
+def test_complement_digit_constant(emu):
+    c = (ctypes.c_uint32 * 17)()
+    emu.emu_cstar(c)
+    assert val(c) == sum((R - 1 + 2**32) << (32 * i) for i in range(8))
+
+
 def test_limb_algorithms(emu):
     rng = random.Random(11)
     o8, o9, o16 = (ctypes.c_uint32 * 8)(), (ctypes.c_uint32 * 9)(), (ctypes.c_uint32 * 16)()
@@ -57,6 +63,9 @@ def test_limb_algorithms(emu):
         emu.emu_mul_ps_wide(arr(a, 8), arr(b, 8), o16)
         assert val(o16) == a * b
         emu.emu_mul_ps_mont(arr(a, 8), arr(b, 8), o9)
+        v = val(o9)
+        assert v % R == a * b * RINV % R and v < 2**256 + R
+        emu.emu_mont_mul_rows(arr(a, 8), arr(b, 8), o9)
         v = val(o9)
         assert v % R == a * b * RINV % R and v < 2**256 + R
         T = rnd(rng, 2**512)

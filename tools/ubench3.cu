@@ -7,7 +7,7 @@
 using namespace zksc;
 #define CHECK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); return 1; } } while (0)
 
-// MODE 0: fr_mul (row-wise, even/odd chains)   MODE 1: fr_mul_ps (product scanning)
+// MODE 0: first-generation row-wise multiplier   MODE 1: library fr_mul   MODE 4: product-scanning multiplier
 // MODE 2: mul_wide + acc17                     MODE 3: mul_ps<false> + acc17
 template <int MODE>
 __global__ void __launch_bounds__(128) fr_kernel(const Fr* in, Fr* out, int iters) {
@@ -18,9 +18,10 @@ __global__ void __launch_bounds__(128) fr_kernel(const Fr* in, Fr* out, int iter
         if (MODE == 0) x = rowwise::fr_mul(x, y);
         else if (MODE == 1) x = fr_mul(x, y);
         else if (MODE == 2) { uint32_t T[16]; rowwise::mul_wide(T, x, y); acc_add<17, 16>(acc, T); x.l[0] ^= T[3]; }
-        else { uint32_t T[16]; (void)mul_ps<false>(T, x, y); acc_add<17, 16>(acc, T); x.l[0] ^= T[3]; }
+        else if (MODE == 3) { uint32_t T[16]; (void)mul_ps<false>(T, x, y); acc_add<17, 16>(acc, T); x.l[0] ^= T[3]; }
+        else { Fr o; (void)mul_ps<true>(o.l, x, y); cond_sub_r(o.l); x = o; }
     }
-    if (MODE >= 2) x = acc17_reduce(acc);
+    if (MODE == 2 || MODE == 3) x = acc17_reduce(acc);
     st256(out + tid, x);
 }
 
@@ -99,16 +100,17 @@ int main() {
         for (int i = 0; i < 1024; i++) for (int k = 0; k < 8; k++) h[i].l[k] = (k == 7) ? (0x1234567u + i) : (2654435761u * (i * 8 + k + 1));
         CHECK(cudaMemcpy(fin, h, sizeof h, cudaMemcpyHostToDevice));
     }
-    const char* fnames[] = {"fr_mul row-wise even/odd (first generation)", "fr_mul product scanning (library)", "mul_wide + acc17 (lazy, row-wise)", "mul_ps<false> + acc17 (lazy, product scanning)"};
+    const char* fnames[] = {"fr_mul row-wise, negated digit (first generation)", "fr_mul row-wise, complement digit (library)", "mul_wide + acc17 (lazy, row-wise, library)", "mul_ps<false> + acc17 (lazy, product scanning)", "mul_ps<true> product scanning, complement digit"};
     for (int wpb = 0; wpb < 2; wpb++) {
         const int fblocks = sms * (wpb ? 16 : 4), fiters = 2048;
-        for (int mode = 0; mode < 4; mode++) {
+        for (int mode = 0; mode < 5; mode++) {
             auto L = [&]() {
                 switch (mode) {
                     case 0: fr_kernel<0><<<fblocks, 128>>>(fin, fout, fiters); break;
                     case 1: fr_kernel<1><<<fblocks, 128>>>(fin, fout, fiters); break;
                     case 2: fr_kernel<2><<<fblocks, 128>>>(fin, fout, fiters); break;
-                    default: fr_kernel<3><<<fblocks, 128>>>(fin, fout, fiters); break;
+                    case 3: fr_kernel<3><<<fblocks, 128>>>(fin, fout, fiters); break;
+                    default: fr_kernel<4><<<fblocks, 128>>>(fin, fout, fiters); break;
                 }
             };
             double ms = time_ms(L, 5);

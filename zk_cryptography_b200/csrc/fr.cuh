@@ -253,15 +253,132 @@ ZKSC_DEV uint32_t mul_ps(uint32_t* out, const Fr& a, const Fr& b) {
     return 0;
 }
 
+// ---- operand scanning (row-wise) multiplication with even/odd carry chains ------------------------------
+// IMAD.WIDE needs its 64-bit accumulator in an aligned register pair, so partial products whose low limb
+// sits at an EVEN position accumulate in E[] and those at an ODD position in O[] (index = absolute limb
+// position).  For one multiplier limb x at base position i the products with a0,a2,a4,a6 form one carry
+// chain (IMAD.WIDE.U32 / IMAD.WIDE.U32.X) in the array of i's parity and those with a1,a3,a5,a7 a second
+// one in the other array: two independent chains per row, and rows overlap, which keeps the multiplier
+// pipe busy at 4 warps per scheduler (92% vs 72% for product scanning; profiles/r01_ncu_ubench3_fr_mul.txt).
+template <bool CARRY_IN>
+ZKSC_DEV void chain4(uint32_t* X, int pos, uint32_t v0, uint32_t v2, uint32_t v4, uint32_t v6, uint32_t x) {
+    using namespace ptx;
+    X[pos + 0] = CARRY_IN ? madc_lo_cc(x, v0, X[pos + 0]) : mad_lo_cc(x, v0, X[pos + 0]);
+    X[pos + 1] = madc_hi_cc(x, v0, X[pos + 1]);
+    X[pos + 2] = madc_lo_cc(x, v2, X[pos + 2]); X[pos + 3] = madc_hi_cc(x, v2, X[pos + 3]);
+    X[pos + 4] = madc_lo_cc(x, v4, X[pos + 4]); X[pos + 5] = madc_hi_cc(x, v4, X[pos + 5]);
+    X[pos + 6] = madc_lo_cc(x, v6, X[pos + 6]); X[pos + 7] = madc_hi_cc(x, v6, X[pos + 7]);
+    X[pos + 8] = addc(X[pos + 8], 0u);
+}
+// 512-bit product a*b, any a, b < 2^256
+ZKSC_DEV void mul_wide(uint32_t (&T)[16], const Fr& a, const Fr& b) {
+    uint32_t E[17], O[17];
+#pragma unroll
+    for (int i = 0; i < 17; i++) { E[i] = 0; O[i] = 0; }
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint32_t* A = (i & 1) ? O : E;
+        uint32_t* B = (i & 1) ? E : O;
+        chain4<false>(A, i, a.l[0], a.l[2], a.l[4], a.l[6], b.l[i]);
+        chain4<false>(B, i + 1, a.l[1], a.l[3], a.l[5], a.l[7], b.l[i]);
+    }
+    T[0] = E[0];
+    T[1] = ptx::add_cc(E[1], O[1]);
+#pragma unroll
+    for (int i = 2; i < 15; i++) T[i] = ptx::addc_cc(E[i], O[i]);
+    T[15] = ptx::addc(E[15], O[15]);
+}
+
+// Limb k of C* = sum_{i=0..7} (p - 1 + 2^32) * 2^(32 i): what the "+1" parts of the complement digits add
+// (see mont_mul_rows).  Evaluated at compile time.
+ZKSC_DEV constexpr uint32_t cstar_limb(int k) {
+    unsigned long long carry = 0, limb = 0;
+    for (int pos = 0; pos <= k; pos++) {
+        unsigned long long s = carry;
+        for (int i = 0; i < 8; i++) {
+            const int j = pos - i;                       // limb j of (p - 1 + 2^32) lands on position i + j
+            if (j < 0 || j > 8) continue;
+            // p - 1 + 2^32 = p + 0xffffffff: limbs (p0 - 1 = 0, p1 + 1 -> 0 carry 1, ...) computed on the fly
+            unsigned long long c = 0, v = 0;
+            for (int l = 0; l <= j; l++) {
+                unsigned long long w = (l < 8 ? mod_limb(l) : 0ull) + (l == 0 ? 0xffffffffull : 0ull) + c;
+                v = w & 0xffffffffull;
+                c = w >> 32;
+            }
+            s += v;
+        }
+        limb = s & 0xffffffffull;
+        carry = s >> 32;
+    }
+    return (uint32_t)limb;
+}
+
+template <int K>
+struct CStar {
+    static constexpr uint32_t v = cstar_limb(K);   // forces compile-time evaluation
+};
+
+// Montgomery multiplication (CIOS, even/odd chains, complement digits).
+// Row i adds a*b_i, then reads limb i of the running total, t = E[i] + O[i] + k (k = carry out of limb
+// i-1), and adds (m' + 1) * p * 2^(32 i) with m' = ~t:
+//   * m' is a COMPLEMENT, not the textbook negation -t: ptxas folds a negation into operand modifiers and
+//     then splits every digit product into IMAD + IMAD.HI.U32 (7 multiplier-pipe cycles instead of ~4);
+//   * limb i becomes t + m' * p_0 = 2^32 - 1, and its "+1" would turn that into 0 with a carry of one, so
+//     the +1 is booked one limb higher instead; all the "+1" parts together are the constant C* that E[]
+//     starts from (no run-time cost).  Limbs 0..7 end as 0xffffffff instead of 0 and are discarded;
+//   * m' * p_0 = m' needs no multiplication: an add at the head of the even chain.
+// 64 + 56 IMAD.WIDE in all.  Inputs: a, b < 2^256 with a*b < p * 2^256 for a result < 2p.
+// Returns limbs 8..16 of the total: res[0..7] and the top limb.
+ZKSC_DEV void mont_mul_rows(uint32_t (&res)[8], uint32_t& top, const Fr& a, const Fr& b) {
+    using namespace ptx;
+    uint32_t E[18], O[18];
+#pragma unroll
+    for (int i = 0; i < 18; i++) O[i] = 0;
+    E[0] = CStar<0>::v; E[1] = CStar<1>::v; E[2] = CStar<2>::v; E[3] = CStar<3>::v; E[4] = CStar<4>::v; E[5] = CStar<5>::v;
+    E[6] = CStar<6>::v; E[7] = CStar<7>::v; E[8] = CStar<8>::v; E[9] = CStar<9>::v; E[10] = CStar<10>::v; E[11] = CStar<11>::v;
+    E[12] = CStar<12>::v; E[13] = CStar<13>::v; E[14] = CStar<14>::v; E[15] = CStar<15>::v; E[16] = CStar<16>::v; E[17] = 0u;
+    const uint32_t p1 = ZKSC_P1, p2 = ZKSC_P2, p3 = ZKSC_P3, p4 = ZKSC_P4, p5 = ZKSC_P5, p6 = ZKSC_P6, p7 = ZKSC_P7;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint32_t* A = (i & 1) ? O : E;
+        uint32_t* B = (i & 1) ? E : O;
+        chain4<false>(A, i, a.l[0], a.l[2], a.l[4], a.l[6], b.l[i]);
+        chain4<false>(B, i + 1, a.l[1], a.l[3], a.l[5], a.l[7], b.l[i]);
+        uint32_t m;
+        if (i == 0) {
+            m = ~E[0];
+            A[0] = add_cc(A[0], m);
+        } else {
+            (void)add_cc(E[i - 1], O[i - 1]);          // limb i-1 is 2^32 - 1 (+ 2^32 k): CF = k
+            m = ~addc(E[i], O[i]);
+            A[i] = addc_cc(A[i], m);                   // k enters here
+        }
+        A[i + 1] = addc_cc(A[i + 1], 0u);
+        A[i + 2] = madc_lo_cc(m, p2, A[i + 2]); A[i + 3] = madc_hi_cc(m, p2, A[i + 3]);
+        A[i + 4] = madc_lo_cc(m, p4, A[i + 4]); A[i + 5] = madc_hi_cc(m, p4, A[i + 5]);
+        A[i + 6] = madc_lo_cc(m, p6, A[i + 6]); A[i + 7] = madc_hi_cc(m, p6, A[i + 7]);
+        A[i + 8] = addc(A[i + 8], 0u);
+        chain4<false>(B, i + 1, p1, p3, p5, p7, m);
+    }
+    (void)add_cc(O[7], E[7]);                          // k_7
+#pragma unroll
+    for (int i = 0; i < 8; i++) res[i] = addc_cc(E[8 + i], O[8 + i]);
+    top = addc(E[16], O[16]);
+}
+
 // Montgomery product, canonical result.  a, b < r.
 ZKSC_DEV Fr fr_mul(const Fr& a, const Fr& b) {
     Fr o;
-    (void)mul_ps<true>(o.l, a, b);   // < 2r < 2^256: top == 0
+    uint32_t top;
+#ifdef ZKSC_MUL_PRODUCT_SCANNING
+    top = mul_ps<true>(o.l, a, b);
+#else
+    mont_mul_rows(o.l, top, a, b);   // < 2r < 2^256: top == 0
+#endif
+    (void)top;
     cond_sub_r(o.l);
     return o;
 }
-// 512-bit product a*b, any a, b < 2^256
-ZKSC_DEV void mul_wide(uint32_t (&T)[16], const Fr& a, const Fr& b) { (void)mul_ps<false>(T, a, b); }
 
 // Montgomery reduction of a 16-limb T (any T < 2^512): (T + M r) / 2^256, 8 limbs + top.
 // Only used on the once-per-block slow path and in tests.

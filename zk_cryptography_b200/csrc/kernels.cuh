@@ -48,6 +48,21 @@ struct Lazy {
     static constexpr int NL = (D == 1) ? 9 : (wide ? 17 : 9);
 };
 
+// Degrees above 5 are rare (the reference's benches stop at 5): their multiplications are real calls, which
+// keeps the code size -- and the build time -- of those instantiations in check.
+static __device__ __noinline__ Fr fr_mul_call(const Fr& a, const Fr& b) { return fr_mul(a, b); }
+static __device__ __noinline__ Fr fr_fold_call(const Fr& a, const Fr& b, const Fr& r) { return fr_fold(a, b, r); }
+template <int D>
+ZKSC_DEV Fr fr_mul_d(const Fr& a, const Fr& b) {
+    if constexpr (D > 5) return fr_mul_call(a, b);
+    else return fr_mul(a, b);
+}
+template <int D>
+ZKSC_DEV Fr fr_fold_d(const Fr& a, const Fr& b, const Fr& r) {
+    if constexpr (D > 5) return fr_fold_call(a, b, r);
+    else return fr_fold(a, b, r);
+}
+
 // acc += prod_k f[k]
 template <int D>
 ZKSC_DEV void accumulate_product(Acc<Lazy<D>::NL>& acc, const Fr (&f)[D]) {
@@ -63,7 +78,7 @@ ZKSC_DEV void accumulate_product(Acc<Lazy<D>::NL>& acc, const Fr (&f)[D]) {
     } else {
         Fr g = f[0];
 #pragma unroll
-        for (int k = 1; k < D; k++) g = fr_mul(g, f[k]);
+        for (int k = 1; k < D; k++) g = fr_mul_d<D>(g, f[k]);
         acc_add<9, 8>(acc, g.l);
     }
 }
@@ -173,8 +188,8 @@ __global__ void __launch_bounds__(kThreads) round_kernel(const __grid_constant__
                 // T_{j-1} has 4*half entries; its pairs are (y, y + 2*half)
                 Fr p0 = ld256(t + x), p1 = ld256(t + x + 2 * half);
                 Fr q0 = ld256(t + x + half), q1 = ld256(t + x + 3 * half);
-                a[k] = fr_fold(p0, p1, r);
-                b[k] = fr_fold(q0, q1, r);
+                a[k] = fr_fold_d<D>(p0, p1, r);
+                b[k] = fr_fold_d<D>(q0, q1, r);
                 Fr* o = out + (size_t)k * args.out_tab_stride;
                 st256(o + x, a[k]);
                 st256(o + x + half, b[k]);
