@@ -235,6 +235,14 @@ def run_b200(args):
                                    "GBps": round(top["bytes"] / (top["ms"] * 1e-3) / 1e9, 1)},
         "kernel_share_of_step": round(top["ms"] / ms, 4),
     }
+    # per-round profile of the timed region: average event-bracketed duration of every launch shape
+    prof = {}
+    for r in recs:
+        k = (r["degree"], r["fold"], r["pairs"], r["proofs"])
+        e = prof.setdefault(k, [0.0, 0])
+        e[0] += r["ms"]; e[1] += 1
+    round_profile = [{"degree": k[0], "fold": k[1], "pairs": k[2], "proofs": k[3], "avg_us": round(v[0] / v[1] * 1e3, 2)}
+                     for k, v in sorted(prof.items(), key=lambda kv: -kv[0][2])]
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             tr = json.load(f).get(roofline["kernel"])
@@ -309,6 +317,8 @@ def run_b200(args):
         "clocks": sampler.summary(), "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline, "int_roofline": int_roofline,
         "cpu_baseline": cpu,
     }
+    if args.round_profile:
+        out["round_profile"] = round_profile
     print(json.dumps(out))
     sys.stdout.flush()
     if dist is not None:
@@ -391,6 +401,7 @@ def main():
     ap.add_argument("--cpu-n", type=int, default=22, help="n_vars of the bounded CPU sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--round-profile", action="store_true", help="add the per-launch-shape average durations to the JSON line")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

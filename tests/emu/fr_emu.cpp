@@ -40,3 +40,12 @@ extern "C" void emu_mont_mul_rows(const uint32_t* a, const uint32_t* b, uint32_t
     uint32_t res[8], top; mont_mul_rows(res, top, x, y); memcpy(out9, res, 32); out9[8] = top;
 }
 extern "C" void emu_cstar(uint32_t* out17) { for (int i = 0; i < 17; i++) out17[i] = cstar_limb(i); }
+extern "C" void emu_mul_fixed(const uint32_t* d, const uint32_t* w64, uint32_t* out8) {
+    FoldTab W; memcpy(W.w, w64, 256);
+    uint32_t dd[8], res[8]; memcpy(dd, d, 32);
+    mul_fixed_rows(res, dd, W); memcpy(out8, res, 32);
+}
+extern "C" void emu_fr_fold_tab(const uint32_t* a, const uint32_t* b, const uint32_t* w64, uint32_t* o) {
+    FoldTab W; memcpy(W.w, w64, 256);
+    Fr x, y; memcpy(x.l, a, 32); memcpy(y.l, b, 32); Fr z = fr_fold_tab(x, y, W); memcpy(o, z.l, 32);
+}

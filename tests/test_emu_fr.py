@@ -101,3 +101,35 @@ def test_lazy_accumulation_of_many_products(emu):
     assert val(acc) == total
     emu.emu_acc17_reduce(acc, o8)
     assert val(o8) == total * RINV % R
+
+
+def fold_table(r_plain):
+    """w[i] = r * 2^(32 (i + 2)) mod p as 8 x 8 little-endian 32-bit limbs (fr.cuh FoldTab)"""
+    flat = []
+    for i in range(8):
+        w = r_plain * (1 << (32 * (i + 2))) % R
+        flat += [(w >> (32 * j)) & 0xFFFFFFFF for j in range(8)]
+    return (ctypes.c_uint32 * 64)(*flat)
+
+
+def test_fixed_multiplicand_fold(emu):
+    """mul_fixed_rows / fr_fold_tab: r * d through the per-round shift table, two Montgomery digits"""
+    rng = random.Random(13)
+    o8 = (ctypes.c_uint32 * 8)()
+    for it in range(4000):
+        r = rnd(rng, R)
+        W = fold_table(r)
+        d = rnd(rng, 2**256)
+        emu.emu_mul_fixed(arr(d, 8), W, o8)
+        v = val(o8)
+        assert v % R == r * d % R and v < 2 * R
+        a, b = rnd(rng, R), rnd(rng, R)
+        emu.emu_fr_fold_tab(arr(a, 8), arr(b, 8), W, o8)
+        assert val(o8) == (a + r * (b - a)) % R
+    # extreme table / operand limbs
+    for r in (0, 1, R - 1):
+        W = fold_table(r)
+        for d in (0, 1, 2**256 - 1, 2**32 - 1, 2**64 - 1, R, R - 1):
+            emu.emu_mul_fixed(arr(d, 8), W, o8)
+            v = val(o8)
+            assert v % R == r * d % R and v < 2 * R

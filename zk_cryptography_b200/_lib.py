@@ -25,7 +25,8 @@ _u8p = ctypes.POINTER(ctypes.c_uint8)
 
 
 def lib_path():
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libzksc.so")
+    # ZKSC_LIB: an alternative build of the same library (kernel experiments: tools/gpu_variants.sh)
+    return os.environ.get("ZKSC_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libzksc.so")
 
 
 def lib():

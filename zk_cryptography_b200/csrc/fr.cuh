@@ -480,4 +480,105 @@ ZKSC_DEV Fr fr_fold(const Fr& a, const Fr& b, const Fr& r) {
     return fr_add(a, fr_mul(r, fr_sub(b, a)));
 }
 
+// ---- multiplication by a FIXED element through a precomputed shift table --------------------------
+// A whole round folds every table entry with the SAME challenge r, so the host precomputes (once per
+// round, 8 Montgomery multiplications)
+//     w[i] = r * 2^(32 (i + 2)) mod p,   i = 0..7      (canonical residues; r = the plain challenge)
+// and the device evaluates  r * d  for d = sum d_i 2^(32 i)  as  T = sum_i d_i * w[i]  -- an 8 x 8 limb
+// product whose rows all land on limb 0 (the shifts live in the table), T < 2^35 p < 2^290 -- followed by
+// TWO Montgomery digit steps that divide out the extra 2^64:  V = (T + M p) / 2^64 < 2^226 + p(1 + 2^-32)
+// < 2p,  V == r * d (mod p).  With d in Montgomery form, V is the Montgomery form of r * (d/R): exactly
+// what mont_mul(r~, d) returns, at 64 + 12 IMAD.WIDE instead of 64 + 56.
+// Digit steps.  p = 1 - 2^32 + 2^64 K  with  K = (p >> 64) + 1  (six limbs), so for a digit m' = ~t (t = the
+// low limb, complement instead of negation for the reason given at mont_mul_rows):
+//     (T + (m' + 1) p) / 2^32 = (T >> 32) + (t + 1) + 2^32 (m' K + K - 1)
+// -- every term non-negative, six products per digit.  Both digits follow from limbs 0 and 1 of T alone
+// (u = t_1 + t_0 + 1 is the low limb after step one), so the 12 reduction products do not wait for
+// each other.  K - 1 = p >> 64 of both steps is the constant E[] starts from.
+struct FoldTab {
+    uint32_t w[8][8];
+};
+ZKSC_DEV constexpr uint32_t foldk_limb(int j) { return (uint32_t)(mod_limb(j + 2) + (j == 0 ? 1ull : 0ull)); }   // K, limbs 0..5
+// limb k (absolute position, k >= 2) of ((p >> 64) * (1 + 2^32)) << 64
+ZKSC_DEV constexpr uint32_t foldq_limb(int k) {
+    unsigned long long carry = 0, limb = 0;
+    for (int pos = 2; pos <= k; pos++) {
+        unsigned long long s = carry;
+        const int j0 = pos - 2, j1 = pos - 3;            // Q limb j0 from the first copy, j1 from the shifted copy
+        if (j0 >= 0 && j0 < 6) s += mod_limb(j0 + 2);
+        if (j1 >= 0 && j1 < 6) s += mod_limb(j1 + 2);
+        limb = s & 0xffffffffull;
+        carry = s >> 32;
+    }
+    return (uint32_t)limb;
+}
+template <int K>
+struct FoldQ {
+    static constexpr uint32_t v = foldq_limb(K);
+};
+// three fused lo/hi pairs on X[pos..pos+5], carry into X[pos+6]
+ZKSC_DEV void chain3(uint32_t* X, int pos, uint32_t v0, uint32_t v2, uint32_t v4, uint32_t x) {
+    using namespace ptx;
+    X[pos + 0] = mad_lo_cc(x, v0, X[pos + 0]);  X[pos + 1] = madc_hi_cc(x, v0, X[pos + 1]);
+    X[pos + 2] = madc_lo_cc(x, v2, X[pos + 2]); X[pos + 3] = madc_hi_cc(x, v2, X[pos + 3]);
+    X[pos + 4] = madc_lo_cc(x, v4, X[pos + 4]); X[pos + 5] = madc_hi_cc(x, v4, X[pos + 5]);
+    X[pos + 6] = addc(X[pos + 6], 0u);
+}
+// res (8 limbs, < 2p) == r * d (mod p) for ANY d < 2^256, W the shift table of r.
+ZKSC_DEV void mul_fixed_rows(uint32_t (&res)[8], const uint32_t (&d)[8], const FoldTab& W) {
+    using namespace ptx;
+    uint32_t E[11], O[11];
+#pragma unroll
+    for (int i = 0; i < 11; i++) O[i] = 0;
+    E[0] = 0; E[1] = 0; E[2] = FoldQ<2>::v; E[3] = FoldQ<3>::v; E[4] = FoldQ<4>::v; E[5] = FoldQ<5>::v;
+    E[6] = FoldQ<6>::v; E[7] = FoldQ<7>::v; E[8] = FoldQ<8>::v; E[9] = FoldQ<9>::v; E[10] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        chain4<false>(E, 0, W.w[i][0], W.w[i][2], W.w[i][4], W.w[i][6], d[i]);
+        chain4<false>(O, 1, W.w[i][1], W.w[i][3], W.w[i][5], W.w[i][7], d[i]);
+    }
+    // limbs 0 and 1 of T, the two digits, and what the low 64 bits leave behind at limb 2
+    const uint32_t t0 = E[0];
+    const uint32_t t1 = add_cc(E[1], O[1]);
+    uint32_t cs = addc(0u, 0u);                       // c1: carry of E + O out of limb 1
+    uint32_t u = add_cc(t1, t0);
+    cs = addc(cs, 0u);
+    u = add_cc(u, 1u);
+    cs = addc(cs, 0u);                                // + c0: carry of t1 + t0 + 1
+    uint32_t small_lo = add_cc(u, 1u);                // small = (u + 1) + c0 + c1, at limb 2
+    uint32_t small_hi = addc(0u, 0u);
+    small_lo = add_cc(small_lo, cs);
+    small_hi = addc(small_hi, 0u);
+    const uint32_t m0 = ~t0, m1 = ~u;
+    const uint32_t k0 = foldk_limb(0), k1 = foldk_limb(1), k2 = foldk_limb(2), k3 = foldk_limb(3), k4 = foldk_limb(4), k5 = foldk_limb(5);
+    chain3(E, 2, k0, k2, k4, m0);
+    chain3(O, 3, k1, k3, k5, m0);
+    chain3(O, 3, k0, k2, k4, m1);
+    chain3(E, 4, k1, k3, k5, m1);
+    res[0] = add_cc(E[2], O[2]);
+#pragma unroll
+    for (int i = 1; i < 7; i++) res[i] = addc_cc(E[2 + i], O[2 + i]);
+    res[7] = addc(E[9], O[9]);
+    res[0] = add_cc(res[0], small_lo);
+    res[1] = addc_cc(res[1], small_hi);
+#pragma unroll
+    for (int i = 2; i < 7; i++) res[i] = addc_cc(res[i], 0u);
+    res[7] = addc(res[7], 0u);
+}
+// fold through the table: a + r * (b - a), canonical.  a, b < p.
+ZKSC_DEV Fr fr_fold_tab(const Fr& a, const Fr& b, const FoldTab& W) {
+    using namespace ptx;
+    uint32_t d[8];                                     // b - a + p  in (0, 2p): no conditional
+    d[0] = sub_cc(b.l[0], a.l[0]);
+#pragma unroll
+    for (int i = 1; i < 7; i++) d[i] = subc_cc(b.l[i], a.l[i]);
+    d[7] = subc(b.l[7], a.l[7]);
+    d[0] = add_cc(d[0], ZKSC_P0); d[1] = addc_cc(d[1], ZKSC_P1); d[2] = addc_cc(d[2], ZKSC_P2); d[3] = addc_cc(d[3], ZKSC_P3);
+    d[4] = addc_cc(d[4], ZKSC_P4); d[5] = addc_cc(d[5], ZKSC_P5); d[6] = addc_cc(d[6], ZKSC_P6); d[7] = addc(d[7], ZKSC_P7);
+    Fr v;
+    mul_fixed_rows(v.l, d, W);
+    cond_sub_r(v.l);
+    return fr_add(a, v);
+}
+
 }  // namespace zksc

@@ -121,6 +121,19 @@ inline FrH from_u64(uint64_t x) {
     uint64_t c[4] = {x, 0, 0, 0};
     return from_canonical(c);
 }
+// Shift table of a challenge for the device's fixed-multiplicand fold (fr.cuh mul_fixed_rows):
+// w[i] = r * 2^(32 (i + 2)) mod p as 8 little-endian 32-bit limbs, r = the plain value of r_mont.
+inline void fold_table(const FrH& r_mont, uint32_t w[8][8]) {
+    for (int i = 0; i < 8; i++) {
+        const int e = i + 2;                       // 2^(32 e) mod p as RAW limbs: mul(r R, X) = r X
+        FrH x = kZero;
+        if (e < 8) x.v[e / 2] = 1ull << (32 * (e % 2));
+        else if (e == 8) x = kOne;                 // 2^256 mod p
+        else x = from_u64(1ull << 32);             // 2^288 mod p
+        FrH v = mul(r_mont, x);
+        memcpy(w[i], v.v, 32);
+    }
+}
 inline FrH pow_u(const FrH& a, const uint64_t e[4]) {
     FrH acc = kOne;
     for (int i = 255; i >= 0; i--) {

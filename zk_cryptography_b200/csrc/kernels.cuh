@@ -26,7 +26,7 @@ constexpr int kWarps = kThreads / 32;
 constexpr int kMaxBatch = 64;   // proofs per launch (challenges travel as kernel parameters)
 constexpr int kMaxDegree = 8;
 
-struct RoundArgs {
+struct RoundBase {
     const Fr* in;              // table 0 of proof 0 (current tables)
     Fr* out;                   // FOLD: where the folded tables go (may alias `in`)
     unsigned long long in_tab_stride, in_proof_stride;    // elements
@@ -39,7 +39,14 @@ struct RoundArgs {
     unsigned int npts;         // evaluation points 0..npts-1 are wanted (<= D+1); SKIP1 kernels leave point 1 untouched
     volatile unsigned int* flag;  // optional: set to flag_value (system scope) after the results
     unsigned int flag_value;
-    Fr chal[kMaxBatch];        // FOLD: challenge of the previous round, Montgomery form, per proof
+};
+// NB = proofs per launch.  The per-proof challenge data travels in the kernel parameters (constant bank): a
+// single-proof launch carries 288 bytes of it, a batched one 18 KiB -- large parameter blocks make every
+// launch slower, so the two cases are separate instantiations.
+template <int NB>
+struct RoundArgsT : RoundBase {
+    Fr chal[NB];               // FOLD: challenge of the previous round, Montgomery form, per proof (degrees > 5)
+    FoldTab tab[NB];           // FOLD: its shift table (fr.cuh mul_fixed_rows), per proof; read straight from the constant bank
 };
 
 template <int D>
@@ -93,7 +100,7 @@ ZKSC_DEV Fr acc_finish(const Acc<NL>& a) {
 // block of each proof to arrive -- the final cross-block sum.
 // Accumulator slot s holds evaluation point s, or with SKIP1 point (s == 0 ? 0 : s + 1).
 template <int NL, int NP, bool SKIP1>
-ZKSC_DEV void reduce_and_publish(Acc<NL> (&acc)[NP], const RoundArgs& args, int npts) {
+ZKSC_DEV void reduce_and_publish(Acc<NL> (&acc)[NP], const RoundBase& args, int npts) {
     auto point_of = [](int slot) { return (SKIP1 && slot > 0) ? slot + 1 : slot; };
     __shared__ Acc<NL> s_warp[kWarps][NP];
     __shared__ bool s_last;
@@ -159,20 +166,40 @@ ZKSC_DEV void reduce_and_publish(Acc<NL> (&acc)[NP], const RoundArgs& args, int 
     }
 }
 
+// acc[] += the products at every evaluation point of one pair (a = even half, b = odd half of each factor)
+template <int D, bool SKIP1, int NP>
+ZKSC_DEV void accumulate_points(Acc<Lazy<D>::NL> (&acc)[NP], Fr (&a)[D], Fr (&b)[D], int npts) {
+    // evaluation points 0 and 1 are the two halves themselves
+    accumulate_product<D>(acc[0], a);
+    if (!SKIP1 && npts > 1) accumulate_product<D>(acc[1], b);
+    if (D >= 2 && npts > 2) {
+        // f_k(t) = a_k + t (b_k - a_k): walk t = 2..D by repeated addition of the difference
+        Fr delta[D];
+#pragma unroll
+        for (int k = 0; k < D; k++) delta[k] = fr_sub(b[k], a[k]);
+#pragma unroll
+        for (int p = 2; p <= D; p++) {
+#pragma unroll
+            for (int k = 0; k < D; k++) b[k] = fr_add(b[k], delta[k]);
+            if (p < npts) accumulate_product<D>(acc[SKIP1 ? p - 1 : p], b);
+        }
+    }
+}
+
 // FOLD = false : evaluate the round polynomial of the tables as they are (first round).
 // FOLD = true  : bind the previous challenge (in -> out), then evaluate the next round on the result.
-template <int D, bool FOLD, bool SKIP1>
-__global__ void __launch_bounds__(kThreads) round_kernel(const __grid_constant__ RoundArgs args) {
+template <int D, bool FOLD, bool SKIP1, int NB>
+__global__ void __launch_bounds__(kThreads) round_kernel(const __grid_constant__ RoundArgsT<NB> args) {
     constexpr int NL = Lazy<D>::NL;
     constexpr int NP = SKIP1 ? D : D + 1;   // accumulators
-    const int proof = blockIdx.y;
+    const int proof = (NB == 1) ? 0 : blockIdx.y;
     const Fr* in = args.in + (size_t)proof * args.in_proof_stride;
     Fr* out = args.out + (size_t)proof * args.out_proof_stride;
     const unsigned long long half = args.half;
     const int npts = args.npts;
 
     Fr r;
-    if constexpr (FOLD) r = args.chal[proof];
+    if constexpr (FOLD && D > 5) r = args.chal[proof];
 
     Acc<NL> acc[NP];
 #pragma unroll
@@ -188,8 +215,13 @@ __global__ void __launch_bounds__(kThreads) round_kernel(const __grid_constant__
                 // T_{j-1} has 4*half entries; its pairs are (y, y + 2*half)
                 Fr p0 = ld256(t + x), p1 = ld256(t + x + 2 * half);
                 Fr q0 = ld256(t + x + half), q1 = ld256(t + x + 3 * half);
-                a[k] = fr_fold_d<D>(p0, p1, r);
-                b[k] = fr_fold_d<D>(q0, q1, r);
+                if constexpr (D <= 5) {
+                    a[k] = fr_fold_tab(p0, p1, args.tab[proof]);
+                    b[k] = fr_fold_tab(q0, q1, args.tab[proof]);
+                } else {
+                    a[k] = fr_fold_d<D>(p0, p1, r);
+                    b[k] = fr_fold_d<D>(q0, q1, r);
+                }
                 Fr* o = out + (size_t)k * args.out_tab_stride;
                 st256(o + x, a[k]);
                 st256(o + x + half, b[k]);
@@ -198,21 +230,147 @@ __global__ void __launch_bounds__(kThreads) round_kernel(const __grid_constant__
                 b[k] = ld256_stream(t + x + half);
             }
         }
-        // evaluation points 0 and 1 are the two halves themselves
-        accumulate_product<D>(acc[0], a);
-        if (!SKIP1 && npts > 1) accumulate_product<D>(acc[1], b);
-        if (D >= 2 && npts > 2) {
-            // f_k(t) = a_k + t (b_k - a_k): walk t = 2..D by repeated addition of the difference
-            Fr delta[D];
+        accumulate_points<D, SKIP1>(acc, a, b, npts);
+    }
+    reduce_and_publish<NL, NP, SKIP1>(acc, args, npts);
+}
+
+// ---- TMA-staged variant ---------------------------------------------------------------------------------
+// Same arithmetic, different data movement.  The kernel above issues its global loads at the top of every
+// iteration and then waits for them; with ~450-1000 multiplier-pipe instructions per pair only four warps
+// fit per scheduler, too few to cover HBM latency that way.  Here every warp owns one shared-memory slot
+// (32 pairs: 4 D segments of 1 KiB with FOLD, 2 D without) and one mbarrier; lane 0 fills the slot with
+// cp.async.bulk (the TMA engine, UBLKCP in SASS) for the warp's NEXT tile as soon as the current tile has
+// been copied from the slot into registers, so the whole compute phase of a tile overlaps the fetch of the
+// next one.  No producer warp, no cross-warp synchronisation: the slot is released by the warp that owns it.
+// The loads carry an L2 evict_first policy (T_{j-1} is dead after this pass) so that the folded tables
+// just written stay in L2 for the next round when they fit.
+// Requires half % 32 == 0 (the host falls back to round_kernel for the tiny rounds).
+ZKSC_DEV uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+ZKSC_DEV void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+ZKSC_DEV void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+ZKSC_DEV void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "ZKSC_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra ZKSC_DONE_%=;\n"
+        "bra ZKSC_WAIT_%=;\n"
+        "ZKSC_DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+ZKSC_DEV unsigned long long l2_evict_first_policy() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+ZKSC_DEV void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, unsigned long long policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar), "l"(policy)
+                 : "memory");
+}
+// plain C++ loads (2 x LDS.128): ordered by the compiler against the mbarrier wait / __syncwarp around them,
+// free to be scheduled between the two
+ZKSC_DEV Fr lds256(const unsigned char* p) {
+    const uint4 lo = *reinterpret_cast<const uint4*>(p), hi = *reinterpret_cast<const uint4*>(p + 16);
+    Fr v;
+    v.l[0] = lo.x; v.l[1] = lo.y; v.l[2] = lo.z; v.l[3] = lo.w;
+    v.l[4] = hi.x; v.l[5] = hi.y; v.l[6] = hi.z; v.l[7] = hi.w;
+    return v;
+}
+
+#ifndef ZKSC_TMA_MINB
+#define ZKSC_TMA_MINB(D) ((D) <= 2 ? 4 : 3)
+#endif
+constexpr int kTilePairs = 32;                       // pairs per warp tile: one per lane
+constexpr int kSegBytes = kTilePairs * 32;           // one table segment of a tile
+template <int D, bool FOLD>
+__host__ __device__ constexpr int tma_slot_bytes() { return (FOLD ? 4 : 2) * D * kSegBytes; }
+
+template <int D, bool FOLD, bool SKIP1, int NB>
+__global__ void __launch_bounds__(kThreads, ZKSC_TMA_MINB(D)) round_tma_kernel(const __grid_constant__ RoundArgsT<NB> args) {
+    static_assert(D <= 5, "the staged kernel uses the table fold");
+    constexpr int NL = Lazy<D>::NL;
+    constexpr int NP = SKIP1 ? D : D + 1;
+    constexpr int NSEG = FOLD ? 4 : 2;
+    constexpr int SLOT = tma_slot_bytes<D, FOLD>();
+    extern __shared__ __align__(128) unsigned char zksc_slots[];
+    __shared__ __align__(8) unsigned long long s_bar[kWarps];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int proof = (NB == 1) ? 0 : blockIdx.y;
+    const Fr* in = args.in + (size_t)proof * args.in_proof_stride;
+    Fr* out = args.out + (size_t)proof * args.out_proof_stride;
+    const unsigned long long half = args.half;
+    const int npts = args.npts;
+    const unsigned char* my_slot = zksc_slots + warp * SLOT;
+    const uint32_t slot = smem_addr(my_slot);
+    const uint32_t bar = smem_addr(&s_bar[warp]);
+    // 32-bit tile counters: half / 32 < 2^32 for any table that fits in memory
+    const unsigned int n_tiles = (unsigned int)(half / kTilePairs);
+    const unsigned int tile_stride = gridDim.x * kWarps;
+    unsigned int tile = blockIdx.x * kWarps + warp;
+
+    auto issue = [&](unsigned int t) {               // lane 0 only
+        const unsigned long long x0 = (unsigned long long)t * kTilePairs;
+        const unsigned long long policy = l2_evict_first_policy();
+        mbar_expect_tx(bar, SLOT);
 #pragma unroll
-            for (int k = 0; k < D; k++) delta[k] = fr_sub(b[k], a[k]);
+        for (int k = 0; k < D; k++)
 #pragma unroll
-            for (int p = 2; p <= D; p++) {
+            for (int sgm = 0; sgm < NSEG; sgm++)
+                bulk_g2s(slot + (k * NSEG + sgm) * kSegBytes, in + (size_t)k * args.in_tab_stride + x0 + sgm * half, kSegBytes, bar, policy);
+    };
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (tile < n_tiles) issue(tile);
+    }
+    __syncwarp();
+
+    Acc<NL> acc[NP];
 #pragma unroll
-                for (int k = 0; k < D; k++) b[k] = fr_add(b[k], delta[k]);
-                if (p < npts) accumulate_product<D>(acc[SKIP1 ? p - 1 : p], b);
+    for (int p = 0; p < NP; p++) acc_zero(acc[p]);
+
+    uint32_t phase = 0;
+    for (; tile < n_tiles; tile += tile_stride) {
+        const unsigned long long x = (unsigned long long)tile * kTilePairs + lane;
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        Fr a[D], b[D];
+#pragma unroll
+        for (int k = 0; k < D; k++) {
+            // operands are copied out of the slot just before they are used (two entries at a time with FOLD),
+            // which keeps the live registers low; the slot is released after the last copy
+            const unsigned char* tab = my_slot + k * NSEG * kSegBytes + lane * 32;
+            if constexpr (FOLD) {
+                // segments: x, x + half, x + 2 half, x + 3 half of T_{j-1}; its pairs are (y, y + 2 half)
+                Fr* o = out + (size_t)k * args.out_tab_stride;
+                {
+                    const Fr p0 = lds256(tab), p1 = lds256(tab + 2 * kSegBytes);
+                    a[k] = fr_fold_tab(p0, p1, args.tab[proof]);
+                    st256(o + x, a[k]);
+                }
+                const Fr q0 = lds256(tab + kSegBytes), q1 = lds256(tab + 3 * kSegBytes);
+                if (k == D - 1) {
+                    __syncwarp();                     // every lane has its last operands: the slot is free
+                    if (lane == 0 && tile + tile_stride < n_tiles) issue(tile + tile_stride);
+                }
+                b[k] = fr_fold_tab(q0, q1, args.tab[proof]);
+                st256(o + x + half, b[k]);
+            } else {
+                a[k] = lds256(tab);
+                b[k] = lds256(tab + kSegBytes);
+                if (k == D - 1) {
+                    __syncwarp();
+                    if (lane == 0 && tile + tile_stride < n_tiles) issue(tile + tile_stride);
+                }
             }
         }
+        accumulate_points<D, SKIP1>(acc, a, b, npts);
     }
     reduce_and_publish<NL, NP, SKIP1>(acc, args, npts);
 }

@@ -77,7 +77,9 @@ struct zksc_ctx {
     Fr* results_send = nullptr;  // [kMaxBatch * kMaxEvals]
     Fr* results_host = nullptr;  // pinned mirror of results_dev
     size_t results_cap = 0;      // elements per rank slot
-    int occ[kMaxDegree + 1][3];   // resident CTAs per SM of round_kernel<D, variant>
+    int occ[kMaxDegree + 1][6];   // resident CTAs per SM of round_kernel<D, variant> (0..2) and round_tma_kernel (3..5; 0 = none)
+    bool staged = true;           // use the TMA-staged kernels where they apply (ZKSC_NO_STAGED=1 turns them off)
+    bool staged_fold = false;     // ... also for the fused fold+evaluate rounds (ZKSC_STAGED_FOLD=1; slower today: DESIGN.md)
     std::string err;
     int rank = 0, n_ranks = 1;
 #if ZKSC_HAVE_NCCL_H
@@ -105,6 +107,7 @@ struct zksc_tables {
     int where;               // 0 orig, 1 work, 2 tail
     bool pending;
     std::vector<Fr> pending_chal;
+    std::vector<FoldTab> pending_tab;   // shift tables of pending_chal (fr.cuh mul_fixed_rows)
     // round-0 evaluations computed by zksc_poly_sum, handed to the next round-0 zksc_round_evals once
     // (calculate_poly_sum followed by prove is the reference's calling pattern; the input is immutable)
     std::vector<uint64_t> r0_cache;
@@ -153,8 +156,10 @@ extern "C" int zksc_device_count(void) {
 }
 
 // per-degree launchers live in round_inst.cu (one object per degree, compiled in parallel)
-#define ZKSC_DECL_ROUND(D)                                                                   \
-    void zksc_launch_round_##D(int variant, dim3 grid, cudaStream_t s, const RoundArgs& a);   \
+#define ZKSC_DECL_ROUND(D)                                                                               \
+    void zksc_launch_round_##D(int variant, bool staged, dim3 grid, cudaStream_t s, const RoundArgsT<1>& a);          \
+    void zksc_launch_round_##D(int variant, bool staged, dim3 grid, cudaStream_t s, const RoundArgsT<kMaxBatch>& a);  \
+    void zksc_prepare_round_##D();                                                                        \
     int zksc_occ_round_##D(int variant);
 ZKSC_DECL_ROUND(1) ZKSC_DECL_ROUND(2) ZKSC_DECL_ROUND(3) ZKSC_DECL_ROUND(4)
 ZKSC_DECL_ROUND(5) ZKSC_DECL_ROUND(6) ZKSC_DECL_ROUND(7) ZKSC_DECL_ROUND(8)
@@ -182,9 +187,11 @@ extern "C" int zksc_ctx_create(int device, zksc_ctx** out) {
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
     if ((e = cudaMalloc(&ctx->counters, (kMaxBatch + 1) * sizeof(unsigned int))) != cudaSuccess) return fail(e, "cudaMalloc");
     if ((e = cudaMemset(ctx->counters, 0, (kMaxBatch + 1) * sizeof(unsigned int))) != cudaSuccess) return fail(e, "cudaMemset");
-#define ZKSC_OCC(D) for (int v = 0; v < 3; v++) ctx->occ[D][v] = zksc_occ_round_##D(v);
+#define ZKSC_OCC(D) zksc_prepare_round_##D(); for (int v = 0; v < 6; v++) ctx->occ[D][v] = zksc_occ_round_##D(v);
     ZKSC_OCC(1) ZKSC_OCC(2) ZKSC_OCC(3) ZKSC_OCC(4) ZKSC_OCC(5) ZKSC_OCC(6) ZKSC_OCC(7) ZKSC_OCC(8)
     if ((e = cudaGetLastError()) != cudaSuccess) return fail(e, "occupancy query (is this an sm_100a device?)");
+    { const char* e_ = getenv("ZKSC_NO_STAGED"); ctx->staged = !(e_ && e_[0] == '1'); }
+    { const char* e_ = getenv("ZKSC_STAGED_FOLD"); ctx->staged_fold = (e_ && e_[0] == '1'); }
     *out = ctx;
     return ZKSC_OK;
 }
@@ -595,6 +602,27 @@ static int gather_tail(zksc_tables* t) {
 #endif
 }
 
+// fill in the per-proof challenge data and launch the round kernel of degree D
+template <int NB>
+static int launch_round(const zksc_tables* t, const RoundBase& base, int D, int variant, bool staged, dim3 grid, bool fold, uint32_t b0, uint32_t nb) {
+    static thread_local RoundArgsT<NB> a;   // 18 KiB for NB = kMaxBatch: kept off the stack
+    static_cast<RoundBase&>(a) = base;
+    if (fold) for (uint32_t b = 0; b < nb; b++) { a.chal[b] = t->pending_chal[b0 + b]; a.tab[b] = t->pending_tab[b0 + b]; }
+    cudaStream_t s = t->ctx->stream;
+    switch (D) {
+        case 1: zksc_launch_round_1(variant, staged, grid, s, a); break;
+        case 2: zksc_launch_round_2(variant, staged, grid, s, a); break;
+        case 3: zksc_launch_round_3(variant, staged, grid, s, a); break;
+        case 4: zksc_launch_round_4(variant, staged, grid, s, a); break;
+        case 5: zksc_launch_round_5(variant, staged, grid, s, a); break;
+        case 6: zksc_launch_round_6(variant, staged, grid, s, a); break;
+        case 7: zksc_launch_round_7(variant, staged, grid, s, a); break;
+        case 8: zksc_launch_round_8(variant, staged, grid, s, a); break;
+        default: return ZKSC_ERR_UNSUPPORTED;
+    }
+    return ZKSC_OK;
+}
+
 // One round: evaluations of every product of every proof at 0..npts_cap-1 (capped by degree+1).
 static int round_evals_impl(zksc_tables* t, uint64_t* out, uint32_t npts_cap) {
     zksc_ctx* ctx = t->ctx;
@@ -629,33 +657,25 @@ static int round_evals_impl(zksc_tables* t, uint64_t* out, uint32_t npts_cap) {
         uint32_t nb = t->B - b0 < (uint32_t)kMaxBatch ? t->B - b0 : kMaxBatch;
         for (uint32_t p = 0; p < t->P; p++) {
             const int D = t->deg[p];
-            int gx = grid_for(ctx, half, kThreads, ctx->occ[D][variant]);
+            // the staged kernel works on whole 32-pair warp tiles and pays off once HBM latency matters
+            const bool staged = ctx->staged && (variant == 0 || ctx->staged_fold) && ctx->occ[D][3 + variant] > 0 && half % kTilePairs == 0 && half >= 4096;
+            int gx = staged ? grid_for(ctx, half / kTilePairs * 32, kThreads, ctx->occ[D][3 + variant]) : grid_for(ctx, half, kThreads, ctx->occ[D][variant]);
             TRY(ensure_partials(ctx, (size_t)nb * gx * (D + 1)));
-            RoundArgs a;
-            a.in = gi.base + (size_t)b0 * gi.proof_stride + (size_t)t->koff[p] * gi.tab_stride;
-            a.out = go.base + (size_t)b0 * go.proof_stride + (size_t)t->koff[p] * go.tab_stride;
-            a.in_tab_stride = gi.tab_stride; a.in_proof_stride = gi.proof_stride;
-            a.out_tab_stride = go.tab_stride; a.out_proof_stride = go.proof_stride;
-            a.half = half;
-            a.partials = ctx->partials; a.counters = ctx->counters;
-            a.result = res + (size_t)b0 * t->E + t->eoff[p];
-            a.res_stride = t->E;
-            a.npts = (uint32_t)(D + 1) < npts_cap ? (D + 1) : npts_cap;
-            a.flag = nullptr; a.flag_value = 0;
-            if (fold) for (uint32_t b = 0; b < nb; b++) a.chal[b] = t->pending_chal[b0 + b];
+            RoundBase base;
+            base.in = gi.base + (size_t)b0 * gi.proof_stride + (size_t)t->koff[p] * gi.tab_stride;
+            base.out = go.base + (size_t)b0 * go.proof_stride + (size_t)t->koff[p] * go.tab_stride;
+            base.in_tab_stride = gi.tab_stride; base.in_proof_stride = gi.proof_stride;
+            base.out_tab_stride = go.tab_stride; base.out_proof_stride = go.proof_stride;
+            base.half = half;
+            base.partials = ctx->partials; base.counters = ctx->counters;
+            base.result = res + (size_t)b0 * t->E + t->eoff[p];
+            base.res_stride = t->E;
+            base.npts = (uint32_t)(D + 1) < npts_cap ? (D + 1) : npts_cap;
+            base.flag = nullptr; base.flag_value = 0;
             dim3 grid(gx, nb);
             TRY(timing_open(ctx, D, fold, half, nb));
-            switch (D) {
-                case 1: zksc_launch_round_1(variant, grid, ctx->stream, a); break;
-                case 2: zksc_launch_round_2(variant, grid, ctx->stream, a); break;
-                case 3: zksc_launch_round_3(variant, grid, ctx->stream, a); break;
-                case 4: zksc_launch_round_4(variant, grid, ctx->stream, a); break;
-                case 5: zksc_launch_round_5(variant, grid, ctx->stream, a); break;
-                case 6: zksc_launch_round_6(variant, grid, ctx->stream, a); break;
-                case 7: zksc_launch_round_7(variant, grid, ctx->stream, a); break;
-                case 8: zksc_launch_round_8(variant, grid, ctx->stream, a); break;
-                default: FAIL(ZKSC_ERR_UNSUPPORTED, "degree");
-            }
+            int rc = (nb == 1) ? launch_round<1>(t, base, D, variant, staged, grid, fold, b0, nb) : launch_round<kMaxBatch>(t, base, D, variant, staged, grid, fold, b0, nb);
+            if (rc != ZKSC_OK) FAIL(rc, "degree");
             TRY(timing_close(ctx));
             ctx->launches++;
             CK(cudaGetLastError());
@@ -714,7 +734,11 @@ extern "C" int zksc_bind(zksc_tables* t, const uint64_t* challenges) {
     }
     if (ctx->n_ranks > 1 && t->where != 2 && t->cur_n == 1) TRY(gather_tail(t));
     t->pending_chal.resize(t->B);
-    for (uint32_t b = 0; b < t->B; b++) memcpy(t->pending_chal[b].l, challenges + 4 * b, 32);
+    t->pending_tab.resize(t->B);
+    for (uint32_t b = 0; b < t->B; b++) {
+        memcpy(t->pending_chal[b].l, challenges + 4 * b, 32);
+        host::fold_table(load_h(challenges + 4 * b), t->pending_tab[b].w);
+    }
     t->pending = true;
     t->vars_left--;
     // claim for the next round: this round's polynomial of every product at the challenge
