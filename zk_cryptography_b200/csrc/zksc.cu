@@ -75,7 +75,12 @@ struct zksc_ctx {
     unsigned int* counters = nullptr;
     Fr* results_dev = nullptr;   // [n_ranks][kMaxBatch * kMaxEvals] (allgather target)
     Fr* results_send = nullptr;  // [kMaxBatch * kMaxEvals]
-    Fr* results_host = nullptr;  // pinned mirror of results_dev
+    Fr* results_host = nullptr;  // pinned, device-mapped: the final block of a round writes the evaluations straight into it
+    Fr* results_host_dev = nullptr;   // device address of results_host
+    volatile unsigned int* flag_host = nullptr;   // pinned, device-mapped completion word of the current round (system-scope store by the kernel)
+    unsigned int* flag_dev = nullptr;
+    unsigned int flag_seq = 0;
+    bool mapped_results = true;  // ZKSC_NO_MAPPED=1: cudaMemcpyAsync + stream synchronize per round instead
     size_t results_cap = 0;      // elements per rank slot
     int occ[kMaxDegree + 1][6];   // resident CTAs per SM of round_kernel<D, variant> (0..2) and round_tma_kernel (3..5; 0 = none)
     bool staged = true;           // use the TMA-staged kernels where they apply (ZKSC_NO_STAGED=1 turns them off)
@@ -190,6 +195,16 @@ extern "C" int zksc_ctx_create(int device, zksc_ctx** out) {
 #define ZKSC_OCC(D) zksc_prepare_round_##D(); for (int v = 0; v < 6; v++) ctx->occ[D][v] = zksc_occ_round_##D(v);
     ZKSC_OCC(1) ZKSC_OCC(2) ZKSC_OCC(3) ZKSC_OCC(4) ZKSC_OCC(5) ZKSC_OCC(6) ZKSC_OCC(7) ZKSC_OCC(8)
     if ((e = cudaGetLastError()) != cudaSuccess) return fail(e, "occupancy query (is this an sm_100a device?)");
+    {
+        void* fh = nullptr;
+        if ((e = cudaHostAlloc(&fh, 64, cudaHostAllocMapped)) != cudaSuccess) return fail(e, "cudaHostAlloc(flag)");
+        memset(fh, 0, 64);
+        ctx->flag_host = (volatile unsigned int*)fh;
+        void* fd = nullptr;
+        if ((e = cudaHostGetDevicePointer(&fd, fh, 0)) != cudaSuccess) return fail(e, "cudaHostGetDevicePointer(flag)");
+        ctx->flag_dev = (unsigned int*)fd;
+    }
+    { const char* e_ = getenv("ZKSC_NO_MAPPED"); ctx->mapped_results = !(e_ && e_[0] == '1'); }
     { const char* e_ = getenv("ZKSC_NO_STAGED"); ctx->staged = !(e_ && e_[0] == '1'); }
     { const char* e_ = getenv("ZKSC_STAGED_FOLD"); ctx->staged_fold = (e_ && e_[0] == '1'); }
     *out = ctx;
@@ -209,6 +224,7 @@ extern "C" int zksc_ctx_destroy(zksc_ctx* ctx) {
     cudaFree(ctx->results_dev);
     cudaFree(ctx->results_send);
     cudaFreeHost(ctx->results_host);
+    cudaFreeHost((void*)ctx->flag_host);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return ZKSC_OK;
@@ -327,7 +343,8 @@ static int ensure_results(zksc_ctx* ctx, size_t elems) {
     ctx->results_dev = nullptr; ctx->results_send = nullptr; ctx->results_host = nullptr; ctx->results_cap = 0;
     CK(cudaMalloc(&ctx->results_dev, elems * ctx->n_ranks * sizeof(Fr)));
     CK(cudaMalloc(&ctx->results_send, elems * sizeof(Fr)));
-    CK(cudaHostAlloc(&ctx->results_host, elems * ctx->n_ranks * sizeof(Fr), cudaHostAllocDefault));
+    CK(cudaHostAlloc(&ctx->results_host, elems * ctx->n_ranks * sizeof(Fr), cudaHostAllocMapped));
+    { void* d = nullptr; CK(cudaHostGetDevicePointer(&d, ctx->results_host, 0)); ctx->results_host_dev = (Fr*)d; }
     ctx->results_cap = elems;
     return ZKSC_OK;
 }
@@ -602,6 +619,28 @@ static int gather_tail(zksc_tables* t) {
 #endif
 }
 
+// Wait for the round's completion word (written by the last block of the round's last launch, after its
+// results, with a system-scope fence in between).  Polling a pinned word costs ~1 us after the kernel's
+// store; cudaMemcpyAsync + cudaStreamSynchronize cost ~15 us per round.  The stream is queried now and then so
+// that a failed launch surfaces as an error instead of an endless spin.
+static int wait_flag(zksc_ctx* ctx, unsigned int seq) {
+    for (unsigned long long spins = 1;; spins++) {
+        if (*ctx->flag_host == seq) break;
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+        if ((spins & 0xffff) == 0) {
+            cudaError_t q = cudaStreamQuery(ctx->stream);
+            if (q == cudaErrorNotReady) continue;
+            if (q != cudaSuccess) { ctx->err = std::string("round kernel: ") + cudaGetErrorString(q); return ZKSC_ERR_CUDA; }
+            if (*ctx->flag_host == seq) break;
+            FAIL(ZKSC_ERR_CUDA, "round kernel finished without publishing its results");
+        }
+    }
+    __atomic_thread_fence(__ATOMIC_ACQUIRE);
+    return ZKSC_OK;
+}
+
 // fill in the per-proof challenge data and launch the round kernel of degree D
 template <int NB>
 static int launch_round(const zksc_tables* t, const RoundBase& base, int D, int variant, bool staged, dim3 grid, bool fold, uint32_t b0, uint32_t nb) {
@@ -651,7 +690,9 @@ static int round_evals_impl(zksc_tables* t, uint64_t* out, uint32_t npts_cap) {
     int to = fold ? ((t->where == 0) ? 1 : t->where) : t->where;
     Geo go = geo_of(t, to);
     const unsigned long long half = n_eval / 2;
-    Fr* res = reduce_ranks ? ctx->results_send : ctx->results_dev;
+    const bool mapped = ctx->mapped_results && !reduce_ranks;
+    Fr* res = reduce_ranks ? ctx->results_send : (mapped ? ctx->results_host_dev : ctx->results_dev);
+    const unsigned int seq = ++ctx->flag_seq;
 
     for (uint32_t b0 = 0; b0 < t->B; b0 += kMaxBatch) {
         uint32_t nb = t->B - b0 < (uint32_t)kMaxBatch ? t->B - b0 : kMaxBatch;
@@ -671,7 +712,9 @@ static int round_evals_impl(zksc_tables* t, uint64_t* out, uint32_t npts_cap) {
             base.result = res + (size_t)b0 * t->E + t->eoff[p];
             base.res_stride = t->E;
             base.npts = (uint32_t)(D + 1) < npts_cap ? (D + 1) : npts_cap;
-            base.flag = nullptr; base.flag_value = 0;
+            const bool last_launch = (b0 + nb == t->B) && (p + 1 == t->P);
+            base.flag = (mapped && last_launch) ? ctx->flag_dev : nullptr;
+            base.flag_value = seq;
             dim3 grid(gx, nb);
             TRY(timing_open(ctx, D, fold, half, nb));
             int rc = (nb == 1) ? launch_round<1>(t, base, D, variant, staged, grid, fold, b0, nb) : launch_round<kMaxBatch>(t, base, D, variant, staged, grid, fold, b0, nb);
@@ -684,7 +727,10 @@ static int round_evals_impl(zksc_tables* t, uint64_t* out, uint32_t npts_cap) {
     if (fold) { t->where = to; t->cur_n /= 2; t->pending = false; }
 
     const size_t n_res = (size_t)t->B * t->E;
-    if (!reduce_ranks) {
+    if (mapped) {
+        TRY(wait_flag(ctx, seq));
+        memcpy(out, ctx->results_host, n_res * sizeof(Fr));
+    } else if (!reduce_ranks) {
         CK(cudaMemcpyAsync(ctx->results_host, ctx->results_dev, n_res * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         memcpy(out, ctx->results_host, n_res * sizeof(Fr));
