@@ -336,7 +336,8 @@ def run_b200(args):
         "config": {"workload": "%s: %s" % (args.workload, wl["desc"]), "n_vars": n, "degrees": wl["degs"], "proofs": proofs_total,
                    "table_bytes_per_gpu": int(proofs_local * tables.n_tables * ((1 << n) // (G if sharded else 1)) * 32),
                    "l2_policy": "inputs_exceed_l2" if proofs_local * tables.n_tables * ((1 << n) // (G if sharded else 1)) * 32 > 126e6 * 2 else "inputs_fit_l2_no_flush",
-                   "sharding": ("index mod %d (last-bound variables), per-round ncclAllGather of %d field elements" % (G, tables.n_evals)) if sharded else
+                   "sharding": ("index mod %d (last-bound variables); per round %d field elements per rank exchanged %s" % (
+                                   G, tables.n_evals, "through NVLink peer memory inside the round kernel" if ctx.peer_exchange() else "by ncclAllGather + host sum")) if sharded else
                                ("replicas" if G > 1 else "single GPU"),
                    "proof_bytes": len(_lib.proof_to_bytes(proto, msgs[0], lens[0]))},
         "clocks": sampler.summary(), "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline, "int_roofline": int_roofline,

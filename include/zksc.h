@@ -54,6 +54,9 @@ const char* zksc_last_error(const zksc_ctx* ctx);
 int zksc_comm_unique_id(uint8_t out_id[128]);
 int zksc_comm_init(zksc_ctx* ctx, int n_ranks, int rank, const uint8_t unique_id[128]);
 int zksc_ctx_rank(const zksc_ctx* ctx, int* rank, int* n_ranks);
+/* 1 when the per-round partial evaluations of a sharded context travel through peer memory (CUDA IPC over
+ * NVLink) inside the round kernel, 0 when they go through ncclAllGather + a host sum (single rank: 0). */
+int zksc_ctx_peer_exchange(const zksc_ctx* ctx);
 int zksc_ctx_synchronize(zksc_ctx* ctx);
 /* Measurement hooks (bench.py; no reference counterpart).  zksc_ctx_stream: the cudaStream_t every kernel
  * of this context is launched on (so callers can record their own events on it).  zksc_ctx_launch_count:

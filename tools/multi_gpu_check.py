@@ -38,6 +38,8 @@ def main():
     dist.broadcast(uid, 0)
     ctx.comm_init(world, rank, bytes(uid.cpu().numpy().tobytes()))
     solo = zk.Context(local) if rank == 0 else None
+    if rank == 0:
+        print("peer-memory exchange:", ctx.peer_exchange(), flush=True)
     lg = world.bit_length() - 1
     ok = True
     for n, degs, seed, use_oracle in CASES:

@@ -51,6 +51,7 @@ def lib():
         "zksc_ctx_synchronize": (ctypes.c_int, [vp]),
         "zksc_ctx_stream": (vp, [vp]),
         "zksc_ctx_launch_count": (ctypes.c_ulonglong, [vp]),
+        "zksc_ctx_peer_exchange": (ctypes.c_int, [vp]),
         "zksc_ctx_timing": (ctypes.c_int, [vp, ctypes.c_int]),
         "zksc_ctx_timing_read": (ctypes.c_int, [vp, ctypes.c_uint32, _u32p, ctypes.POINTER(ctypes.c_float), _u32p, _u32p, _u64p, _u64p]),
         "zksc_tables_reupload": (ctypes.c_int, [vp, ctypes.POINTER(_u64p), ctypes.c_int]),
@@ -184,6 +185,9 @@ class Context:
     def stream_handle(self):
         """The cudaStream_t (as int) all kernels of this context run on."""
         return int(lib().zksc_ctx_stream(self._h) or 0)
+
+    def peer_exchange(self):
+        return bool(lib().zksc_ctx_peer_exchange(self._h))
 
     def launch_count(self):
         return int(lib().zksc_ctx_launch_count(self._h))

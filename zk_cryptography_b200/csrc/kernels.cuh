@@ -26,6 +26,23 @@ constexpr int kWarps = kThreads / 32;
 constexpr int kMaxBatch = 64;   // proofs per launch (challenges travel as kernel parameters)
 constexpr int kMaxDegree = 8;
 
+constexpr int kMaxRanks = 8;    // GPUs of one NVSwitch box reachable through peer memory
+// Cross-GPU exchange of a round's partial evaluations, fused into the tail of the round kernel (sharded
+// contexts).  Every rank owns an exchange buffer  data[2][n_ranks][cap]  +  tags[2][n_ranks]  in its own HBM,
+// opened by the peers through CUDA IPC.  The last block of the round stores this rank's partials into slot
+// [seq & 1][rank] of EVERY rank's buffer (peer stores over NVLink), fences, stores the round's sequence
+// number into the matching tag of every rank, waits until all n_ranks tags of its own buffer carry that
+// number, adds the n_ranks partials mod r and writes the sums to the host-mapped result buffer.  No NCCL call,
+// no extra launch, no host reduction.  Two slots suffice: a rank can be at most one round ahead of a peer,
+// because it needs that peer's partials of round s before it can leave round s.
+struct XchArgs {
+    Fr* peer_data[kMaxRanks];
+    unsigned int* peer_tags[kMaxRanks];
+    const Fr* send;            // this rank's partials (n_elems elements, device memory)
+    Fr* out;                   // where the reduced values go (host-mapped)
+    unsigned int n_ranks, rank, seq, n_elems, cap;
+};
+
 struct RoundBase {
     const Fr* in;              // table 0 of proof 0 (current tables)
     Fr* out;                   // FOLD: where the folded tables go (may alias `in`)
@@ -38,7 +55,8 @@ struct RoundBase {
     unsigned int res_stride;
     unsigned int npts;         // evaluation points 0..npts-1 are wanted (<= D+1); SKIP1 kernels leave point 1 untouched
     volatile unsigned int* flag;  // optional: set to flag_value (system scope) after the results
-    unsigned int flag_value;
+    unsigned int flag_value;      // (0xffffffff is stored instead when the exchange timed out)
+    XchArgs xch;                  // n_ranks > 1: exchange + reduce across GPUs before the flag is raised
 };
 // NB = proofs per launch.  The per-proof challenge data travels in the kernel parameters (constant bank): a
 // single-proof launch carries 288 bytes of it, a batched one 18 KiB -- large parameter blocks make every
@@ -96,6 +114,65 @@ ZKSC_DEV Fr acc_finish(const Acc<NL>& a) {
     else return acc17_reduce(a);
 }
 
+ZKSC_DEV Fr ld256_volatile(const Fr* p) {
+    Fr v;
+    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.l[0]), "=r"(v.l[1]), "=r"(v.l[2]), "=r"(v.l[3]) : "l"(p) : "memory");
+    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4+16];" : "=r"(v.l[4]), "=r"(v.l[5]), "=r"(v.l[6]), "=r"(v.l[7]) : "l"(p) : "memory");
+    return v;
+}
+// Two 128-bit stores, for peer / IPC-exported / host-mapped destinations.  Measured on this pool's B200s
+// (driver 580): a 256-bit st.global.v8.u32 (STG.E.ENL2.256) to memory that is exported through CUDA IPC -- local
+// or peer side -- stored only its first 32-bit word; 128-bit stores behave.
+ZKSC_DEV void st256_2x128(Fr* p, const Fr& v) {
+    asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.l[0]), "r"(v.l[1]), "r"(v.l[2]), "r"(v.l[3]) : "memory");
+    asm volatile("st.global.v4.u32 [%0+16], {%1,%2,%3,%4};" ::"l"(p), "r"(v.l[4]), "r"(v.l[5]), "r"(v.l[6]), "r"(v.l[7]) : "memory");
+}
+ZKSC_DEV void st_release_sys(unsigned int* p, unsigned int v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+ZKSC_DEV unsigned int ld_acquire_sys(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+ZKSC_DEV unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+constexpr unsigned long long kXchTimeoutNs = 20ull * 1000 * 1000 * 1000;
+
+// The whole (final) block: all-to-all of the partials through peer memory + modular sum.  Returns false on timeout.
+static __device__ __noinline__ bool exchange_partials(const XchArgs& x) {
+    __shared__ unsigned int s_ok;
+    const unsigned int G = x.n_ranks, slot = (x.seq & 1u) * G;
+    __threadfence();                                   // the partials were written by other blocks of this and earlier launches
+    for (unsigned int i = threadIdx.x; i < x.n_elems; i += kThreads) {
+        const Fr v = ld256_volatile(x.send + i);
+        for (unsigned int g = 0; g < G; g++) st256_2x128(x.peer_data[g] + (size_t)(slot + x.rank) * x.cap + i, v);
+    }
+    if (threadIdx.x == 0) s_ok = 1u;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < G) {
+        st_release_sys(x.peer_tags[threadIdx.x] + slot + x.rank, x.seq);
+        const unsigned int* mine = x.peer_tags[x.rank] + slot + threadIdx.x;
+        const unsigned long long t0 = global_timer_ns();
+        while (ld_acquire_sys(mine) != x.seq) {
+            if (global_timer_ns() - t0 > kXchTimeoutNs) { s_ok = 0u; break; }
+        }
+    }
+    __syncthreads();
+    if (!s_ok) return false;
+    __threadfence_system();
+    const Fr* data = x.peer_data[x.rank] + (size_t)slot * x.cap;
+    for (unsigned int i = threadIdx.x; i < x.n_elems; i += kThreads) {
+        Fr s = ld256_volatile(data + i);
+        for (unsigned int g = 1; g < G; g++) s = fr_add(s, ld256_volatile(data + (size_t)g * x.cap + i));
+        st256_2x128(x.out + i, s);
+    }
+    __syncthreads();
+    return true;
+}
+
 // Block-level reduction of NP accumulators, publication of the block partial, and -- in the last
 // block of each proof to arrive -- the final cross-block sum.
 // Accumulator slot s holds evaluation point s, or with SKIP1 point (s == 0 ? 0 : s + 1).
@@ -147,22 +224,32 @@ ZKSC_DEV void reduce_and_publish(Acc<NL> (&acc)[NP], const RoundBase& args, int 
         acc_warp_reduce(a);
         if (lane == 0) {
             Fr v = acc9_reduce(a);
-            st256(args.result + (size_t)proof * args.res_stride + point_of(p), v);
+            st256_2x128(args.result + (size_t)proof * args.res_stride + point_of(p), v);   // may be host-mapped
         }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         args.counters[proof] = 0;
+        bool final_block = false;
         if (args.flag) {
             __threadfence_system();
             // one flag word per proof would be wasteful: proofs bump a shared word via the counter slot
             unsigned int fin = atomicAdd(args.counters + gridDim.y, 1u);
             if (fin == gridDim.y - 1) {
                 args.counters[gridDim.y] = 0;
-                __threadfence_system();
-                *args.flag = args.flag_value;
+                final_block = true;
             }
         }
+        s_last = final_block;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    // the block that finished the launch's last proof: exchange across GPUs if asked, then raise the flag
+    unsigned int flag_value = args.flag_value;
+    if (args.xch.n_ranks > 1 && !exchange_partials(args.xch)) flag_value = 0xffffffffu;
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        *args.flag = flag_value;
     }
 }
 

@@ -12,6 +12,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -33,6 +34,9 @@ using zksc::host::FrH;
 static_assert(kMaxDegree == ZKSC_MAX_DEGREE, "header / kernel limits differ");
 
 static thread_local std::string g_create_error;
+
+constexpr size_t kXchTagBytes = 256;               // 2 * kMaxRanks tags, padded
+constexpr unsigned int kXchCap = 2048;             // elements per (slot, rank): rounds with more partials use NCCL
 
 // ------------------------------------------------------------------------------------------------
 // NCCL, loaded at run time (single-GPU use must not depend on libnccl being present)
@@ -87,6 +91,14 @@ struct zksc_ctx {
     bool staged_fold = false;     // ... also for the fused fold+evaluate rounds (ZKSC_STAGED_FOLD=1; slower today: DESIGN.md)
     std::string err;
     int rank = 0, n_ranks = 1;
+    // ZKSC_PROFILE=1: host-side wall-clock split of every round of zksc_prove, printed to stderr (ns)
+    bool profile = false;
+    double prof_launch = 0, prof_wait = 0;
+    // peer-memory exchange of the per-round partials (sharded contexts; kernels.cuh XchArgs)
+    bool p2p = false;
+    unsigned char* xch_local = nullptr;            // tags[2][n_ranks] (first kXchTagBytes) then data[2][n_ranks][kXchCap]
+    void* xch_peer[kMaxRanks] = {};                // the same buffer of every rank (own entry = xch_local)
+    unsigned int xch_seq = 0;
 #if ZKSC_HAVE_NCCL_H
     ncclComm_t comm = nullptr;
 #endif
@@ -205,6 +217,7 @@ extern "C" int zksc_ctx_create(int device, zksc_ctx** out) {
         ctx->flag_dev = (unsigned int*)fd;
     }
     { const char* e_ = getenv("ZKSC_NO_MAPPED"); ctx->mapped_results = !(e_ && e_[0] == '1'); }
+    { const char* e_ = getenv("ZKSC_PROFILE"); ctx->profile = (e_ && e_[0] == '1'); }
     { const char* e_ = getenv("ZKSC_NO_STAGED"); ctx->staged = !(e_ && e_[0] == '1'); }
     { const char* e_ = getenv("ZKSC_STAGED_FOLD"); ctx->staged_fold = (e_ && e_[0] == '1'); }
     *out = ctx;
@@ -215,6 +228,9 @@ extern "C" int zksc_ctx_destroy(zksc_ctx* ctx) {
     if (!ctx) return ZKSC_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    for (int g = 0; g < ctx->n_ranks && g < kMaxRanks; g++)
+        if (ctx->xch_peer[g] && g != ctx->rank) cudaIpcCloseMemHandle(ctx->xch_peer[g]);
+    cudaFree(ctx->xch_local);
 #if ZKSC_HAVE_NCCL_H
     if (ctx->comm) g_nccl.CommDestroy(ctx->comm);
 #endif
@@ -245,6 +261,8 @@ extern "C" int zksc_ctx_rank(const zksc_ctx* ctx, int* rank, int* n_ranks) {
     if (n_ranks) *n_ranks = ctx->n_ranks;
     return ZKSC_OK;
 }
+
+extern "C" int zksc_ctx_peer_exchange(const zksc_ctx* ctx) { return (ctx && ctx->p2p) ? 1 : 0; }
 
 extern "C" void* zksc_ctx_stream(zksc_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
@@ -314,6 +332,61 @@ extern "C" int zksc_comm_unique_id(uint8_t out_id[128]) {
 #endif
 }
 
+#if ZKSC_HAVE_NCCL_H
+// Open every rank's exchange buffer through CUDA IPC (handles travel once through ncclAllGather).  All ranks
+// must agree on whether the peer path is usable: a last all-gather of one status word settles it; on any
+// failure every rank keeps the ncclAllGather + host-sum path.  ZKSC_NO_P2P=1 (on every rank) forces that path.
+static int setup_peer_exchange(zksc_ctx* ctx) {
+    ctx->p2p = false;
+    const int G = ctx->n_ranks;
+    { const char* e_ = getenv("ZKSC_NO_P2P"); if (e_ && e_[0] == '1') return ZKSC_OK; }
+    if (G > kMaxRanks) return ZKSC_OK;
+    const size_t bytes = kXchTagBytes + (size_t)2 * G * kXchCap * sizeof(Fr);
+    struct Msg { cudaIpcMemHandle_t h; unsigned int ok; unsigned int pad[15]; };
+    static_assert(sizeof(Msg) == 128, "exchange handle message");
+    Msg mine;
+    memset(&mine, 0, sizeof(mine));
+    mine.ok = 1;
+    if (cudaMalloc(&ctx->xch_local, bytes) != cudaSuccess || cudaMemsetAsync(ctx->xch_local, 0, bytes, ctx->stream) != cudaSuccess ||
+        cudaIpcGetMemHandle(&mine.h, ctx->xch_local) != cudaSuccess) {
+        cudaGetLastError();
+        mine.ok = 0;
+    }
+    unsigned char* dev = nullptr;
+    CK(cudaMalloc(&dev, sizeof(Msg) * (G + 1)));
+    std::vector<Msg> all(G);
+    auto gather = [&](const Msg& m) -> int {
+        CK(cudaMemcpyAsync(dev + sizeof(Msg) * G, &m, sizeof(Msg), cudaMemcpyHostToDevice, ctx->stream));
+        ncclResult_t r = g_nccl.AllGather(dev + sizeof(Msg) * G, dev, sizeof(Msg), ncclUint8, ctx->comm, ctx->stream);
+        if (r != ncclSuccess) FAIL(ZKSC_ERR_COMM, std::string("ncclAllGather(ipc handles): ") + g_nccl.GetErrorString(r));
+        CK(cudaMemcpyAsync(all.data(), dev, sizeof(Msg) * G, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        return ZKSC_OK;
+    };
+    int rc = gather(mine);
+    if (rc != ZKSC_OK) { cudaFree(dev); return rc; }
+    bool ok = true;
+    for (int g = 0; g < G; g++) ok = ok && all[g].ok;
+    if (ok) {
+        for (int g = 0; g < G && ok; g++) {
+            if (g == ctx->rank) { ctx->xch_peer[g] = ctx->xch_local; continue; }
+            if (cudaIpcOpenMemHandle(&ctx->xch_peer[g], all[g].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                ctx->xch_peer[g] = nullptr;
+                ok = false;
+            }
+        }
+    }
+    mine.ok = ok ? 1 : 0;
+    rc = gather(mine);                                  // second pass: did everyone manage to open everyone?
+    cudaFree(dev);
+    if (rc != ZKSC_OK) return rc;
+    for (int g = 0; g < G; g++) ok = ok && all[g].ok;
+    ctx->p2p = ok;
+    return ZKSC_OK;
+}
+#endif
+
 extern "C" int zksc_comm_init(zksc_ctx* ctx, int n_ranks, int rank, const uint8_t unique_id[128]) {
     if (!ctx) return ZKSC_ERR_STATE;
     if (n_ranks < 1 || (n_ranks & (n_ranks - 1)) || rank < 0 || rank >= n_ranks) FAIL(ZKSC_ERR_SHAPE, "n_ranks must be a power of two and 0 <= rank < n_ranks");
@@ -330,7 +403,7 @@ extern "C" int zksc_comm_init(zksc_ctx* ctx, int n_ranks, int rank, const uint8_
     // result buffers are sized per rank count: drop them so the next use re-allocates
     cudaFree(ctx->results_dev); cudaFree(ctx->results_send); cudaFreeHost(ctx->results_host);
     ctx->results_dev = nullptr; ctx->results_send = nullptr; ctx->results_host = nullptr; ctx->results_cap = 0;
-    return ZKSC_OK;
+    return setup_peer_exchange(ctx);
 #else
     FAIL(ZKSC_ERR_COMM, "built without nccl.h");
 #endif
@@ -625,7 +698,9 @@ static int gather_tail(zksc_tables* t) {
 // that a failed launch surfaces as an error instead of an endless spin.
 static int wait_flag(zksc_ctx* ctx, unsigned int seq) {
     for (unsigned long long spins = 1;; spins++) {
-        if (*ctx->flag_host == seq) break;
+        const unsigned int f = *ctx->flag_host;
+        if (f == seq) break;
+        if (f == 0xffffffffu) { *ctx->flag_host = 0; FAIL(ZKSC_ERR_COMM, "timed out waiting for a peer GPU's partial evaluations"); }
 #if defined(__x86_64__)
         __builtin_ia32_pause();
 #endif
@@ -674,6 +749,7 @@ static int round_evals_impl(zksc_tables* t, uint64_t* out, uint32_t npts_cap) {
         t->last_evals_valid = true;
         return ZKSC_OK;
     }
+    const auto prof_t0 = std::chrono::steady_clock::now();
     const bool sharded_phase = (ctx->n_ranks > 1 && t->where != 2);
     if (sharded_phase) {
         uint64_t n_after = t->pending ? t->cur_n / 2 : t->cur_n;
@@ -690,9 +766,12 @@ static int round_evals_impl(zksc_tables* t, uint64_t* out, uint32_t npts_cap) {
     int to = fold ? ((t->where == 0) ? 1 : t->where) : t->where;
     Geo go = geo_of(t, to);
     const unsigned long long half = n_eval / 2;
-    const bool mapped = ctx->mapped_results && !reduce_ranks;
+    const size_t n_res = (size_t)t->B * t->E;
+    const bool peer = reduce_ranks && ctx->p2p && n_res <= kXchCap;   // exchange + sum inside the round kernel
+    const bool mapped = (ctx->mapped_results && !reduce_ranks) || peer;
     Fr* res = reduce_ranks ? ctx->results_send : (mapped ? ctx->results_host_dev : ctx->results_dev);
     const unsigned int seq = ++ctx->flag_seq;
+    if (peer) ctx->xch_seq++;
 
     for (uint32_t b0 = 0; b0 < t->B; b0 += kMaxBatch) {
         uint32_t nb = t->B - b0 < (uint32_t)kMaxBatch ? t->B - b0 : kMaxBatch;
@@ -715,6 +794,16 @@ static int round_evals_impl(zksc_tables* t, uint64_t* out, uint32_t npts_cap) {
             const bool last_launch = (b0 + nb == t->B) && (p + 1 == t->P);
             base.flag = (mapped && last_launch) ? ctx->flag_dev : nullptr;
             base.flag_value = seq;
+            base.xch.n_ranks = 0;
+            if (peer && last_launch) {
+                XchArgs& x = base.xch;
+                for (int g = 0; g < ctx->n_ranks; g++) {
+                    x.peer_tags[g] = (unsigned int*)ctx->xch_peer[g];
+                    x.peer_data[g] = (Fr*)((unsigned char*)ctx->xch_peer[g] + kXchTagBytes);
+                }
+                x.send = ctx->results_send; x.out = ctx->results_host_dev;
+                x.n_ranks = ctx->n_ranks; x.rank = ctx->rank; x.seq = ctx->xch_seq; x.n_elems = (unsigned int)n_res; x.cap = kXchCap;
+            }
             dim3 grid(gx, nb);
             TRY(timing_open(ctx, D, fold, half, nb));
             int rc = (nb == 1) ? launch_round<1>(t, base, D, variant, staged, grid, fold, b0, nb) : launch_round<kMaxBatch>(t, base, D, variant, staged, grid, fold, b0, nb);
@@ -726,9 +815,11 @@ static int round_evals_impl(zksc_tables* t, uint64_t* out, uint32_t npts_cap) {
     }
     if (fold) { t->where = to; t->cur_n /= 2; t->pending = false; }
 
-    const size_t n_res = (size_t)t->B * t->E;
     if (mapped) {
+        const auto w0 = std::chrono::steady_clock::now();
+        ctx->prof_launch = std::chrono::duration<double, std::micro>(w0 - prof_t0).count();
         TRY(wait_flag(ctx, seq));
+        ctx->prof_wait = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - w0).count();
         memcpy(out, ctx->results_host, n_res * sizeof(Fr));
     } else if (!reduce_ranks) {
         CK(cudaMemcpyAsync(ctx->results_host, ctx->results_dev, n_res * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
@@ -921,7 +1012,9 @@ extern "C" int zksc_prove(zksc_tables* t, int protocol, const uint64_t* sums, ui
     std::vector<uint8_t> bytes;
     memset(round_msgs, 0, (size_t)B * n * stride * 32);
     for (uint32_t round = 0; round < n; round++) {
+        const auto p0 = std::chrono::steady_clock::now();
         TRY(round_evals_impl(t, ev.data(), ZKSC_MAX_DEGREE + 1));
+        const auto p1 = std::chrono::steady_clock::now();
         for (uint32_t b = 0; b < B; b++) {
             uint64_t* msg = round_msgs + ((size_t)b * n + round) * stride * 4;
             uint32_t* len = round_len + (size_t)b * n + round;
@@ -955,7 +1048,14 @@ extern "C" int zksc_prove(zksc_tables* t, int protocol, const uint64_t* sums, ui
             store_h(&chal[4 * b], r);
             store_h(challenges + ((size_t)b * n + round) * 4, r);
         }
+        const auto p2 = std::chrono::steady_clock::now();
         TRY(zksc_bind(t, chal.data()));                               // :103-105 (deferred, fused)
+        if (ctx->profile) {
+            const auto p3 = std::chrono::steady_clock::now();
+            auto us = [](auto a, auto b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+            fprintf(stderr, "[zksc profile] round %2u: evals %7.1f us (launch %6.1f, wait %7.1f)  transcript %5.1f  bind %5.1f\n", round, us(p0, p1),
+                    ctx->prof_launch, ctx->prof_wait, us(p1, p2), us(p2, p3));
+        }
     }
     return ZKSC_OK;
 }
