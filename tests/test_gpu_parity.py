@@ -274,6 +274,80 @@ def test_low_level_round_api_vs_model(ctx):
     t.free()
 
 
+def _model_polys(tabs, degs):
+    out, k = [], 0
+    for d in degs:
+        out.append(pm.ComposedMultilinear([pm.Multilinear(t) for t in tabs[k:k + d]]))
+        k += d
+    return out
+
+
+def test_resident_tail_kernel_call_patterns(ctx):
+    """The persistent tail kernel (K4) is started by round_evals once the tables are small and fed by bind; any other
+    call pattern must stop it without losing state: repeated round_evals, binds in a row, residual / reset / a second
+    handle / a stand-alone Multilinear operation in the middle of a tail."""
+    rng = random.Random(77)
+    n, degs = 7, [2, 1, 3]
+    tabs = [[rng.randrange(R) for _ in range(1 << n)] for _ in range(sum(degs))]
+    t = zk.Tables.upload(ctx, n, degs, [zk.to_mont(x) for x in tabs])
+    other = zk.Tables.synth(ctx, 5, [2], 9)
+    cur = _model_polys(tabs, degs)
+
+    def model_evals():
+        return [v for p in cur for v in pm.round_evals(p)]
+
+    def bind(r):
+        nonlocal cur
+        t.bind(zk.to_mont(r))
+        cur = [p.partial_evaluation(r, 0) for p in cur]
+
+    assert zk.from_mont(t.round_evals()[0]) == model_evals()          # round 0: ordinary launch
+    bind(rng.randrange(R))
+    assert zk.from_mont(t.round_evals()[0]) == model_evals()          # round 1: the tail kernel starts here
+    assert zk.from_mont(t.round_evals()[0]) == model_evals()          # asked again without a bind: tail stopped, recomputed
+    bind(rng.randrange(R))
+    assert zk.from_mont(t.round_evals()[0]) == model_evals()          # round 2 (tail again)
+    bind(rng.randrange(R))
+    bind(rng.randrange(R))                                            # two binds in a row with a tail resident
+    assert zk.from_mont(t.round_evals()[0]) == model_evals()          # round 4
+    bind(rng.randrange(R))
+    o = other.poly_sum()                                              # another handle takes the stream mid-tail
+    assert zk.from_mont(o[0]) == sum(a * b for a, b in zip(*[cref.canon_to_ints(cref.synth_table(9, k, 5)) for k in range(2)])) % R
+    assert zk.from_mont(t.round_evals()[0]) == model_evals()          # round 5
+    bind(rng.randrange(R))
+    m = zk.Multilinear([1, 2, 3, 4]).partial_evaluation(5, 0)            # a stand-alone operation on the same context mid-tail
+    assert m.to_ints() == [(1 + 5 * 2) % R, (2 + 5 * 2) % R]
+    res = t.residual()[0]                                             # residual with a challenge posted to the tail
+    assert [zk.from_mont(res[k]) for k in range(sum(degs))] == [m.evaluations for p in cur for m in p.polys]
+    assert zk.from_mont(t.round_evals()[0]) == model_evals()          # last round, after the residual read
+    t.reset()                                                         # and from the top again, as a whole proof
+    s = t.poly_sum()
+    msgs, lens, chal = t.prove(zk.PROTO_MULTI_PARTIAL, s)
+    proof, ch = pm.MultiComposedSumcheckProver.prove_partial(_model_polys(tabs, degs), zk.from_mont(s[0]))
+    assert _lib.proof_to_bytes(zk.PROTO_MULTI_PARTIAL, msgs[0], lens[0]) == proof.to_bytes()
+    assert zk.from_mont(chal[0]) == ch
+    t.free()
+    other.free()
+
+
+def test_tail_kernel_off_gives_identical_proofs():
+    """ZKSC_NO_TAIL=1 (every round its own launch) and the default (resident tail kernel) must agree byte for byte."""
+    import os
+    outs = []
+    for flag in ("0", "1"):
+        os.environ["ZKSC_NO_TAIL"] = flag
+        c = zk.Context(0)
+        t = zk.Tables.synth(c, 13, [3, 2], 4242, n_proofs=3)
+        s = t.poly_sum()
+        msgs, lens, chal = t.prove(zk.PROTO_MULTI_PARTIAL, s)
+        outs.append((msgs.copy(), lens.copy(), chal.copy()))
+        t.free()
+        c.close()
+    os.environ.pop("ZKSC_NO_TAIL")
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
+
+
 def test_batched_independent_proofs(ctx):
     """config 5 shape at small size: many independent proofs in one launch per round (incl. > 64 proofs)"""
     n, degs = 8, [2]

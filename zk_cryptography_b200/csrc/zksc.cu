@@ -20,6 +20,7 @@
 #include "host_field.hpp"
 #include "aux_kernels.cuh"
 #include "kernels.cuh"
+#include "tail_kernel.cuh"
 
 #if __has_include(<nccl.h>)
 #include <nccl.h>
@@ -32,6 +33,8 @@ using namespace zksc;
 using zksc::host::FrH;
 
 static_assert(kMaxDegree == ZKSC_MAX_DEGREE, "header / kernel limits differ");
+static_assert(kTailMaxProducts == ZKSC_MAX_PRODUCTS, "header / tail kernel limits differ");
+void zksc_launch_tail(dim3 grid, cudaStream_t s, const TailArgs& a);   // tail_inst.cu
 
 static thread_local std::string g_create_error;
 
@@ -91,6 +94,15 @@ struct zksc_ctx {
     bool staged_fold = false;     // ... also for the fused fold+evaluate rounds (ZKSC_STAGED_FOLD=1; slower today: DESIGN.md)
     std::string err;
     int rank = 0, n_ranks = 1;
+    // persistent tail kernel (tail_kernel.cuh): mailbox + result units in pinned, device-mapped host memory
+    bool tail_enabled = true;            // ZKSC_NO_TAIL=1: every round is its own launch
+    volatile uint64_t* tail_mail = nullptr;    // [tail_proofs_cap][kMailUnits]   {word | seq << 32}
+    volatile uint64_t* tail_res = nullptr;     // [tail_units_cap]                {limb | seq << 32}
+    uint2* tail_mail_dev = nullptr;
+    uint2* tail_res_dev = nullptr;
+    size_t tail_proofs_cap = 0, tail_units_cap = 0;
+    unsigned int tail_seq = 0;           // last sequence number handed out
+    struct zksc_tables* active_tail = nullptr;   // the handle whose tail kernel is resident on `stream` (at most one)
     // ZKSC_PROFILE=1: host-side wall-clock split of every round of zksc_prove, printed to stderr (ns)
     bool profile = false;
     double prof_launch = 0, prof_wait = 0;
@@ -136,6 +148,11 @@ struct zksc_tables {
     bool last_evals_valid = false;
     std::vector<FrH> claim;             // [B][P]
     bool claim_valid = false;
+    // persistent tail kernel state
+    bool tail_running = false;          // the kernel is resident and has rounds left
+    bool tail_posted = false;           // a challenge has been posted whose round result has not been collected
+    unsigned int tail_left = 0;         // rounds whose result has not been collected
+    unsigned int tail_cur = 0;          // sequence number of the round posted last
 };
 
 #define CK(call)                                                                                          \
@@ -156,6 +173,9 @@ struct zksc_tables {
         int rc_ = (expr);      \
         if (rc_ != ZKSC_OK) return rc_; \
     } while (0)
+
+static int tail_stop(zksc_tables* t);
+static int quiesce(zksc_ctx* ctx);
 
 static inline FrH to_host(const Fr& f) { FrH h; memcpy(h.v, f.l, 32); return h; }
 static inline FrH load_h(const uint64_t* p) { FrH h; memcpy(h.v, p, 32); return h; }
@@ -218,6 +238,7 @@ extern "C" int zksc_ctx_create(int device, zksc_ctx** out) {
     }
     { const char* e_ = getenv("ZKSC_NO_MAPPED"); ctx->mapped_results = !(e_ && e_[0] == '1'); }
     { const char* e_ = getenv("ZKSC_PROFILE"); ctx->profile = (e_ && e_[0] == '1'); }
+    { const char* e_ = getenv("ZKSC_NO_TAIL"); ctx->tail_enabled = !(e_ && e_[0] == '1'); }
     { const char* e_ = getenv("ZKSC_NO_STAGED"); ctx->staged = !(e_ && e_[0] == '1'); }
     { const char* e_ = getenv("ZKSC_STAGED_FOLD"); ctx->staged_fold = (e_ && e_[0] == '1'); }
     *out = ctx;
@@ -227,6 +248,7 @@ extern "C" int zksc_ctx_create(int device, zksc_ctx** out) {
 extern "C" int zksc_ctx_destroy(zksc_ctx* ctx) {
     if (!ctx) return ZKSC_OK;
     cudaSetDevice(ctx->device);
+    quiesce(ctx);
     cudaStreamSynchronize(ctx->stream);
     for (int g = 0; g < ctx->n_ranks && g < kMaxRanks; g++)
         if (ctx->xch_peer[g] && g != ctx->rank) cudaIpcCloseMemHandle(ctx->xch_peer[g]);
@@ -241,6 +263,8 @@ extern "C" int zksc_ctx_destroy(zksc_ctx* ctx) {
     cudaFree(ctx->results_send);
     cudaFreeHost(ctx->results_host);
     cudaFreeHost((void*)ctx->flag_host);
+    cudaFreeHost((void*)ctx->tail_mail);
+    cudaFreeHost((void*)ctx->tail_res);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return ZKSC_OK;
@@ -251,6 +275,7 @@ extern "C" const char* zksc_last_error(const zksc_ctx* ctx) { return ctx ? ctx->
 extern "C" int zksc_ctx_synchronize(zksc_ctx* ctx) {
     if (!ctx) return ZKSC_ERR_STATE;
     CK(cudaSetDevice(ctx->device));
+    TRY(quiesce(ctx));
     CK(cudaStreamSynchronize(ctx->stream));
     return ZKSC_OK;
 }
@@ -271,6 +296,7 @@ extern "C" unsigned long long zksc_ctx_launch_count(const zksc_ctx* ctx) { retur
 extern "C" int zksc_ctx_timing(zksc_ctx* ctx, int enable) {
     if (!ctx) return ZKSC_ERR_STATE;
     CK(cudaSetDevice(ctx->device));
+    TRY(quiesce(ctx));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->timing = enable != 0;
     ctx->n_recs = 0;
@@ -281,6 +307,7 @@ extern "C" int zksc_ctx_timing_read(zksc_ctx* ctx, uint32_t cap, uint32_t* n_out
                                     uint64_t* proofs) {
     if (!ctx || !n_out) return ZKSC_ERR_STATE;
     CK(cudaSetDevice(ctx->device));
+    TRY(quiesce(ctx));
     CK(cudaStreamSynchronize(ctx->stream));
     uint32_t n = 0;
     for (size_t i = 0; i < ctx->n_recs && n < cap; i++, n++) {
@@ -390,6 +417,7 @@ static int setup_peer_exchange(zksc_ctx* ctx) {
 extern "C" int zksc_comm_init(zksc_ctx* ctx, int n_ranks, int rank, const uint8_t unique_id[128]) {
     if (!ctx) return ZKSC_ERR_STATE;
     if (n_ranks < 1 || (n_ranks & (n_ranks - 1)) || rank < 0 || rank >= n_ranks) FAIL(ZKSC_ERR_SHAPE, "n_ranks must be a power of two and 0 <= rank < n_ranks");
+    TRY(quiesce(ctx));
     if (n_ranks == 1) { ctx->rank = 0; ctx->n_ranks = 1; return ZKSC_OK; }
 #if ZKSC_HAVE_NCCL_H
     if (!g_nccl.load(ctx->err)) return ZKSC_ERR_COMM;
@@ -442,6 +470,7 @@ struct DevBuf {
 static int tables_alloc(zksc_ctx* ctx, uint32_t n_vars, uint32_t B, uint32_t P, const uint32_t* degree, zksc_tables** out) {
     if (!ctx || !out || !degree) return ZKSC_ERR_SHAPE;
     *out = nullptr;
+    TRY(quiesce(ctx));
     if (B < 1 || P < 1 || P > ZKSC_MAX_PRODUCTS) FAIL(ZKSC_ERR_SHAPE, "need 1 <= n_products <= ZKSC_MAX_PRODUCTS and n_proofs >= 1");
     if (n_vars > 40) FAIL(ZKSC_ERR_SHAPE, "n_vars too large");
     int lg = 0;
@@ -480,6 +509,7 @@ static int tables_alloc(zksc_ctx* ctx, uint32_t n_vars, uint32_t B, uint32_t P, 
 
 extern "C" int zksc_tables_reset(zksc_tables* t) {
     if (!t) return ZKSC_ERR_STATE;
+    TRY(tail_stop(t));
     t->vars_left = t->n_vars;
     t->cur_n = t->n_local0;
     t->where = 0;
@@ -493,6 +523,8 @@ extern "C" int zksc_tables_reset(zksc_tables* t) {
 extern "C" int zksc_tables_free(zksc_tables* t) {
     if (!t) return ZKSC_OK;
     cudaSetDevice(t->ctx->device);
+    tail_stop(t);
+    quiesce(t->ctx);      // cudaFree synchronises the whole device
     cudaStreamSynchronize(t->ctx->stream);
     cudaFree(t->orig); cudaFree(t->work); cudaFree(t->tail);
     delete t;
@@ -522,6 +554,7 @@ static inline int grid_for(const zksc_ctx* ctx, unsigned long long n, int thread
 static int upload_into(zksc_tables* t, const uint64_t* const* host_tables, bool local) {
     zksc_ctx* ctx = t->ctx;
     CK(cudaSetDevice(ctx->device));
+    TRY(quiesce(ctx));
     t->r0_valid = false;
     const uint64_t N = 1ull << t->n_vars;
     const size_t n_tabs = (size_t)t->B * t->Dtot;
@@ -580,6 +613,7 @@ extern "C" int zksc_tables_read_local(zksc_tables* t, uint64_t* out) {
     if (!t || !out) return ZKSC_ERR_STATE;
     zksc_ctx* ctx = t->ctx;
     CK(cudaSetDevice(ctx->device));
+    TRY(quiesce(ctx));
     const size_t n = (size_t)t->B * t->Dtot * t->n_local0;
     CK(cudaMemcpyAsync(out, t->orig, n * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -618,9 +652,165 @@ static Geo geo_of(const zksc_tables* t, int where) {
     return g;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// persistent tail kernel: host side (tail_kernel.cuh has the protocol)
+// ------------------------------------------------------------------------------------------------
+static int tail_ensure(zksc_ctx* ctx, size_t proofs, size_t units) {
+    if (proofs <= ctx->tail_proofs_cap && units <= ctx->tail_units_cap) return ZKSC_OK;
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFreeHost((void*)ctx->tail_mail); cudaFreeHost((void*)ctx->tail_res);
+    ctx->tail_mail = nullptr; ctx->tail_res = nullptr; ctx->tail_proofs_cap = 0; ctx->tail_units_cap = 0;
+    void *m = nullptr, *r = nullptr, *d = nullptr;
+    CK(cudaHostAlloc(&m, proofs * kMailUnits * 8, cudaHostAllocMapped));
+    CK(cudaHostAlloc(&r, units * 8, cudaHostAllocMapped));
+    memset(m, 0, proofs * kMailUnits * 8);
+    memset(r, 0, units * 8);
+    ctx->tail_mail = (volatile uint64_t*)m; ctx->tail_res = (volatile uint64_t*)r;
+    CK(cudaHostGetDevicePointer(&d, m, 0)); ctx->tail_mail_dev = (uint2*)d;
+    CK(cudaHostGetDevicePointer(&d, r, 0)); ctx->tail_res_dev = (uint2*)d;
+    ctx->tail_proofs_cap = proofs; ctx->tail_units_cap = units;
+    return ZKSC_OK;
+}
+
+// post the pending challenges' fold tables as round `seq` of every proof
+static void tail_post(zksc_tables* t, unsigned int seq) {
+    zksc_ctx* ctx = t->ctx;
+    for (uint32_t b = 0; b < t->B; b++) {
+        const uint32_t* w = &t->pending_tab[b].w[0][0];
+        volatile uint64_t* m = ctx->tail_mail + (size_t)b * kMailUnits;
+        for (int u = 0; u < kMailUnits; u++) m[u] = (uint64_t)w[u] | ((uint64_t)seq << 32);
+    }
+    t->tail_cur = seq;
+    t->tail_posted = true;
+}
+
+constexpr int kTailExpired = 1;   // internal status of tail_wait (never crosses the C ABI)
+// the kernel left on its own (mailbox timeout): forget it; the pending challenge is still unapplied
+static int tail_expired(zksc_tables* t) {
+    zksc_ctx* ctx = t->ctx;
+    t->tail_running = false; t->tail_posted = false; t->tail_left = 0;
+    if (ctx->active_tail == t) ctx->active_tail = nullptr;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return ZKSC_OK;
+}
+// wait for round `seq` of every (proof, product); copy the evaluations (all points but 1) to out when given
+static int tail_wait(zksc_tables* t, unsigned int seq, uint64_t* out) {
+    zksc_ctx* ctx = t->ctx;
+    unsigned long long spins = 0;
+    for (uint32_t b = 0; b < t->B; b++)
+        for (uint32_t p = 0; p < t->P; p++)
+            for (uint32_t pt = 0; pt <= t->deg[p]; pt++) {
+                if (pt == 1) continue;
+                const size_t e = (size_t)b * t->E + t->eoff[p] + pt;
+                uint32_t limbs[8];
+                for (int l = 0; l < 8; l++) {
+                    volatile uint64_t* u = ctx->tail_res + e * 8 + l;
+                    for (;;) {
+                        const uint64_t v = *u;
+                        const uint32_t tag = (uint32_t)(v >> 32);
+                        if (tag == seq) { limbs[l] = (uint32_t)v; break; }
+                        if (tag == kTailTimeout) return kTailExpired;   // the kernel gave up waiting and left; nothing was folded
+#if defined(__x86_64__)
+                        __builtin_ia32_pause();
+#endif
+                        if ((++spins & 0xfffff) == 0) {
+                            cudaError_t q = cudaStreamQuery(ctx->stream);
+                            if (q != cudaErrorNotReady && q != cudaSuccess) { ctx->err = std::string("tail kernel: ") + cudaGetErrorString(q); return ZKSC_ERR_CUDA; }
+                            if (q == cudaSuccess && (uint32_t)(*u >> 32) != seq) FAIL(ZKSC_ERR_CUDA, "tail kernel ended without publishing its results");
+                        }
+                    }
+                }
+                if (out) memcpy(out + e * 4, limbs, 32);
+            }
+    return ZKSC_OK;
+}
+
+// bookkeeping after a tail round's result has been collected: its fold has been applied
+static void tail_round_done(zksc_tables* t) {
+    zksc_ctx* ctx = t->ctx;
+    if (t->where == 0) t->where = 1;
+    t->cur_n /= 2;
+    t->pending = false;
+    t->tail_posted = false;
+    if (--t->tail_left == 0) {
+        t->tail_running = false;          // the kernel leaves by itself after its last round
+        if (ctx->active_tail == t) ctx->active_tail = nullptr;
+    }
+}
+
+// Stop a resident tail kernel (anything else that wants the stream, the tables or a device-wide call must do
+// this first).  A posted round is completed and accounted for; its evaluations are dropped.
+static int tail_stop(zksc_tables* t) {
+    if (!t || !t->tail_running) return ZKSC_OK;
+    zksc_ctx* ctx = t->ctx;
+    CK(cudaSetDevice(ctx->device));
+    if (t->tail_posted) {
+        const int rc = tail_wait(t, t->tail_cur, nullptr);
+        if (rc == kTailExpired) return tail_expired(t);
+        if (rc != ZKSC_OK) return rc;
+        tail_round_done(t);
+        t->claim_valid = false;
+        t->last_evals_valid = false;
+    }
+    if (t->tail_running) {
+        for (uint32_t b = 0; b < t->B; b++) ctx->tail_mail[(size_t)b * kMailUnits] = (uint64_t)kTailAbort << 32;
+        t->tail_running = false;
+        t->tail_left = 0;
+    }
+    if (ctx->active_tail == t) ctx->active_tail = nullptr;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return ZKSC_OK;
+}
+static int quiesce(zksc_ctx* ctx) { return ctx && ctx->active_tail ? tail_stop(ctx->active_tail) : ZKSC_OK; }
+
+static bool tail_eligible(const zksc_tables* t, unsigned long long half) {
+    const zksc_ctx* ctx = t->ctx;
+    if (!ctx->tail_enabled || half > kTailPairs || (size_t)t->B * t->P > (size_t)ctx->sms) return false;
+    for (uint32_t p = 0; p < t->P; p++)
+        if (t->deg[p] > (uint32_t)kTailMaxDegree) return false;
+    return true;
+}
+
+// Launch the tail kernel for all remaining rounds; the pending challenge is its first mailbox message.
+static int tail_start(zksc_tables* t, unsigned long long half) {
+    zksc_ctx* ctx = t->ctx;
+    TRY(quiesce(ctx));
+    TRY(tail_ensure(ctx, t->B, (size_t)t->B * t->E * 8));
+    unsigned int n_rounds = 0;
+    for (unsigned long long h = half; h >= 1; h >>= 1) n_rounds++;
+    if (ctx->tail_seq > 0xf0000000u) {                    // stay clear of the reserved sequence numbers
+        ctx->tail_seq = 0;
+        memset((void*)ctx->tail_mail, 0, ctx->tail_proofs_cap * kMailUnits * 8);
+        memset((void*)ctx->tail_res, 0, ctx->tail_units_cap * 8);
+    }
+    const unsigned int seq0 = ctx->tail_seq + 1;
+    ctx->tail_seq += n_rounds;
+    Geo gi = geo_of(t, t->where);
+    Geo go = geo_of(t, t->where == 0 ? 1 : t->where);
+    TailArgs a;
+    memset(&a, 0, sizeof(a));
+    a.in = gi.base; a.out = go.base;
+    a.in_tab_stride = gi.tab_stride; a.in_proof_stride = gi.proof_stride;
+    a.out_tab_stride = go.tab_stride; a.out_proof_stride = go.proof_stride;
+    a.half = half; a.n_rounds = n_rounds; a.seq0 = seq0;
+    a.n_products = t->P; a.n_evals = t->E;
+    for (uint32_t p = 0; p < t->P; p++) { a.deg[p] = t->deg[p]; a.koff[p] = t->koff[p]; a.eoff[p] = t->eoff[p]; }
+    a.mail = ctx->tail_mail_dev; a.results = ctx->tail_res_dev;
+    tail_post(t, seq0);
+    zksc_launch_tail(dim3(t->B, t->P), ctx->stream, a);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    t->tail_running = true;
+    t->tail_left = n_rounds;
+    ctx->active_tail = t;
+    return ZKSC_OK;
+}
+
 // Apply the pending challenge with the stand-alone fold kernel (no evaluation).
 static int flush_pending(zksc_tables* t) {
     zksc_ctx* ctx = t->ctx;
+    TRY(quiesce(ctx));
     if (!t->pending) return ZKSC_OK;
     if (t->cur_n < 2) FAIL(ZKSC_ERR_STATE, "no variable left to bind");
     Geo gi = geo_of(t, t->where);
@@ -737,6 +927,23 @@ static int launch_round(const zksc_tables* t, const RoundBase& base, int D, int 
     return ZKSC_OK;
 }
 
+// after the device part of a round: fill in point 1 from the claim, remember the evaluations for the next claim
+static void finish_round(zksc_tables* t, uint64_t* out, bool skip1, bool full) {
+    if (skip1) {
+        // h_p(1) = claim_p - h_p(0)   (what the verifier checks; exact in the field)
+        for (uint32_t b = 0; b < t->B; b++)
+            for (uint32_t p = 0; p < t->P; p++) {
+                uint64_t* e = out + ((size_t)b * t->E + t->eoff[p]) * 4;
+                store_h(e + 4, host::sub(t->claim[(size_t)b * t->P + p], load_h(e)));
+            }
+    }
+    t->claim_valid = false;
+    if (full) {
+        t->last_evals.assign(out, out + (size_t)t->B * t->E * 4);
+        t->last_evals_valid = true;
+    }
+}
+
 // One round: evaluations of every product of every proof at 0..npts_cap-1 (capped by degree+1).
 static int round_evals_impl(zksc_tables* t, uint64_t* out, uint32_t npts_cap) {
     zksc_ctx* ctx = t->ctx;
@@ -750,8 +957,10 @@ static int round_evals_impl(zksc_tables* t, uint64_t* out, uint32_t npts_cap) {
         return ZKSC_OK;
     }
     const auto prof_t0 = std::chrono::steady_clock::now();
+    if (ctx->active_tail && ctx->active_tail != t) TRY(quiesce(ctx));
+    if (t->tail_running && (!t->tail_posted || npts_cap <= ZKSC_MAX_DEGREE)) TRY(tail_stop(t));   // not the prover's call pattern
     const bool sharded_phase = (ctx->n_ranks > 1 && t->where != 2);
-    if (sharded_phase) {
+    if (sharded_phase && !t->tail_running) {
         uint64_t n_after = t->pending ? t->cur_n / 2 : t->cur_n;
         if (n_after == 1) TRY(gather_tail(t));
     }
@@ -767,6 +976,21 @@ static int round_evals_impl(zksc_tables* t, uint64_t* out, uint32_t npts_cap) {
     Geo go = geo_of(t, to);
     const unsigned long long half = n_eval / 2;
     const size_t n_res = (size_t)t->B * t->E;
+    if (t->tail_running || (skip1 && !reduce_ranks && tail_eligible(t, half))) {
+        // small tables: the resident tail kernel runs this round (and all later ones)
+        if (!t->tail_running) TRY(tail_start(t, half));
+        const auto w0 = std::chrono::steady_clock::now();
+        ctx->prof_launch = std::chrono::duration<double, std::micro>(w0 - prof_t0).count();
+        const int rc = tail_wait(t, t->tail_cur, out);
+        if (rc == ZKSC_OK) {
+            ctx->prof_wait = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - w0).count();
+            tail_round_done(t);
+            finish_round(t, out, true, true);
+            return ZKSC_OK;
+        }
+        if (rc != kTailExpired) return rc;
+        TRY(tail_expired(t));     // the host took too long between rounds: this round goes through an ordinary launch
+    }
     const bool peer = reduce_ranks && ctx->p2p && n_res <= kXchCap;   // exchange + sum inside the round kernel
     const bool mapped = (ctx->mapped_results && !reduce_ranks) || peer;
     Fr* res = reduce_ranks ? ctx->results_send : (mapped ? ctx->results_host_dev : ctx->results_dev);
@@ -839,19 +1063,7 @@ static int round_evals_impl(zksc_tables* t, uint64_t* out, uint32_t npts_cap) {
         }
 #endif
     }
-    if (skip1) {
-        // h_p(1) = claim_p - h_p(0)   (what the verifier checks; exact in the field)
-        for (uint32_t b = 0; b < t->B; b++)
-            for (uint32_t p = 0; p < t->P; p++) {
-                uint64_t* e = out + ((size_t)b * t->E + t->eoff[p]) * 4;
-                store_h(e + 4, host::sub(t->claim[(size_t)b * t->P + p], load_h(e)));
-            }
-    }
-    t->claim_valid = false;
-    if (full) {
-        t->last_evals.assign(out, out + n_res * 4);
-        t->last_evals_valid = true;
-    }
+    finish_round(t, out, skip1, full);
     return ZKSC_OK;
 }
 
@@ -865,6 +1077,8 @@ extern "C" int zksc_bind(zksc_tables* t, const uint64_t* challenges) {
     zksc_ctx* ctx = t->ctx;
     CK(cudaSetDevice(ctx->device));
     if (t->vars_left == 0) FAIL(ZKSC_ERR_STATE, "all variables are bound");
+    if (ctx->active_tail && ctx->active_tail != t) TRY(quiesce(ctx));
+    if (t->tail_running && (t->tail_posted || !t->last_evals_valid)) TRY(tail_stop(t));   // bind without the round's evaluations
     if (t->pending) {
         if (ctx->n_ranks > 1 && t->where != 2 && t->cur_n / 2 == 1) TRY(gather_tail(t));
         else TRY(flush_pending(t));
@@ -892,6 +1106,7 @@ extern "C" int zksc_bind(zksc_tables* t, const uint64_t* challenges) {
         t->claim_valid = true;
     }
     t->last_evals_valid = false;
+    if (t->tail_running) tail_post(t, t->tail_cur + 1);     // the resident kernel folds with it and evaluates the next round
     return ZKSC_OK;
 }
 
@@ -899,6 +1114,7 @@ extern "C" int zksc_residual(zksc_tables* t, uint64_t* out) {
     if (!t || !out) return ZKSC_ERR_STATE;
     zksc_ctx* ctx = t->ctx;
     CK(cudaSetDevice(ctx->device));
+    TRY(quiesce(ctx));
     if (ctx->n_ranks > 1 && t->where != 2) {
         uint64_t n_after = t->pending ? t->cur_n / 2 : t->cur_n;
         if (n_after != 1) FAIL(ZKSC_ERR_UNSUPPORTED, "sharded residual is only available once each rank holds one entry per table");
@@ -953,6 +1169,7 @@ extern "C" int zksc_tables_to_bytes(zksc_tables* t, uint32_t proof, uint8_t* out
     if (!t || !out) return ZKSC_ERR_STATE;
     zksc_ctx* ctx = t->ctx;
     CK(cudaSetDevice(ctx->device));
+    TRY(quiesce(ctx));
     if (ctx->n_ranks != 1) FAIL(ZKSC_ERR_UNSUPPORTED, "zksc_tables_to_bytes: single-rank contexts only");
     if (proof >= t->B) FAIL(ZKSC_ERR_SHAPE, "proof index");
     const uint64_t N = t->n_local0;
@@ -1159,6 +1376,7 @@ extern "C" int zksc_ml_partial_evaluation(zksc_ctx* ctx, const uint64_t* evals, 
     if (n < 2 || (n & (n - 1))) FAIL(ZKSC_ERR_SHAPE, "Number of evaluations must be a power of 2 (and at least 2 to bind a variable)");
     if (n % 2 != 0 || variable_index >= n / 2 || (n >> (variable_index + 1)) == 0) FAIL(ZKSC_ERR_SHAPE, "variable_index must be less than n/2 and name an existing variable");
     CK(cudaSetDevice(ctx->device));
+    TRY(quiesce(ctx));
     DevBuf in, o;
     CK(cudaMalloc(&in.p, n * sizeof(Fr)));
     CK(cudaMalloc(&o.p, n / 2 * sizeof(Fr)));
@@ -1182,6 +1400,7 @@ extern "C" int zksc_ml_evaluation(zksc_ctx* ctx, const uint64_t* evals, uint64_t
     if (n < 1 || (n & (n - 1))) FAIL(ZKSC_ERR_SHAPE, "Number of evaluations must be a power of 2");
     if ((1ull << n_points) != n) FAIL(ZKSC_ERR_SHAPE, "Number of evaluation points must match the number of variables");
     CK(cudaSetDevice(ctx->device));
+    TRY(quiesce(ctx));
     DevBuf buf;
     CK(cudaMalloc(&buf.p, n * sizeof(Fr)));
     CK(cudaMemcpyAsync(buf.p, evals, n * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
@@ -1208,6 +1427,7 @@ extern "C" int zksc_ml_outer(zksc_ctx* ctx, int mul, const uint64_t* a, uint64_t
     uint64_t n = na * nb;
     if (n & (n - 1)) FAIL(ZKSC_ERR_SHAPE, "Number of evaluations must be a power of 2");
     CK(cudaSetDevice(ctx->device));
+    TRY(quiesce(ctx));
     DevBuf da, db, dout;
     CK(cudaMalloc(&da.p, na * sizeof(Fr)));
     CK(cudaMalloc(&db.p, nb * sizeof(Fr)));
@@ -1227,6 +1447,7 @@ extern "C" int zksc_ml_elementwise(zksc_ctx* ctx, int op, const uint64_t* a, con
     if (!a || !b || !out || !n) FAIL(ZKSC_ERR_SHAPE, "empty operand");
     if (op < 0 || op > 3) FAIL(ZKSC_ERR_SHAPE, "op");
     CK(cudaSetDevice(ctx->device));
+    TRY(quiesce(ctx));
     DevBuf da, db, dout;
     const uint64_t nb = (op == EW_SCALE) ? 1 : n;
     CK(cudaMalloc(&da.p, n * sizeof(Fr)));
