@@ -40,6 +40,9 @@ static thread_local std::string g_create_error;
 
 constexpr size_t kXchTagBytes = 256;               // 2 * kMaxRanks tags, padded
 constexpr unsigned int kXchCap = 2048;             // elements per (slot, rank): rounds with more partials use NCCL
+// exchange buffer of a rank: tags[2][G] | data[2][G][kXchCap] elements (round kernels) | units[2][G][kXchCap][8] (resident kernel)
+static inline size_t kXchUnitsOffset(int G) { return kXchTagBytes + (size_t)2 * G * kXchCap * 32; }
+static inline size_t kXchUnitsBytes(int G) { return (size_t)2 * G * kXchCap * 64; }
 
 // ------------------------------------------------------------------------------------------------
 // NCCL, loaded at run time (single-GPU use must not depend on libnccl being present)
@@ -98,9 +101,11 @@ struct zksc_ctx {
     bool tail_enabled = true;            // ZKSC_NO_TAIL=1: every round is its own launch
     volatile uint64_t* tail_mail = nullptr;    // [tail_proofs_cap][kMailUnits]   {word | seq << 32}
     volatile uint64_t* tail_res = nullptr;     // [tail_units_cap]                {limb | seq << 32}
-    uint2* tail_mail_dev = nullptr;
-    uint2* tail_res_dev = nullptr;
-    size_t tail_proofs_cap = 0, tail_units_cap = 0;
+    unsigned long long* tail_mail_dev = nullptr;
+    unsigned long long* tail_res_dev = nullptr;
+    unsigned long long* tail_relay = nullptr;  // HBM [tail_groups_cap][kMailUnits]
+    unsigned long long* tail_sums = nullptr;   // HBM [tail_sums_cap] units
+    size_t tail_proofs_cap = 0, tail_units_cap = 0, tail_groups_cap = 0, tail_sums_cap = 0;
     unsigned int tail_seq = 0;           // last sequence number handed out
     struct zksc_tables* active_tail = nullptr;   // the handle whose tail kernel is resident on `stream` (at most one)
     // ZKSC_PROFILE=1: host-side wall-clock split of every round of zksc_prove, printed to stderr (ns)
@@ -265,6 +270,8 @@ extern "C" int zksc_ctx_destroy(zksc_ctx* ctx) {
     cudaFreeHost((void*)ctx->flag_host);
     cudaFreeHost((void*)ctx->tail_mail);
     cudaFreeHost((void*)ctx->tail_res);
+    cudaFree(ctx->tail_relay);
+    cudaFree(ctx->tail_sums);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return ZKSC_OK;
@@ -368,7 +375,7 @@ static int setup_peer_exchange(zksc_ctx* ctx) {
     const int G = ctx->n_ranks;
     { const char* e_ = getenv("ZKSC_NO_P2P"); if (e_ && e_[0] == '1') return ZKSC_OK; }
     if (G > kMaxRanks) return ZKSC_OK;
-    const size_t bytes = kXchTagBytes + (size_t)2 * G * kXchCap * sizeof(Fr);
+    const size_t bytes = kXchUnitsOffset(G) + kXchUnitsBytes(G);
     struct Msg { cudaIpcMemHandle_t h; unsigned int ok; unsigned int pad[15]; };
     static_assert(sizeof(Msg) == 128, "exchange handle message");
     Msg mine;
@@ -656,20 +663,25 @@ static Geo geo_of(const zksc_tables* t, int where) {
 // ------------------------------------------------------------------------------------------------
 // persistent tail kernel: host side (tail_kernel.cuh has the protocol)
 // ------------------------------------------------------------------------------------------------
-static int tail_ensure(zksc_ctx* ctx, size_t proofs, size_t units) {
-    if (proofs <= ctx->tail_proofs_cap && units <= ctx->tail_units_cap) return ZKSC_OK;
+static int tail_ensure(zksc_ctx* ctx, size_t proofs, size_t units, size_t groups, size_t sums) {
+    if (proofs <= ctx->tail_proofs_cap && units <= ctx->tail_units_cap && groups <= ctx->tail_groups_cap && sums <= ctx->tail_sums_cap) return ZKSC_OK;
     CK(cudaStreamSynchronize(ctx->stream));
-    cudaFreeHost((void*)ctx->tail_mail); cudaFreeHost((void*)ctx->tail_res);
-    ctx->tail_mail = nullptr; ctx->tail_res = nullptr; ctx->tail_proofs_cap = 0; ctx->tail_units_cap = 0;
+    cudaFreeHost((void*)ctx->tail_mail); cudaFreeHost((void*)ctx->tail_res); cudaFree(ctx->tail_relay); cudaFree(ctx->tail_sums);
+    ctx->tail_mail = nullptr; ctx->tail_res = nullptr; ctx->tail_relay = nullptr; ctx->tail_sums = nullptr;
+    ctx->tail_proofs_cap = ctx->tail_units_cap = ctx->tail_groups_cap = ctx->tail_sums_cap = 0;
     void *m = nullptr, *r = nullptr, *d = nullptr;
     CK(cudaHostAlloc(&m, proofs * kMailUnits * 8, cudaHostAllocMapped));
     CK(cudaHostAlloc(&r, units * 8, cudaHostAllocMapped));
     memset(m, 0, proofs * kMailUnits * 8);
     memset(r, 0, units * 8);
     ctx->tail_mail = (volatile uint64_t*)m; ctx->tail_res = (volatile uint64_t*)r;
-    CK(cudaHostGetDevicePointer(&d, m, 0)); ctx->tail_mail_dev = (uint2*)d;
-    CK(cudaHostGetDevicePointer(&d, r, 0)); ctx->tail_res_dev = (uint2*)d;
-    ctx->tail_proofs_cap = proofs; ctx->tail_units_cap = units;
+    CK(cudaHostGetDevicePointer(&d, m, 0)); ctx->tail_mail_dev = (unsigned long long*)d;
+    CK(cudaHostGetDevicePointer(&d, r, 0)); ctx->tail_res_dev = (unsigned long long*)d;
+    CK(cudaMalloc(&ctx->tail_relay, groups * kMailUnits * 8));
+    CK(cudaMalloc(&ctx->tail_sums, sums * 8));
+    CK(cudaMemsetAsync(ctx->tail_relay, 0, groups * kMailUnits * 8, ctx->stream));
+    CK(cudaMemsetAsync(ctx->tail_sums, 0, sums * 8, ctx->stream));
+    ctx->tail_proofs_cap = proofs; ctx->tail_units_cap = units; ctx->tail_groups_cap = groups; ctx->tail_sums_cap = sums;
     return ZKSC_OK;
 }
 
@@ -711,6 +723,7 @@ static int tail_wait(zksc_tables* t, unsigned int seq, uint64_t* out) {
                         const uint32_t tag = (uint32_t)(v >> 32);
                         if (tag == seq) { limbs[l] = (uint32_t)v; break; }
                         if (tag == kTailTimeout) return kTailExpired;   // the kernel gave up waiting and left; nothing was folded
+                        if (tag == kTailFailed) FAIL(ZKSC_ERR_COMM, "resident rounds kernel: a CTA or a peer GPU went missing mid-round; the tables are undefined (reset them)");
 #if defined(__x86_64__)
                         __builtin_ia32_pause();
 #endif
@@ -764,25 +777,48 @@ static int tail_stop(zksc_tables* t) {
 }
 static int quiesce(zksc_ctx* ctx) { return ctx && ctx->active_tail ? tail_stop(ctx->active_tail) : ZKSC_OK; }
 
-static bool tail_eligible(const zksc_tables* t, unsigned long long half) {
+// CTAs per (proof, product) group the resident kernel may use: every CTA must be co-resident (1 per SM)
+static unsigned int tail_group_ctas(const zksc_tables* t) {
+    const size_t groups = (size_t)t->B * t->P;
+    size_t c = groups ? (size_t)t->ctx->sms / groups : 0;
+    if (c > (size_t)kTailMaxCtas) c = kTailMaxCtas;
+    return (unsigned int)c;
+}
+static bool tail_eligible(const zksc_tables* t, unsigned long long half, bool sharded) {
     const zksc_ctx* ctx = t->ctx;
-    if (!ctx->tail_enabled || half > kTailPairs || (size_t)t->B * t->P > (size_t)ctx->sms) return false;
-    for (uint32_t p = 0; p < t->P; p++)
-        if (t->deg[p] > (uint32_t)kTailMaxDegree) return false;
+    const unsigned int c = tail_group_ctas(t);
+    if (!ctx->tail_enabled || c == 0) return false;
+    if (sharded && (!ctx->p2p || (size_t)t->B * t->E > kXchCap)) return false;
+    for (uint32_t p = 0; p < t->P; p++) {
+        const unsigned long long d = t->deg[p];
+        if (d > (unsigned long long)kTailMaxDegree) return false;
+        // 32x32 limb products per pair of a fused fold + evaluate round: the resident kernel keeps one
+        // CTA of 8 warps per SM, so it only wins while a round is latency-bound
+        const unsigned long long per_point = d == 1 ? 0 : (d <= 3 ? (d - 2) * 120 + 64 : (d - 1) * 120);
+        if (half * (2 * d * 76 + d * per_point) > kTailWorkPerCta * c) return false;
+    }
     return true;
 }
 
-// Launch the tail kernel for all remaining rounds; the pending challenge is its first mailbox message.
-static int tail_start(zksc_tables* t, unsigned long long half) {
+// Launch the resident kernel for all remaining rounds of this phase; the pending challenge is its first mailbox message.
+static int tail_start(zksc_tables* t, unsigned long long half, bool sharded) {
     zksc_ctx* ctx = t->ctx;
     TRY(quiesce(ctx));
-    TRY(tail_ensure(ctx, t->B, (size_t)t->B * t->E * 8));
+    unsigned int n_ctas = tail_group_ctas(t);
+    const unsigned long long want = (half + kTailThreads - 1) / kTailThreads;
+    if (want < n_ctas) n_ctas = (unsigned int)want;
+    const size_t groups = (size_t)t->B * t->P;
+    TRY(tail_ensure(ctx, t->B, (size_t)t->B * t->E * 8, groups, groups * n_ctas * kTailMaxDegree * 8));
     unsigned int n_rounds = 0;
     for (unsigned long long h = half; h >= 1; h >>= 1) n_rounds++;
     if (ctx->tail_seq > 0xf0000000u) {                    // stay clear of the reserved sequence numbers
+        CK(cudaStreamSynchronize(ctx->stream));
         ctx->tail_seq = 0;
         memset((void*)ctx->tail_mail, 0, ctx->tail_proofs_cap * kMailUnits * 8);
         memset((void*)ctx->tail_res, 0, ctx->tail_units_cap * 8);
+        CK(cudaMemsetAsync(ctx->tail_relay, 0, ctx->tail_groups_cap * kMailUnits * 8, ctx->stream));
+        CK(cudaMemsetAsync(ctx->tail_sums, 0, ctx->tail_sums_cap * 8, ctx->stream));
+        if (ctx->xch_local) CK(cudaMemsetAsync(ctx->xch_local + kXchUnitsOffset(ctx->n_ranks), 0, kXchUnitsBytes(ctx->n_ranks), ctx->stream));
     }
     const unsigned int seq0 = ctx->tail_seq + 1;
     ctx->tail_seq += n_rounds;
@@ -797,8 +833,14 @@ static int tail_start(zksc_tables* t, unsigned long long half) {
     a.n_products = t->P; a.n_evals = t->E;
     for (uint32_t p = 0; p < t->P; p++) { a.deg[p] = t->deg[p]; a.koff[p] = t->koff[p]; a.eoff[p] = t->eoff[p]; }
     a.mail = ctx->tail_mail_dev; a.results = ctx->tail_res_dev;
+    a.relay = ctx->tail_relay; a.sums = ctx->tail_sums;
+    a.n_ranks = 1; a.rank = 0; a.xch_cap = kXchCap;
+    if (sharded) {
+        a.n_ranks = ctx->n_ranks; a.rank = ctx->rank;
+        for (int g = 0; g < ctx->n_ranks; g++) a.peer_units[g] = (unsigned long long*)((unsigned char*)ctx->xch_peer[g] + kXchUnitsOffset(ctx->n_ranks));
+    }
     tail_post(t, seq0);
-    zksc_launch_tail(dim3(t->B, t->P), ctx->stream, a);
+    zksc_launch_tail(dim3(n_ctas, t->B, t->P), ctx->stream, a);
     ctx->launches++;
     CK(cudaGetLastError());
     t->tail_running = true;
@@ -976,9 +1018,9 @@ static int round_evals_impl(zksc_tables* t, uint64_t* out, uint32_t npts_cap) {
     Geo go = geo_of(t, to);
     const unsigned long long half = n_eval / 2;
     const size_t n_res = (size_t)t->B * t->E;
-    if (t->tail_running || (skip1 && !reduce_ranks && tail_eligible(t, half))) {
-        // small tables: the resident tail kernel runs this round (and all later ones)
-        if (!t->tail_running) TRY(tail_start(t, half));
+    if (t->tail_running || (skip1 && tail_eligible(t, half, reduce_ranks))) {
+        // latency-bound rounds: the resident kernel runs this round and all later ones of this phase
+        if (!t->tail_running) TRY(tail_start(t, half, reduce_ranks));
         const auto w0 = std::chrono::steady_clock::now();
         ctx->prof_launch = std::chrono::duration<double, std::micro>(w0 - prof_t0).count();
         const int rc = tail_wait(t, t->tail_cur, out);
