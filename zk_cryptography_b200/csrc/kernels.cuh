@@ -275,8 +275,14 @@ ZKSC_DEV void accumulate_points(Acc<Lazy<D>::NL> (&acc)[NP], Fr (&a)[D], Fr (&b)
 
 // FOLD = false : evaluate the round polynomial of the tables as they are (first round).
 // FOLD = true  : bind the previous challenge (in -> out), then evaluate the next round on the result.
+#ifndef ZKSC_ROUND_MINB
+#define ZKSC_ROUND_MINB 4   // caps the round kernels at 128 registers; measured 1-3 % faster than ptxas' own choice (profiles/r01_variants_v4.txt)
+#endif
+#ifndef ZKSC_FOLD_LOADALL
+#define ZKSC_FOLD_LOADALL 1
+#endif
 template <int D, bool FOLD, bool SKIP1, int NB>
-__global__ void __launch_bounds__(kThreads) round_kernel(const __grid_constant__ RoundArgsT<NB> args) {
+__global__ void __launch_bounds__(kThreads, ZKSC_ROUND_MINB) round_kernel(const __grid_constant__ RoundArgsT<NB> args) {
     constexpr int NL = Lazy<D>::NL;
     constexpr int NP = SKIP1 ? D : D + 1;   // accumulators
     const int proof = (NB == 1) ? 0 : blockIdx.y;
@@ -295,6 +301,21 @@ __global__ void __launch_bounds__(kThreads) round_kernel(const __grid_constant__
     const unsigned long long stride = (unsigned long long)gridDim.x * kThreads;
     for (unsigned long long x = (unsigned long long)blockIdx.x * kThreads + threadIdx.x; x < half; x += stride) {
         Fr a[D], b[D];
+        if constexpr (FOLD && D == 2 && ZKSC_FOLD_LOADALL) {
+            // all eight entries of the pair in flight at once: one exposed memory latency per iteration instead of two
+            const Fr* t0 = in;
+            const Fr* t1 = in + args.in_tab_stride;
+            Fr p0 = ld256(t0 + x), p1 = ld256(t0 + x + 2 * half), q0 = ld256(t0 + x + half), q1 = ld256(t0 + x + 3 * half);
+            Fr r0 = ld256(t1 + x), r1 = ld256(t1 + x + 2 * half), s0 = ld256(t1 + x + half), s1 = ld256(t1 + x + 3 * half);
+            a[0] = fr_fold_tab(p0, p1, args.tab[proof]);
+            b[0] = fr_fold_tab(q0, q1, args.tab[proof]);
+            st256(out + x, a[0]);
+            st256(out + x + half, b[0]);
+            a[1] = fr_fold_tab(r0, r1, args.tab[proof]);
+            b[1] = fr_fold_tab(s0, s1, args.tab[proof]);
+            st256(out + args.out_tab_stride + x, a[1]);
+            st256(out + args.out_tab_stride + x + half, b[1]);
+        } else
 #pragma unroll
         for (int k = 0; k < D; k++) {
             const Fr* t = in + (size_t)k * args.in_tab_stride;

@@ -45,6 +45,7 @@ void ZKSC_CAT(zksc_prepare_round_, ZKSC_D)() {
 // resident CTAs per SM; variants 3..5 = the staged kernels of variants 0..2 (0 when there is none)
 int ZKSC_CAT(zksc_occ_round_, ZKSC_D)(int variant) {
     int o = 0;
+    if (variant >= 6) return 0;
     if (variant == 2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, round_kernel<ZKSC_D, true, true, 1>, kThreads, 0);
     else if (variant == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, round_kernel<ZKSC_D, true, false, 1>, kThreads, 0);
     else if (variant == 0) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, round_kernel<ZKSC_D, false, false, 1>, kThreads, 0);

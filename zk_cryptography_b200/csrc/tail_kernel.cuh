@@ -40,7 +40,7 @@ constexpr int kMailUnits = 64;                      // FoldTab words per proof a
 constexpr unsigned int kTailAbort = 0xffffffffu;    // sequence number that tells the kernel to leave
 constexpr unsigned int kTailTimeout = 0xfffffffeu;  // published when no challenge arrived in time (nothing folded: recoverable)
 constexpr unsigned int kTailFailed = 0xfffffffdu;   // published when a CTA or a peer GPU went missing in the middle of a round
-constexpr unsigned long long kTailTimeoutNs = 10ull * 1000 * 1000 * 1000;
+constexpr unsigned long long kTailTimeoutNs = 2ull * 1000 * 1000 * 1000;    // CTA 0 waiting for the host; everything else waits a multiple
 
 struct TailArgs {
     const Fr* in;              // tables before the first fold of the tail (table 0 of proof 0)
@@ -116,7 +116,7 @@ ZKSC_DEV bool tail_read_elem(const unsigned long long* u, unsigned int seq, Fr& 
             for (int l = 0; l < 8; l++) out.l[l] = (unsigned int)v[l];
             return true;
         }
-        if ((spins & 0x3ff) == 0 && global_timer_ns() - t0 > 2 * kTailTimeoutNs) return false;
+        if ((spins & 0x3ff) == 0 && global_timer_ns() - t0 > 10 * kTailTimeoutNs) return false;
     }
 }
 

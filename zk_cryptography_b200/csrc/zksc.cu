@@ -698,9 +698,13 @@ static void tail_post(zksc_tables* t, unsigned int seq) {
 }
 
 constexpr int kTailExpired = 1;   // internal status of tail_wait (never crosses the C ABI)
-// the kernel left on its own (mailbox timeout): forget it; the pending challenge is still unapplied
+// The kernel left on its own (mailbox timeout): forget it; the pending challenge is still unapplied.  This happens
+// when kernel launches are synchronous (under Nsight Compute every launch blocks until the kernel has ended, so the
+// host can never answer a resident kernel) or when the host thread was stopped for seconds: the context goes back
+// to one launch per round for good.
 static int tail_expired(zksc_tables* t) {
     zksc_ctx* ctx = t->ctx;
+    ctx->tail_enabled = false;
     t->tail_running = false; t->tail_posted = false; t->tail_left = 0;
     if (ctx->active_tail == t) ctx->active_tail = nullptr;
     CK(cudaStreamSynchronize(ctx->stream));
