@@ -99,6 +99,20 @@ int zksc_tables_read_local(zksc_tables* t, uint64_t* out);
  * DESIGN.md "Synthetic inputs"); each rank generates only its shard. */
 int zksc_tables_synth(zksc_ctx* ctx, uint32_t n_vars, uint32_t n_proofs, uint32_t n_products, const uint32_t* degree, uint64_t seed,
                       zksc_tables** out);
+/* Tables built on the device (GKR layer polynomials, gkr/src/protocol.rs:67-93 and gkr/src/utils.rs:23-33):
+ * zksc_tables_alloc gives uninitialised tables of a shape; every table must then be filled by one of
+ *   zksc_tables_fill_outer  : table = a (+) b or a (x) b, the outer sum / product of two host vectors --
+ *                             Multilinear::add_distinct / mul_distinct (evaluation_form.rs:28-52); na * nb == 2^n_vars
+ *   zksc_tables_fill_sparse : table = 0 except table[idx[i]] = vals[i] (indices distinct) -- a wiring table
+ *                             (Circuit::add_mult_mle, circuit/src/circuit.rs:57-95) after partial_evaluations over
+ *                             its gate-label variables, scaled and summed (protocol.rs:70-74, 86-88)
+ *   zksc_tables_fill_dense  : table = the given 2^n_vars host elements
+ * `table` counts proof-major, then product, then factor.  On a sharded context every rank passes the same
+ * (global) arguments and keeps its own entries. */
+int zksc_tables_alloc(zksc_ctx* ctx, uint32_t n_vars, uint32_t n_proofs, uint32_t n_products, const uint32_t* degree, zksc_tables** out);
+int zksc_tables_fill_outer(zksc_tables* t, uint32_t table, int mul, const uint64_t* a, uint64_t na, const uint64_t* b, uint64_t nb);
+int zksc_tables_fill_sparse(zksc_tables* t, uint32_t table, const uint64_t* idx, const uint64_t* vals, uint64_t count);
+int zksc_tables_fill_dense(zksc_tables* t, uint32_t table, const uint64_t* evals);
 int zksc_tables_free(zksc_tables* t);
 /* Forget all bound challenges: back to the tables as uploaded (the input is never modified). */
 int zksc_tables_reset(zksc_tables* t);

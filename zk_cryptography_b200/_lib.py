@@ -59,6 +59,10 @@ def lib():
         "zksc_tables_read_local": (ctypes.c_int, [vp, _u64p]),
         "zksc_tables_upload": (ctypes.c_int, [vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, _u32p, ctypes.POINTER(_u64p), ctypes.POINTER(vp)]),
         "zksc_tables_synth": (ctypes.c_int, [vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, _u32p, ctypes.c_uint64, ctypes.POINTER(vp)]),
+        "zksc_tables_alloc": (ctypes.c_int, [vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, _u32p, ctypes.POINTER(vp)]),
+        "zksc_tables_fill_outer": (ctypes.c_int, [vp, ctypes.c_uint32, ctypes.c_int, _u64p, ctypes.c_uint64, _u64p, ctypes.c_uint64]),
+        "zksc_tables_fill_sparse": (ctypes.c_int, [vp, ctypes.c_uint32, _u64p, _u64p, ctypes.c_uint64]),
+        "zksc_tables_fill_dense": (ctypes.c_int, [vp, ctypes.c_uint32, _u64p]),
         "zksc_tables_free": (ctypes.c_int, [vp]),
         "zksc_tables_reset": (ctypes.c_int, [vp]),
         "zksc_tables_vars_left": (ctypes.c_int, [vp, _u32p]),
@@ -277,6 +281,34 @@ class Tables:
         h = ctypes.c_void_p()
         ctx.check(lib().zksc_tables_synth(ctx._h, n_vars, n_proofs, len(deg), p32(deg), seed, ctypes.byref(h)))
         return Tables(ctx, n_vars, degrees, h, n_proofs)
+
+    @staticmethod
+    def alloc(ctx, n_vars, degrees, n_proofs=1):
+        """Uninitialised device tables, to be filled in place by fill_outer / fill_sparse / fill_dense."""
+        deg = np.asarray(degrees, dtype=np.uint32)
+        h = ctypes.c_void_p()
+        ctx.check(lib().zksc_tables_alloc(ctx._h, n_vars, n_proofs, len(deg), p32(deg), ctypes.byref(h)))
+        return Tables(ctx, n_vars, degrees, h, n_proofs)
+
+    def fill_outer(self, table, mul, a, b):
+        """table = a (+) b (mul False: add_distinct) or a (x) b (mul True: mul_distinct), computed on the device"""
+        a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4)
+        b = np.ascontiguousarray(b, dtype=np.uint64).reshape(-1, 4)
+        self.ctx.check(lib().zksc_tables_fill_outer(self._h, table, 1 if mul else 0, p64(a), a.shape[0], p64(b), b.shape[0]))
+
+    def fill_sparse(self, table, idx, vals):
+        """table = 0 except table[idx[i]] = vals[i] (Montgomery elements)"""
+        idx = np.ascontiguousarray(idx, dtype=np.uint64).reshape(-1)
+        vals = np.ascontiguousarray(vals, dtype=np.uint64).reshape(-1, 4)
+        if idx.shape[0] != vals.shape[0]:
+            raise ZkscError(-3, "one value per index")
+        self.ctx.check(lib().zksc_tables_fill_sparse(self._h, table, p64(idx), p64(vals), idx.shape[0]))
+
+    def fill_dense(self, table, evals):
+        evals = np.ascontiguousarray(evals, dtype=np.uint64).reshape(-1, 4)
+        if evals.shape[0] != 1 << self.n_vars:
+            raise ZkscError(-3, "Number of evaluations must be 2^n_vars")
+        self.ctx.check(lib().zksc_tables_fill_dense(self._h, table, p64(evals)))
 
     def reset(self):
         self.ctx.check(lib().zksc_tables_reset(self._h))

@@ -65,6 +65,25 @@ __global__ void __launch_bounds__(256) outer_kernel(int mul, const Fr* a, unsign
     }
 }
 
+// The same, written into this rank's shard of a table of a zksc_tables handle: out[i'] = a[i / nb] (+|*) b[i % nb],
+// i = i' * shard_count + shard_index  (GKR: W(b) + W(c), W(b) * W(c), gkr/src/protocol.rs:80-81).
+__global__ void __launch_bounds__(256) outer_fill_kernel(int mul, const Fr* a, const Fr* b, unsigned long long nb, Fr* out, unsigned long long n_local,
+                                                         unsigned long long shard_index, unsigned long long shard_count) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long il = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; il < n_local; il += stride) {
+        const unsigned long long o = il * shard_count + shard_index;
+        Fr x = ld256(a + o / nb), y = ld256(b + o % nb);
+        st256(out + il, mul ? fr_mul(x, y) : fr_add(x, y));
+    }
+}
+// out[idx[i]] = vals[i] for the entries of this rank's shard (the table has been zeroed): what folding the gate-label
+// variables of a 0/1 wiring table leaves behind (circuit/src/circuit.rs:57-95 + gkr/src/protocol.rs:70-74, 86-88).
+__global__ void __launch_bounds__(256) scatter_kernel(const unsigned long long* idx, const Fr* vals, unsigned long long count, Fr* out,
+                                                      unsigned long long shard_index, unsigned long long shard_count) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count && idx[i] % shard_count == shard_index) st256(out + idx[i] / shard_count, ld256(vals + i));
+}
+
 // Multilinear::to_bytes (evaluation_form.rs:54-62): Montgomery -> canonical -> 32 big-endian bytes
 __global__ void __launch_bounds__(256) to_bytes_kernel(const Fr* a, Fr* out, unsigned long long n) {
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;

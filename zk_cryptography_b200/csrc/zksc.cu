@@ -645,6 +645,86 @@ extern "C" int zksc_tables_synth(zksc_ctx* ctx, uint32_t n_vars, uint32_t n_proo
     return ZKSC_OK;
 }
 
+extern "C" int zksc_tables_alloc(zksc_ctx* ctx, uint32_t n_vars, uint32_t n_proofs, uint32_t n_products, const uint32_t* degree, zksc_tables** out) {
+    if (!ctx) return ZKSC_ERR_STATE;
+    return tables_alloc(ctx, n_vars, n_proofs, n_products, degree, out);
+}
+
+// common checks of the fill calls: the handle must be unbound (its `orig` tables are being replaced)
+static int fill_prepare(zksc_tables* t, uint32_t table) {
+    zksc_ctx* ctx = t->ctx;
+    CK(cudaSetDevice(ctx->device));
+    TRY(quiesce(ctx));
+    if (table >= t->B * t->Dtot) FAIL(ZKSC_ERR_SHAPE, "table index out of range");
+    TRY(zksc_tables_reset(t));
+    t->r0_valid = false;
+    return ZKSC_OK;
+}
+
+extern "C" int zksc_tables_fill_outer(zksc_tables* t, uint32_t table, int mul, const uint64_t* a, uint64_t na, const uint64_t* b, uint64_t nb) {
+    if (!t) return ZKSC_ERR_STATE;
+    zksc_ctx* ctx = t->ctx;
+    if (!a || !b || !na || !nb) FAIL(ZKSC_ERR_SHAPE, "empty operand");
+    if (na * nb != (1ull << t->n_vars)) FAIL(ZKSC_ERR_SHAPE, "add_distinct / mul_distinct: the operand sizes must multiply to 2^n_vars");
+    TRY(fill_prepare(t, table));
+    DevBuf da, db;
+    CK(cudaMalloc(&da.p, na * sizeof(Fr)));
+    CK(cudaMalloc(&db.p, nb * sizeof(Fr)));
+    CK(cudaMemcpyAsync(da.p, a, na * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(db.p, b, nb * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    outer_fill_kernel<<<grid_for(ctx, t->n_local0, 256, 8), 256, 0, ctx->stream>>>(mul, da.p, db.p, nb, t->orig + (size_t)table * t->n_local0, t->n_local0, ctx->rank,
+                                                                                   ctx->n_ranks);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    return ZKSC_OK;
+}
+
+extern "C" int zksc_tables_fill_sparse(zksc_tables* t, uint32_t table, const uint64_t* idx, const uint64_t* vals, uint64_t count) {
+    if (!t) return ZKSC_ERR_STATE;
+    zksc_ctx* ctx = t->ctx;
+    if (count && (!idx || !vals)) FAIL(ZKSC_ERR_SHAPE, "NULL argument");
+    for (uint64_t i = 0; i < count; i++)
+        if (idx[i] >> t->n_vars) FAIL(ZKSC_ERR_SHAPE, "sparse entry index out of range");
+    TRY(fill_prepare(t, table));
+    Fr* dst = t->orig + (size_t)table * t->n_local0;
+    CK(cudaMemsetAsync(dst, 0, t->n_local0 * sizeof(Fr), ctx->stream));
+    if (count) {
+        DevBuf dv, di;
+        CK(cudaMalloc(&dv.p, count * sizeof(Fr)));
+        CK(cudaMalloc(&di.p, (count + 3) / 4 * sizeof(Fr)));
+        CK(cudaMemcpyAsync(dv.p, vals, count * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(di.p, idx, count * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+        scatter_kernel<<<(unsigned int)((count + 255) / 256), 256, 0, ctx->stream>>>((const unsigned long long*)di.p, dv.p, count, dst, ctx->rank, ctx->n_ranks);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return ZKSC_OK;
+}
+
+extern "C" int zksc_tables_fill_dense(zksc_tables* t, uint32_t table, const uint64_t* evals) {
+    if (!t) return ZKSC_ERR_STATE;
+    zksc_ctx* ctx = t->ctx;
+    if (!evals) FAIL(ZKSC_ERR_SHAPE, "NULL argument");
+    TRY(fill_prepare(t, table));
+    Fr* dst = t->orig + (size_t)table * t->n_local0;
+    if (ctx->n_ranks == 1) {
+        CK(cudaMemcpyAsync(dst, evals, t->n_local0 * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        const uint64_t N = 1ull << t->n_vars;
+        DevBuf stage;
+        CK(cudaMalloc(&stage.p, N * sizeof(Fr)));
+        CK(cudaMemcpyAsync(stage.p, evals, N * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+        pick_shard_kernel<<<grid_for(ctx, t->n_local0, 256, 8), 256, 0, ctx->stream>>>(stage.p, dst, t->n_local0, ctx->n_ranks, ctx->rank);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return ZKSC_OK;
+}
+
 // current buffer geometry
 struct Geo {
     Fr* base;

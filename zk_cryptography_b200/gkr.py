@@ -1,0 +1,238 @@
+"""GKR layer driver over the zksc C ABI: host-side mirror of the reference's `circuit` and `gkr` crates.
+
+  Gate, GateType, CircuitLayer, Circuit      circuit/src/{gate.rs, circuit.rs, utils.rs}
+  GKRProof, GKRProtocol                      gkr/src/{protocol.rs, utils.rs}
+
+Per layer the reference builds four 2^(2k)-entry tables (k = bits of a gate input label) and proves
+    sum_{b,c} add~(b,c) (W(b) + W(c)) + mul~(b,c) (W(b) W(c))           (gkr/src/protocol.rs:67-93)
+with MultiComposedSumcheckProver::prove_partial.  Here the tables are built ON THE DEVICE, straight into the
+prover's table handle:
+  * W(b) + W(c), W(b) W(c)   (add_distinct / mul_distinct, evaluation_form.rs:28-52): one outer-sum / outer-product
+    kernel each from the 2^k layer values                                        -> zksc_tables_fill_outer
+  * add~ = alpha add(r_b, ., .) + beta add(r_c, ., .) (and mul~): the reference folds a dense 0/1 table of 2^(3k-1)
+    entries k-1 times; what is left is  sum over gates g of eq(r, g) at entry (in0(g), in1(g))  -- at most one
+    entry per gate.  Those few values are formed on the host (exact field arithmetic, hence bit-identical) and
+    scattered into a zeroed table                                                -> zksc_tables_fill_sparse
+  * the layer sumcheck (P = 2, d = (2, 2)) runs in the CUDA round kernels        -> zksc_prove
+  * W(b*), W(c*) by k folds on the device                                        -> zksc_ml_evaluation
+The Fiat-Shamir transcripts (outer GKR transcript and the per-layer sumcheck transcripts) stay on the host.
+There is no CPU fallback for the table-sized work.
+"""
+import numpy as np
+
+from . import _lib
+from ._lib import PROTO_MULTI_PARTIAL, Tables, ZkscError, from_mont, to_mont
+from .api import FiatShamirTranscript, Multilinear, MultiComposedProof, MultiComposedSumcheckVerifier, SparseUnivariatePolynomial, default_context
+
+R = _lib.R_MOD
+
+
+class GateType:                  # circuit/src/gate.rs:2-5
+    Add = "Add"
+    Mul = "Mul"
+
+
+class Gate:                      # circuit/src/gate.rs:8-17
+    def __init__(self, gate_type, inputs):
+        self.gate_type, self.inputs = gate_type, list(inputs)
+
+    new = classmethod(lambda cls, gate_type, inputs: cls(gate_type, inputs))
+
+
+class CircuitLayer:              # circuit/src/circuit.rs:10-25
+    def __init__(self, layer):
+        self.layer = list(layer)
+
+    new = classmethod(lambda cls, layer: cls(layer))
+
+
+def size_of_mle_n_var_at_each_layer(layer_index):   # circuit/src/utils.rs:1-10
+    return 1 << 3 if layer_index == 0 else 1 << (layer_index + 2 * (layer_index + 1))
+
+
+def transform_label_to_binary_and_to_decimal(layer_index, a, b, c):   # circuit/src/utils.rs:12-34
+    bits = layer_index + 1
+    for v, w in ((a, max(layer_index, 1)), (b, bits), (c, bits)):
+        if v >> w:
+            raise ZkscError(-3, "gate label does not fit its bit field")
+    return (a << (2 * bits)) | (b << bits) | c
+
+
+class Circuit:                   # circuit/src/circuit.rs:15-122
+    def __init__(self, layers):
+        self.layers = list(layers)
+
+    new = classmethod(lambda cls, layers: cls(layers))
+
+    def evaluation(self, inp):   # :32-55 -- one pass over the gates, host (not table-sized work of the sumcheck path)
+        layers = [[int(v) % R for v in inp]]
+        cur = layers[0]
+        for layer in reversed(self.layers):
+            cur = [(cur[g.inputs[0]] + cur[g.inputs[1]]) % R if g.gate_type == GateType.Add else (cur[g.inputs[0]] * cur[g.inputs[1]]) % R
+                   for g in layer.layer]
+            layers.append(cur)
+        layers.reverse()
+        return layers
+
+    def add_mult_mle(self, layer_index):   # :57-95 (dense; the prover below never materialises it beyond layer 0)
+        n = size_of_mle_n_var_at_each_layer(layer_index)
+        add, mul = [0] * n, [0] * n
+        for gi, g in enumerate(self.layers[layer_index].layer):
+            d = transform_label_to_binary_and_to_decimal(layer_index, gi, g.inputs[0], g.inputs[1])
+            (add if g.gate_type == GateType.Add else mul)[d] = 1
+        return Multilinear(add), Multilinear(mul)
+
+    @staticmethod
+    def random(num_of_layers):   # :97-121
+        layers = []
+        for li in range(num_of_layers):
+            n_in = 2 ** (li + 1)
+            gt = GateType.Add if li % 2 == 0 else GateType.Mul
+            layers.append(CircuitLayer([Gate(gt, [(g * 2) % n_in, (g * 2 + 1) % n_in]) for g in range(2 ** li)]))
+        return Circuit(layers)
+
+
+class GKRProof:                  # gkr/src/protocol.rs:10-15
+    def __init__(self, sumcheck_proofs, wb_s, wc_s, w_0_mle):
+        self.sumcheck_proofs, self.wb_s, self.wc_s, self.w_0_mle = sumcheck_proofs, wb_s, wc_s, w_0_mle
+
+    def to_bytes(self):
+        """w_0, then per layer the sumcheck proof bytes (ComposedSumcheckProof::to_bytes), wb, wc.  The reference has no
+        GKRProof serialiser; this is what its transcript absorbs plus the two claimed evaluations, for comparisons."""
+        out = b"".join(int(e).to_bytes(32, "big") for e in self.w_0_mle.to_ints())
+        for p, wb, wc in zip(self.sumcheck_proofs, self.wb_s, self.wc_s):
+            out += p.to_bytes() + int(wb).to_bytes(32, "big") + int(wc).to_bytes(32, "big")
+        return out
+
+
+def _eq_vector(r):
+    """eq(r, a), a = 0..2^len(r) - 1 with a's most significant bit paired with r[0]: what partial_evaluations(r, [0; len])
+    (evaluation_form.rs:143-159) leaves of the indicator of a."""
+    v = [1]
+    for x in r:
+        nx = (1 - x) % R
+        v = [e * f % R for e in v for f in (nx, x)]
+    return v
+
+
+def _wiring_entries(circuit, layer_index, points_and_scales):
+    """{(in0 << bits) | in1: value} of  sum_j scale_j * add(r_j, ., .)  and the same for mul, circuit layer `layer_index`."""
+    bits = layer_index + 1
+    add, mul = {}, {}
+    for r, scale in points_and_scales:
+        eq = _eq_vector(r)
+        if len(eq) != 1 << max(layer_index, 1):
+            raise ZkscError(-3, "challenge vector does not match the layer's gate-label bits")
+        for gi, g in enumerate(circuit.layers[layer_index].layer):
+            if (g.inputs[0] >> bits) or (g.inputs[1] >> bits):
+                raise ZkscError(-3, "gate input label does not fit its bit field")
+            d = (g.inputs[0] << bits) | g.inputs[1]
+            tgt = add if g.gate_type == GateType.Add else mul
+            tgt[d] = (tgt.get(d, 0) + eq[gi] * scale) % R
+    return add, mul
+
+
+def _fill_sparse(tables, index, entries):
+    idx = np.fromiter(entries.keys(), dtype=np.uint64, count=len(entries))
+    vals = to_mont(list(entries.values())) if entries else np.zeros((0, 4), dtype=np.uint64)
+    tables.fill_sparse(index, idx, vals)
+
+
+class GKRProtocol:               # gkr/src/protocol.rs:17-195
+    @staticmethod
+    def _layer(ctx, circuit, layer_index, w_ints, points_and_scales, claimed_sum, transcript, proofs, wb_s, wc_s):
+        """One layer: build the four tables on the device, prove_partial, absorb the proof, evaluate W at the two halves of
+        the challenge vector, draw (alpha, beta).  gkr/src/utils.rs:12-57 and gkr/src/protocol.rs:66-104."""
+        k = len(w_ints).bit_length() - 1
+        if len(w_ints) != 1 << k:
+            raise ZkscError(-3, "Number of evaluations must be a power of 2")
+        w = to_mont(w_ints)
+        add, mul = _wiring_entries(circuit, layer_index, points_and_scales)
+        t = Tables.alloc(ctx, 2 * k, [2, 2])
+        try:
+            _fill_sparse(t, 0, add)                 # alpha add(r_b, b, c) + beta add(r_c, b, c)
+            t.fill_outer(1, False, w, w)            # W(b) + W(c)      add_distinct
+            _fill_sparse(t, 2, mul)                 # alpha mul(r_b, b, c) + beta mul(r_c, b, c)
+            t.fill_outer(3, True, w, w)             # W(b) W(c)        mul_distinct
+            msgs, lens, chal = t.prove(PROTO_MULTI_PARTIAL, to_mont(claimed_sum))
+        finally:
+            t.free()
+        n = 2 * k
+        rps = []
+        for r in range(n):
+            m = int(lens[0, r])
+            v = from_mont(msgs[0, r, :2 * m]) if m else []
+            rps.append(SparseUnivariatePolynomial([(v[2 * i], v[2 * i + 1]) for i in range(m)]))
+        proof = MultiComposedProof(rps, claimed_sum % R, (msgs[0], lens[0]))
+        transcript.commit(proof.to_bytes())
+        proofs.append(proof)
+        ch = from_mont(chal[0]) if n else []
+        b, c = ch[:len(ch) // 2], ch[len(ch) // 2:]
+        wm = Multilinear(w)
+        eval_wb, eval_wc = wm.evaluation(b), wm.evaluation(c)
+        wb_s.append(eval_wb)
+        wc_s.append(eval_wc)
+        alpha, beta = transcript.evaluate_challenge_into_field(), transcript.evaluate_challenge_into_field()
+        return (alpha * eval_wb + beta * eval_wc) % R, alpha, beta, b, c
+
+    @staticmethod
+    def prove(circuit, circuit_evaluation, ctx=None):   # :21-113
+        ctx = ctx or default_context()
+        transcript = FiatShamirTranscript()
+        proofs, wb_s, wc_s = [], [], []
+        w_0_mle = Multilinear([int(v) % R for v in circuit_evaluation[0]] + [0])            # :31-34
+        transcript.commit(b"".join(int(e).to_bytes(32, "big") for e in w_0_mle.to_ints()))  # :35
+        n_r = transcript.evaluate_n_challenge_into_field(w_0_mle.n_vars)                    # :37
+        claimed = w_0_mle.evaluation(n_r)                                                   # :38
+        # layer one: add(n_r, b, c), mul(n_r, b, c) unscaled (gkr/src/utils.rs:23-33)
+        claimed, alpha, beta, r_b, r_c = GKRProtocol._layer(ctx, circuit, 0, circuit_evaluation[1], [(n_r, 1)], claimed, transcript, proofs, wb_s, wc_s)
+        for layer_index in range(2, len(circuit_evaluation)):                               # :65-105
+            claimed, alpha, beta, r_b, r_c = GKRProtocol._layer(ctx, circuit, layer_index - 1, circuit_evaluation[layer_index],
+                                                                [(r_b, alpha), (r_c, beta)], claimed, transcript, proofs, wb_s, wc_s)
+        return GKRProof(proofs, wb_s, wc_s, w_0_mle)
+
+    @staticmethod
+    def verify(circuit, inp, proof):          # :115-195
+        if len(proof.sumcheck_proofs) != len(proof.wb_s) or len(proof.sumcheck_proofs) != len(proof.wc_s):
+            return False
+        transcript = FiatShamirTranscript()
+        transcript.commit(b"".join(int(e).to_bytes(32, "big") for e in proof.w_0_mle.to_ints()))
+        n_r = transcript.evaluate_n_challenge_into_field(proof.w_0_mle.n_vars)
+        claimed = proof.w_0_mle.evaluation(n_r)
+        # generate_layer_one_verify_sumcheck, gkr/src/utils.rs:59-98
+        p0 = proof.sumcheck_proofs[0]
+        if claimed != p0.sum:
+            return False
+        transcript.commit(p0.to_bytes())
+        try:
+            sub = MultiComposedSumcheckVerifier.verify_partial(p0)
+        except ZkscError as e:
+            if e.code == -7:
+                return False
+            raise
+        add1, mul1 = circuit.add_mult_mle(0)
+        rbc = list(n_r) + list(sub.challenges)
+        wb, wc = proof.wb_s[0], proof.wc_s[0]
+        if (add1.evaluation(rbc) * ((wb + wc) % R) + mul1.evaluation(rbc) * (wb * wc % R)) % R != sub.sum:
+            return False
+        alpha, beta = transcript.evaluate_challenge_into_field(), transcript.evaluate_challenge_into_field()
+        claimed = (alpha * wb + beta * wc) % R
+        r_b, r_c = [], []
+        for i in range(1, len(proof.sumcheck_proofs)):         # :155-181
+            p = proof.sumcheck_proofs[i]
+            if claimed != p.sum:
+                return False
+            transcript.commit(p.to_bytes())
+            try:
+                sub = MultiComposedSumcheckVerifier.verify_partial(p)
+            except ZkscError as e:
+                if e.code == -7:
+                    return False
+                raise
+            ch = sub.challenges
+            r_b, r_c = ch[:len(ch) // 2], ch[len(ch) // 2:]
+            wb, wc = proof.wb_s[i], proof.wc_s[i]
+            alpha, beta = transcript.evaluate_challenge_into_field(), transcript.evaluate_challenge_into_field()
+            claimed = (alpha * wb + beta * wc) % R
+        w_in = Multilinear([int(v) % R for v in inp])
+        return claimed == (alpha * w_in.evaluation(r_b) + beta * w_in.evaluation(r_c)) % R     # :183-192
