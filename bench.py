@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- sumcheck prover throughput (hypercube evals/s) on N B200s, or the CPU reference arm.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c1|c5] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c1|c4|c5] [--impl b200|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 One step = what the reference's `multi_composed_sumcheck_with_prove_partial_benchmark` times
@@ -12,6 +12,7 @@ on synthetic seeded tables.  Workloads (BASELINE.json configs):
     c3            one degree-3 product, 2^28 entries in total, sharded over the N GPUs (strong scaling)
     c1            Sumcheck::prove on one 2^20-entry multilinear (replicated on every GPU)
     c5            64 independent degree-2 proofs of 2^22 entries, 64/N per GPU (replicas, batched launches)
+    c4            GKRProtocol::prove on Circuit::random(10): 10 layer sumchecks (largest 2^20 entries) with device-built tables
 `value`   : tables resident in HBM when the clock starts (generated on the device).
 `e2e`     : the same step through the public API with HOST tables: pinned host -> device copy of every
             table and device -> host copy of the proof inside the timed region.
@@ -42,6 +43,9 @@ WORKLOADS = {
                desc="MultiComposedSumcheckProver: calculate_poly_sum + prove_partial, one degree-3 product, 2^28 entries in total"),
     "c1": dict(n=20, degs=[1], proto="sumcheck", proofs=1, scaling="replicas",
                desc="Sumcheck: poly_sum + prove, one 2^20-entry multilinear per GPU"),
+    "c4": dict(n=20, degs=[2, 2], proto="gkr", proofs=1, scaling="replicas", depth=10,
+               desc="GKRProtocol::prove on Circuit::random(10) (the reference's circuit shape: 2^10 inputs, 10 layer sumchecks of 2^2..2^20 entries, "
+                    "P=2, d=(2,2); layer tables built on the device), replicated on every GPU"),
     "c5": dict(n=22, degs=[2], proto="multi_partial", proofs=64, scaling="strong",
                desc="64 independent prove_partial (degree-2 product, 2^22 entries each), 64/N proofs per GPU, batched launches"),
 }
@@ -164,6 +168,8 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     wl = dict(WORKLOADS[args.workload])
+    if wl["proto"] == "gkr":
+        return run_gkr(args, wl, world, rank, local_rank, dist)
     G = world
     lgG = int(math.log2(G))
     ctx = zk.Context(local_rank)
@@ -352,6 +358,93 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def gkr_inputs(depth):
+    R = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+    return [(0x9E3779B97F4A7C15 * (i + 1) + SEED) % R for i in range(1 << depth)]
+
+
+def run_gkr(args, wl, world, rank, local_rank, dist):
+    """c4: one step = GKRProtocol::prove (gkr/src/protocol.rs:21-113) of Circuit::random(depth) on host-resident layer values.
+    The unit is the hypercube entries of the layer sumchecks (sum over layers of 2^(2k)).  Inputs live on the host by
+    construction (circuit evaluation is the caller's), so `value` and `e2e` time the same call; only the clock differs."""
+    import torch
+
+    import zk_cryptography_b200 as zk
+    depth = wl["depth"]
+    ctx = zk.Context(local_rank)
+    zk.set_default_context(ctx)
+    circuit = zk.Circuit.random(depth)
+    inp = gkr_inputs(depth)
+    ev = circuit.evaluation(inp)
+    evals_per_step = sum(len(l) ** 2 for l in ev[1:]) * world
+    stream = torch.cuda.ExternalStream(ctx.stream_handle(), device=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        proof = zk.GKRProtocol.prove(circuit, ev, ctx)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    launches0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.start()
+    e0.record(stream)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        proof = zk.GKRProtocol.prove(circuit, ev, ctx)
+    e1.record(stream)
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    sampler.stop_flag = True
+    ms = e0.elapsed_time(e1)
+    launches = ctx.launch_count() - launches0
+    if dist is not None:
+        tms = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    sampler.join(timeout=1.0)
+    assert zk.GKRProtocol.verify(circuit, inp, proof), "GKR proof does not verify"
+    if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+    h2d = sum(2 * 32 * len(l) for l in ev[1:]) + sum(2 * 40 * len(l.layer) for l in circuit.layers)
+    d2h = len(proof.to_bytes())
+    value = evals_per_step * args.steps / (ms * 1e-3)
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        from oracle import gkrmodel as g
+        oc = g.Circuit.random(depth - 2)
+        oin = gkr_inputs(depth - 2)
+        oev = oc.evaluation(oin)
+        t1 = time.perf_counter()
+        g.GKRProtocol.prove_sparse(oc, oev, layer_prover=g.c_layer_prover, evaluate=g.c_evaluate)
+        dt = time.perf_counter() - t1
+        cpu = {"value": sum(len(l) ** 2 for l in oev[1:]) / dt, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": "oracle/gkrmodel.py prove_sparse (Python layer driver, layer sumchecks in oracle/zkref.c, 1 thread) on Circuit::random(%d), %.2f s" % (depth - 2, dt)}
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (256-bit modular integer, BLS12-381 Fr, Montgomery)",
+        "data": "synthetic (Circuit::random gates, seeded inputs)",
+        "config": {"workload": "c4: " + wl["desc"], "depth": depth, "layer_sumcheck_entries": [len(l) ** 2 for l in ev[1:]], "degrees": wl["degs"],
+                   "l2_policy": "inputs_fit_l2_no_flush (largest layer: 4 x 32 MiB)", "sharding": "replicas" if world > 1 else "single GPU", "proof_bytes": d2h},
+        "clocks": sampler.summary(), "gpu_launches": int(launches),
+        "e2e": {"value": evals_per_step * args.steps / (wall_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": round(wall_ms / args.steps, 4), "api": "GKRProtocol.prove(circuit, circuit_evaluation): host layer values in, proof out (host wall clock)"},
+        "roofline": None, "int_roofline": None, "cpu_baseline": cpu,
+        "note": "latency-bound: 110 sumcheck rounds + 10 layer set-ups per proof, Python layer driver; no single dominant kernel, hence no roofline object",
+    }
+    print(json.dumps(out))
+    sys.stdout.flush()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def cpu_workload(workload, sample_n):
     import numpy as np
     from oracle import cref
@@ -390,6 +483,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if WORKLOADS[args.workload]["proto"] == "gkr":
+        return run_reference_gkr(args)
     cref, wl, n, tabs, proto = cpu_workload(args.workload, args.cpu_n)
     th = cref.max_threads()
     cref.set_threads(th)
@@ -415,6 +510,40 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(out))
+
+
+def run_reference_gkr(args):
+    """c4 on the host: the oracle's GKR driver (Python) with its layer sumchecks in the C oracle, on a bounded sample
+    (Circuit::random(depth - 2): cost is dominated by the largest layers, 4x per extra layer)."""
+    from oracle import cref
+    from oracle import gkrmodel as g
+    wl = WORKLOADS[args.workload]
+    depth = wl["depth"] - 2
+    th = cref.max_threads()
+    cref.set_threads(th)
+    oc = g.Circuit.random(depth)
+    oev = oc.evaluation(gkr_inputs(depth))
+    units = sum(len(l) ** 2 for l in oev[1:])
+
+    def step():
+        g.GKRProtocol.prove_sparse(oc, oev, layer_prover=g.c_layer_prover, evaluate=g.c_evaluate)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = units * args.steps / dt
+    sample = "oracle/gkrmodel.py prove_sparse on Circuit::random(%d) (bounded sample of c4), layer sumchecks in oracle/zkref.c on %d OpenMP threads" % (depth, th)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64 limbs (256-bit modular integer, BLS12-381 Fr, Montgomery)", "data": "synthetic (same circuit family and inputs)",
+        "config": {"workload": "c4: " + wl["desc"], "depth": depth},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": th, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
 
 
 def main():

@@ -227,6 +227,12 @@ extern "C" int zksc_ctx_create(int device, zksc_ctx** out) {
     if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail(e, "cudaGetDeviceProperties");
     ctx->sms = prop.multiProcessorCount;
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
+    {   // keep up to 2 GiB of released blocks in the device's stream-ordered pool (dev_alloc below); larger ones go back at the next sync
+        cudaMemPool_t pool;
+        unsigned long long keep = 2ull << 30;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        cudaGetLastError();
+    }
     if ((e = cudaMalloc(&ctx->counters, (kMaxBatch + 1) * sizeof(unsigned int))) != cudaSuccess) return fail(e, "cudaMalloc");
     if ((e = cudaMemset(ctx->counters, 0, (kMaxBatch + 1) * sizeof(unsigned int))) != cudaSuccess) return fail(e, "cudaMemset");
 #define ZKSC_OCC(D) zksc_prepare_round_##D(); for (int v = 0; v < 6; v++) ctx->occ[D][v] = zksc_occ_round_##D(v);
@@ -466,9 +472,18 @@ static int ensure_partials(zksc_ctx* ctx, size_t elems) {
     return ZKSC_OK;
 }
 
+// Device memory comes from the device's stream-ordered pool (cudaMallocAsync on the context's stream): an allocation or a
+// release costs microseconds and never synchronises the device -- the GKR driver builds and drops four tables per layer,
+// and a plain cudaFree would wait for a resident rounds kernel to time out.
+static cudaError_t dev_alloc(zksc_ctx* ctx, void** p, size_t bytes) { return cudaMallocAsync(p, bytes ? bytes : 1, ctx->stream); }
+static void dev_free(zksc_ctx* ctx, void* p) { if (p) cudaFreeAsync(p, ctx->stream); }
 struct DevBuf {
+    zksc_ctx* ctx;
     Fr* p = nullptr;
-    ~DevBuf() { cudaFree(p); }
+    explicit DevBuf(zksc_ctx* c) : ctx(c) {}
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { dev_free(ctx, p); }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -494,11 +509,11 @@ static int tables_alloc(zksc_ctx* ctx, uint32_t n_vars, uint32_t B, uint32_t P, 
     CK(cudaSetDevice(ctx->device));
     size_t n_orig = (size_t)B * t->Dtot * t->n_local0;
     size_t n_work = (size_t)B * t->Dtot * (t->n_local0 > 1 ? t->n_local0 / 2 : 1);
-    cudaError_t e = cudaMalloc(&t->orig, n_orig * sizeof(Fr));
-    if (e == cudaSuccess) e = cudaMalloc(&t->work, n_work * sizeof(Fr));
-    if (e == cudaSuccess && ctx->n_ranks > 1) e = cudaMalloc(&t->tail, (size_t)B * t->Dtot * ctx->n_ranks * sizeof(Fr));
+    cudaError_t e = dev_alloc(ctx, (void**)&t->orig, n_orig * sizeof(Fr));
+    if (e == cudaSuccess) e = dev_alloc(ctx, (void**)&t->work, n_work * sizeof(Fr));
+    if (e == cudaSuccess && ctx->n_ranks > 1) e = dev_alloc(ctx, (void**)&t->tail, (size_t)B * t->Dtot * ctx->n_ranks * sizeof(Fr));
     if (e != cudaSuccess) {
-        cudaFree(t->orig); cudaFree(t->work); cudaFree(t->tail);
+        dev_free(ctx, t->orig); dev_free(ctx, t->work); dev_free(ctx, t->tail);
         delete t;
         ctx->err = std::string("cudaMalloc(tables): ") + cudaGetErrorString(e);
         cudaGetLastError();
@@ -507,7 +522,7 @@ static int tables_alloc(zksc_ctx* ctx, uint32_t n_vars, uint32_t B, uint32_t P, 
     {
         size_t need = (size_t)B * t->E, need2 = (size_t)B * t->Dtot;
         int rc = ensure_results(ctx, need > need2 ? need : need2);
-        if (rc != ZKSC_OK) { cudaFree(t->orig); cudaFree(t->work); cudaFree(t->tail); delete t; return rc; }
+        if (rc != ZKSC_OK) { dev_free(ctx, t->orig); dev_free(ctx, t->work); dev_free(ctx, t->tail); delete t; return rc; }
     }
     zksc_tables_reset(t);
     *out = t;
@@ -529,11 +544,10 @@ extern "C" int zksc_tables_reset(zksc_tables* t) {
 
 extern "C" int zksc_tables_free(zksc_tables* t) {
     if (!t) return ZKSC_OK;
-    cudaSetDevice(t->ctx->device);
+    zksc_ctx* ctx = t->ctx;
+    cudaSetDevice(ctx->device);
     tail_stop(t);
-    quiesce(t->ctx);      // cudaFree synchronises the whole device
-    cudaStreamSynchronize(t->ctx->stream);
-    cudaFree(t->orig); cudaFree(t->work); cudaFree(t->tail);
+    dev_free(ctx, t->orig); dev_free(ctx, t->work); dev_free(ctx, t->tail);   // stream-ordered: after everything queued so far
     delete t;
     return ZKSC_OK;
 }
@@ -570,8 +584,8 @@ static int upload_into(zksc_tables* t, const uint64_t* const* host_tables, bool 
         for (size_t i = 0; i < n_tabs; i++) CK(cudaMemcpyAsync(t->orig + i * NL, host_tables[i], NL * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
     } else {
         // stage one full table at a time, keep the entries with index = rank (mod n_ranks)
-        DevBuf stage;
-        CK(cudaMalloc(&stage.p, N * sizeof(Fr)));
+        DevBuf stage(ctx);
+        CK(dev_alloc(ctx, (void**)&stage.p, N * sizeof(Fr)));
         for (size_t i = 0; i < n_tabs; i++) {
             CK(cudaMemcpyAsync(stage.p, host_tables[i], N * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
             pick_shard_kernel<<<grid_for(ctx, t->n_local0, 256, 8), 256, 0, ctx->stream>>>(stage.p, t->orig + i * t->n_local0, t->n_local0, ctx->n_ranks, ctx->rank);
@@ -667,9 +681,9 @@ extern "C" int zksc_tables_fill_outer(zksc_tables* t, uint32_t table, int mul, c
     if (!a || !b || !na || !nb) FAIL(ZKSC_ERR_SHAPE, "empty operand");
     if (na * nb != (1ull << t->n_vars)) FAIL(ZKSC_ERR_SHAPE, "add_distinct / mul_distinct: the operand sizes must multiply to 2^n_vars");
     TRY(fill_prepare(t, table));
-    DevBuf da, db;
-    CK(cudaMalloc(&da.p, na * sizeof(Fr)));
-    CK(cudaMalloc(&db.p, nb * sizeof(Fr)));
+    DevBuf da(ctx), db(ctx);
+    CK(dev_alloc(ctx, (void**)&da.p, na * sizeof(Fr)));
+    CK(dev_alloc(ctx, (void**)&db.p, nb * sizeof(Fr)));
     CK(cudaMemcpyAsync(da.p, a, na * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(db.p, b, nb * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
     outer_fill_kernel<<<grid_for(ctx, t->n_local0, 256, 8), 256, 0, ctx->stream>>>(mul, da.p, db.p, nb, t->orig + (size_t)table * t->n_local0, t->n_local0, ctx->rank,
@@ -690,9 +704,9 @@ extern "C" int zksc_tables_fill_sparse(zksc_tables* t, uint32_t table, const uin
     Fr* dst = t->orig + (size_t)table * t->n_local0;
     CK(cudaMemsetAsync(dst, 0, t->n_local0 * sizeof(Fr), ctx->stream));
     if (count) {
-        DevBuf dv, di;
-        CK(cudaMalloc(&dv.p, count * sizeof(Fr)));
-        CK(cudaMalloc(&di.p, (count + 3) / 4 * sizeof(Fr)));
+        DevBuf dv(ctx), di(ctx);
+        CK(dev_alloc(ctx, (void**)&dv.p, count * sizeof(Fr)));
+        CK(dev_alloc(ctx, (void**)&di.p, (count + 3) / 4 * sizeof(Fr)));
         CK(cudaMemcpyAsync(dv.p, vals, count * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemcpyAsync(di.p, idx, count * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
         scatter_kernel<<<(unsigned int)((count + 255) / 256), 256, 0, ctx->stream>>>((const unsigned long long*)di.p, dv.p, count, dst, ctx->rank, ctx->n_ranks);
@@ -713,8 +727,8 @@ extern "C" int zksc_tables_fill_dense(zksc_tables* t, uint32_t table, const uint
         CK(cudaMemcpyAsync(dst, evals, t->n_local0 * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
     } else {
         const uint64_t N = 1ull << t->n_vars;
-        DevBuf stage;
-        CK(cudaMalloc(&stage.p, N * sizeof(Fr)));
+        DevBuf stage(ctx);
+        CK(dev_alloc(ctx, (void**)&stage.p, N * sizeof(Fr)));
         CK(cudaMemcpyAsync(stage.p, evals, N * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
         pick_shard_kernel<<<grid_for(ctx, t->n_local0, 256, 8), 256, 0, ctx->stream>>>(stage.p, dst, t->n_local0, ctx->n_ranks, ctx->rank);
         ctx->launches++;
@@ -1300,8 +1314,9 @@ extern "C" int zksc_tables_to_bytes(zksc_tables* t, uint32_t proof, uint8_t* out
     if (proof >= t->B) FAIL(ZKSC_ERR_SHAPE, "proof index");
     const uint64_t N = t->n_local0;
     const uint64_t chunk = N < (1ull << 22) ? N : (1ull << 22);
-    Fr* tmp = nullptr;
-    CK(cudaMalloc(&tmp, chunk * sizeof(Fr)));
+    DevBuf tmpbuf(ctx);
+    CK(dev_alloc(ctx, (void**)&tmpbuf.p, chunk * sizeof(Fr)));
+    Fr* const tmp = tmpbuf.p;
     for (uint32_t k = 0; k < t->Dtot; k++) {
         const Fr* src = t->orig + ((size_t)proof * t->Dtot + k) * N;
         for (uint64_t off = 0; off < N; off += chunk) {
@@ -1309,10 +1324,9 @@ extern "C" int zksc_tables_to_bytes(zksc_tables* t, uint32_t proof, uint8_t* out
             ctx->launches++;
             cudaError_t e = cudaMemcpyAsync(out + ((size_t)k * N + off) * 32, tmp, chunk * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream);
             if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-            if (e != cudaSuccess) { cudaFree(tmp); ctx->err = std::string("to_bytes: ") + cudaGetErrorString(e); return ZKSC_ERR_CUDA; }
+            if (e != cudaSuccess) { ctx->err = std::string("to_bytes: ") + cudaGetErrorString(e); return ZKSC_ERR_CUDA; }
         }
     }
-    cudaFree(tmp);
     return ZKSC_OK;
 }
 
@@ -1503,9 +1517,9 @@ extern "C" int zksc_ml_partial_evaluation(zksc_ctx* ctx, const uint64_t* evals, 
     if (n % 2 != 0 || variable_index >= n / 2 || (n >> (variable_index + 1)) == 0) FAIL(ZKSC_ERR_SHAPE, "variable_index must be less than n/2 and name an existing variable");
     CK(cudaSetDevice(ctx->device));
     TRY(quiesce(ctx));
-    DevBuf in, o;
-    CK(cudaMalloc(&in.p, n * sizeof(Fr)));
-    CK(cudaMalloc(&o.p, n / 2 * sizeof(Fr)));
+    DevBuf in(ctx), o(ctx);
+    CK(dev_alloc(ctx, (void**)&in.p, n * sizeof(Fr)));
+    CK(dev_alloc(ctx, (void**)&o.p, n / 2 * sizeof(Fr)));
     CK(cudaMemcpyAsync(in.p, evals, n * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
     FoldArgs a;
     a.in = in.p; a.out = o.p;
@@ -1527,8 +1541,8 @@ extern "C" int zksc_ml_evaluation(zksc_ctx* ctx, const uint64_t* evals, uint64_t
     if ((1ull << n_points) != n) FAIL(ZKSC_ERR_SHAPE, "Number of evaluation points must match the number of variables");
     CK(cudaSetDevice(ctx->device));
     TRY(quiesce(ctx));
-    DevBuf buf;
-    CK(cudaMalloc(&buf.p, n * sizeof(Fr)));
+    DevBuf buf(ctx);
+    CK(dev_alloc(ctx, (void**)&buf.p, n * sizeof(Fr)));
     CK(cudaMemcpyAsync(buf.p, evals, n * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
     uint64_t cur = n;
     for (uint32_t j = 0; j < n_points; j++) {
@@ -1554,10 +1568,10 @@ extern "C" int zksc_ml_outer(zksc_ctx* ctx, int mul, const uint64_t* a, uint64_t
     if (n & (n - 1)) FAIL(ZKSC_ERR_SHAPE, "Number of evaluations must be a power of 2");
     CK(cudaSetDevice(ctx->device));
     TRY(quiesce(ctx));
-    DevBuf da, db, dout;
-    CK(cudaMalloc(&da.p, na * sizeof(Fr)));
-    CK(cudaMalloc(&db.p, nb * sizeof(Fr)));
-    CK(cudaMalloc(&dout.p, n * sizeof(Fr)));
+    DevBuf da(ctx), db(ctx), dout(ctx);
+    CK(dev_alloc(ctx, (void**)&da.p, na * sizeof(Fr)));
+    CK(dev_alloc(ctx, (void**)&db.p, nb * sizeof(Fr)));
+    CK(dev_alloc(ctx, (void**)&dout.p, n * sizeof(Fr)));
     CK(cudaMemcpyAsync(da.p, a, na * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(db.p, b, nb * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
     outer_kernel<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(mul, da.p, na, db.p, nb, dout.p);
@@ -1574,11 +1588,11 @@ extern "C" int zksc_ml_elementwise(zksc_ctx* ctx, int op, const uint64_t* a, con
     if (op < 0 || op > 3) FAIL(ZKSC_ERR_SHAPE, "op");
     CK(cudaSetDevice(ctx->device));
     TRY(quiesce(ctx));
-    DevBuf da, db, dout;
+    DevBuf da(ctx), db(ctx), dout(ctx);
     const uint64_t nb = (op == EW_SCALE) ? 1 : n;
-    CK(cudaMalloc(&da.p, n * sizeof(Fr)));
-    CK(cudaMalloc(&db.p, nb * sizeof(Fr)));
-    CK(cudaMalloc(&dout.p, n * sizeof(Fr)));
+    CK(dev_alloc(ctx, (void**)&da.p, n * sizeof(Fr)));
+    CK(dev_alloc(ctx, (void**)&db.p, nb * sizeof(Fr)));
+    CK(dev_alloc(ctx, (void**)&dout.p, n * sizeof(Fr)));
     CK(cudaMemcpyAsync(da.p, a, n * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(db.p, b, nb * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
     ew_kernel<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(op, da.p, db.p, dout.p, n);
