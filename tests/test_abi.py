@@ -31,3 +31,11 @@ def test_version_and_device_count(built):
     L = zk.lib()
     assert b"sm_100a" in L.zksc_version()
     assert L.zksc_device_count() >= 0
+
+
+def test_rust_ffi_is_in_sync_with_the_header(built):
+    """rust/zksc-sys/src/ffi.rs is generated from include/zksc.h (tools/gen_rust_ffi.py): every declared entry point must
+    be declared there too (the Rust crates are source only -- no toolchain in the image -- so drift would go unnoticed)."""
+    ffi = open(os.path.join(ROOT, "rust", "zksc-sys", "src", "ffi.rs")).read()
+    rust = set(re.findall(r"pub fn (zksc_[a-z0-9_]+)\(", ffi))
+    assert rust == set(declared_symbols())
