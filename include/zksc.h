@@ -93,6 +93,12 @@ int zksc_tables_upload_local(zksc_ctx* ctx, uint32_t n_vars, uint32_t n_proofs, 
  * zksc_tables_upload (local == 0) / zksc_tables_upload_local (local != 0) for callers that prove many
  * instances of one shape. */
 int zksc_tables_reupload(zksc_tables* t, const uint64_t* const* host_tables, int local);
+/* The same refill, split in two so that it overlaps other work of the context (double buffering across proofs: prove handle
+ * A on the compute stream while handle B is refilled on the context's copy stream).  _begin queues the copies and returns;
+ * the host buffers (pinned memory for a truly asynchronous copy) stay borrowed until _end returns.  Any other call on the
+ * handle finishes a pending refill first.  Sharded contexts with full (non-local) tables copy synchronously in _begin. */
+int zksc_tables_reupload_begin(zksc_tables* t, const uint64_t* const* host_tables, int local);
+int zksc_tables_reupload_end(zksc_tables* t);
 /* This rank's copy of the tables as uploaded (n_proofs x n_tables x 2^n_vars / n_ranks elements). */
 int zksc_tables_read_local(zksc_tables* t, uint64_t* out);
 /* Fill tables on the device with the seeded synthetic generator (entry = f(seed + proof, table, i);
@@ -174,6 +180,28 @@ int zksc_verify_rounds(int protocol, uint32_t n_vars, uint32_t msg_stride, const
  * ComposedSumcheck::verify (:94): sum_p prod_k f_{p,k}(points), by n successive folds on the device.
  * points: n_proofs x n_vars elements; out: n_proofs elements.  Resets the tables first and after. */
 int zksc_evaluate(zksc_tables* t, const uint64_t* points, uint64_t* out);
+
+/* ---- GKR layer driver -------------------------------------------------------
+ * GKRProtocol::prove (gkr/src/protocol.rs:21-113, layer one: gkr/src/utils.rs:12-57) in one call: per layer the four
+ * tables [alpha add(r_b,.,.) + beta add(r_c,.,.), W(b)+W(c), alpha mul(..) + beta mul(..), W(b) W(c)] are built in HBM
+ * (outer sum / product kernels; the wiring tables as a sparse scatter of sum_g eq(r, g) at (in0(g), in1(g))), the layer
+ * sumcheck is MultiComposedSumcheckProver::prove_partial on the device, W(b*), W(c*) are evaluated on the device, and the
+ * outer Fiat-Shamir transcript (w_0 bytes, every proof's to_bytes, n_r, alpha, beta) runs on the host.
+ * Circuit (circuit/src/circuit.rs:10-25): n_layers layers, output layer first; layer i has n_gates[i] = 2^i gates whose
+ * inputs are labels of i + 1 bits into layer i + 1 (circuit/src/utils.rs:12-34); gates of all layers concatenated in
+ * gate_type (0 = Add, 1 = Mul, gate.rs:2-5), gate_in0, gate_in1.
+ * layer_values: n_layers + 1 host vectors = Circuit::evaluation's result (circuit.rs:32-55), [0] = output ... [n_layers] =
+ * input, value_len[i] = 2^i Montgomery elements.
+ * Outputs (Montgomery): w0[2] = [out, 0] (protocol.rs:31-34); per layer i: sums[i] (the claimed sum of its sumcheck),
+ * wb_s[i], wc_s[i] (protocol.rs:103-105); the rounds of all layers concatenated -- layer i has 2 (i + 1) rounds,
+ * zksc_gkr_total_rounds(n_layers) = n_layers (n_layers + 1) in total -- as round_msgs (6 elements per round: up to three
+ * (coeff, pow) monomials), round_len (monomials per round) and challenges (one element per round), the per-layer slices
+ * being exactly what zksc_prove(ZKSC_PROTO_MULTI_PARTIAL) writes and zksc_proof_to_bytes / zksc_verify_rounds read.
+ * Shape violations the reference's constructors panic on return ZKSC_ERR_SHAPE.  Unsharded contexts only. */
+uint64_t zksc_gkr_total_rounds(uint32_t n_layers);
+int zksc_gkr_prove(zksc_ctx* ctx, uint32_t n_layers, const uint32_t* n_gates, const uint8_t* gate_type, const uint32_t* gate_in0,
+                   const uint32_t* gate_in1, const uint64_t* const* layer_values, const uint64_t* value_len, uint64_t* w0, uint64_t* sums,
+                   uint64_t* wb_s, uint64_t* wc_s, uint64_t* round_msgs, uint32_t* round_len, uint64_t* challenges);
 
 /* ---- stand-alone Multilinear operations on caller-owned host vectors (device compute) -----------
  * Each copies its inputs to the device, runs the CUDA kernel and copies the result back. */

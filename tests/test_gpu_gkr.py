@@ -78,3 +78,45 @@ def test_gkr_full_width_roundtrip():
     assert zk.GKRProtocol.verify(zc, inp, proof)
     assert zk.GKRProtocol.prove(zc, ev).to_bytes() == proof.to_bytes()
     assert len(proof.sumcheck_proofs) == 10 and len(proof.sumcheck_proofs[-1].round_polys) == 20
+
+
+@pytest.mark.parametrize("depth", [1, 2, 3, 6])
+def test_gkr_c_driver_matches_layerwise_driver(depth):
+    """zksc_gkr_prove (the whole proof in one C call) against the same protocol driven layer by layer over the finer-grained
+    entry points: same bytes, same claimed evaluations, same sums."""
+    zc = zk.Circuit.random(depth)
+    inp = [(0xA24BAED4963EE407 * (i + 3)) % R for i in range(1 << depth)]
+    ev = zc.evaluation(inp)
+    a, b = zk.GKRProtocol.prove(zc, ev), zk.GKRProtocol.prove_layerwise(zc, ev)
+    assert a.to_bytes() == b.to_bytes()
+    assert a.wb_s == b.wb_s and a.wc_s == b.wc_s
+    assert [p.sum for p in a.sumcheck_proofs] == [p.sum for p in b.sumcheck_proofs]
+    if depth >= 2:   # with one layer the reference's verifier never sets r_b / r_c and panics in evaluation (protocol.rs:133-186)
+        assert zk.GKRProtocol.verify(zc, inp, a)
+    else:
+        with pytest.raises(zk.ZkscError):
+            zk.GKRProtocol.verify(zc, inp, a)
+
+
+def test_gkr_c_driver_reference_cases_layerwise_too():
+    for layers, inp in [(CIRCUIT_1, [2, 3, 4, 5]), (CIRCUIT_2, [2, 1, 3, 1, 4, 1, 2, 2, 3, 3, 4, 4, 2, 3, 3, 4])]:
+        zc, oc = both(layers)
+        ev = zc.evaluation(inp)
+        assert zk.GKRProtocol.prove_layerwise(zc, ev).to_bytes() == g.GKRProtocol.prove(oc, ev).to_bytes()
+
+
+def test_gkr_c_driver_shape_errors():
+    """what the reference's constructors panic on (Multilinear::new power-of-two, ComposedMultilinear::new equal arity,
+    label widths of circuit/src/utils.rs:12-34) comes back as ZKSC_ERR_SHAPE"""
+    zc = zk.Circuit.random(3)
+    ev = zc.evaluation(list(range(1, 9)))
+    bad = [list(l) for l in ev]
+    bad[2] = bad[2][:3]                                   # not a power of two
+    with pytest.raises(zk.ZkscError) as e:
+        zk.GKRProtocol.prove(zc, bad)
+    assert e.value.code == -3
+    with pytest.raises(zk.ZkscError):
+        zk.GKRProtocol.prove(zc, ev[:-1])                 # a layer is missing
+    two_out = zk.Circuit([zk.CircuitLayer([zk.Gate(zk.GateType.Add, [0, 1]), zk.Gate(zk.GateType.Mul, [0, 1])])])
+    with pytest.raises(zk.ZkscError):
+        zk.GKRProtocol.prove(two_out, [[3, 2], [1, 2]])   # two output gates: w_0 would have 3 entries

@@ -16,6 +16,6 @@ from ._lib import (ZkscError, Context, Tables, lib, R_MOD, to_mont, from_mont, P
 from .api import (Multilinear, ComposedMultilinear, Sumcheck, SumcheckProof, ComposedSumcheck, ComposedSumcheckProof,
                   MultiComposedSumcheckProver, MultiComposedSumcheckVerifier, MultiComposedProof, SubClaim,
                   FiatShamirTranscript, SparseUnivariatePolynomial, default_context, set_default_context)
-from .gkr import Gate, GateType, CircuitLayer, Circuit, GKRProof, GKRProtocol
+from .gkr import Gate, GateType, CircuitLayer, Circuit, GKRProof, GKRProtocol, GKRInstance
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -55,6 +55,8 @@ def lib():
         "zksc_ctx_timing": (ctypes.c_int, [vp, ctypes.c_int]),
         "zksc_ctx_timing_read": (ctypes.c_int, [vp, ctypes.c_uint32, _u32p, ctypes.POINTER(ctypes.c_float), _u32p, _u32p, _u64p, _u64p]),
         "zksc_tables_reupload": (ctypes.c_int, [vp, ctypes.POINTER(_u64p), ctypes.c_int]),
+        "zksc_tables_reupload_begin": (ctypes.c_int, [vp, ctypes.POINTER(_u64p), ctypes.c_int]),
+        "zksc_tables_reupload_end": (ctypes.c_int, [vp]),
         "zksc_tables_upload_local": (ctypes.c_int, [vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, _u32p, ctypes.POINTER(_u64p), ctypes.POINTER(vp)]),
         "zksc_tables_read_local": (ctypes.c_int, [vp, _u64p]),
         "zksc_tables_upload": (ctypes.c_int, [vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, _u32p, ctypes.POINTER(_u64p), ctypes.POINTER(vp)]),
@@ -76,6 +78,8 @@ def lib():
         "zksc_proof_to_bytes": (ctypes.c_int, [ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, _u64p, _u32p, _u8p, ctypes.POINTER(ctypes.c_size_t)]),
         "zksc_verify_rounds": (ctypes.c_int, [ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, _u64p, _u64p, _u32p, _u8p, ctypes.c_size_t, _u64p, _u64p]),
         "zksc_evaluate": (ctypes.c_int, [vp, _u64p, _u64p]),
+        "zksc_gkr_total_rounds": (ctypes.c_uint64, [ctypes.c_uint32]),
+        "zksc_gkr_prove": (ctypes.c_int, [vp, ctypes.c_uint32, _u32p, _u8p, _u32p, _u32p, ctypes.POINTER(_u64p), _u64p, _u64p, _u64p, _u64p, _u64p, _u64p, _u32p, _u64p]),
         "zksc_ml_partial_evaluation": (ctypes.c_int, [vp, _u64p, ctypes.c_uint64, _u64p, ctypes.c_uint32, _u64p]),
         "zksc_ml_evaluation": (ctypes.c_int, [vp, _u64p, ctypes.c_uint64, _u64p, ctypes.c_uint32, _u64p]),
         "zksc_ml_outer": (ctypes.c_int, [vp, ctypes.c_int, _u64p, ctypes.c_uint64, _u64p, ctypes.c_uint64, _u64p]),
@@ -255,6 +259,21 @@ class Tables:
             raise ZkscError(-3, "tables do not match the shape this handle was created with")
         ptrs = (_u64p * len(arrs))(*[p64(a) for a in arrs])
         self.ctx.check(lib().zksc_tables_reupload(self._h, ptrs, 1 if local else 0))
+
+    def reupload_begin(self, tables, local=False):
+        """Start refilling this handle on the context's copy stream (zksc_tables_reupload_begin); the arrays must stay alive
+        and untouched until reupload_end()."""
+        arrs = [np.ascontiguousarray(t, dtype=np.uint64) for t in tables]
+        n = (1 << self.n_vars) // (self.ctx.n_ranks if local else 1)
+        if len(arrs) != self.n_proofs * self.n_tables or any(a.shape != (n, 4) for a in arrs):
+            raise ZkscError(-3, "tables do not match the shape this handle was created with")
+        self._refill = arrs
+        ptrs = (_u64p * len(arrs))(*[p64(a) for a in arrs])
+        self.ctx.check(lib().zksc_tables_reupload_begin(self._h, ptrs, 1 if local else 0))
+
+    def reupload_end(self):
+        self.ctx.check(lib().zksc_tables_reupload_end(self._h))
+        self._refill = None
 
     @staticmethod
     def upload_local(ctx, n_vars, degrees, local_tables, n_proofs=1):

@@ -10,11 +10,13 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <chrono>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "host_field.hpp"
@@ -80,6 +82,8 @@ struct zksc_ctx {
     int device = 0;
     int sms = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // zksc_tables_reupload_begin: host->device copies that overlap the compute stream
+    cudaEvent_t copy_event = nullptr;
     Fr* partials = nullptr;
     size_t partials_cap = 0;
     unsigned int* counters = nullptr;
@@ -158,6 +162,7 @@ struct zksc_tables {
     bool tail_posted = false;           // a challenge has been posted whose round result has not been collected
     unsigned int tail_left = 0;         // rounds whose result has not been collected
     unsigned int tail_cur = 0;          // sequence number of the round posted last
+    bool copy_pending = false;          // zksc_tables_reupload_begin without its _end: `orig` is being written by the copy stream
 };
 
 #define CK(call)                                                                                          \
@@ -278,6 +283,7 @@ extern "C" int zksc_ctx_destroy(zksc_ctx* ctx) {
     cudaFreeHost((void*)ctx->tail_res);
     cudaFree(ctx->tail_relay);
     cudaFree(ctx->tail_sums);
+    if (ctx->copy_stream) { cudaStreamDestroy(ctx->copy_stream); cudaEventDestroy(ctx->copy_event); }
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return ZKSC_OK;
@@ -529,8 +535,10 @@ static int tables_alloc(zksc_ctx* ctx, uint32_t n_vars, uint32_t B, uint32_t P, 
     return ZKSC_OK;
 }
 
+static int copy_finish(zksc_tables* t);
 extern "C" int zksc_tables_reset(zksc_tables* t) {
     if (!t) return ZKSC_ERR_STATE;
+    TRY(copy_finish(t));
     TRY(tail_stop(t));
     t->vars_left = t->n_vars;
     t->cur_n = t->n_local0;
@@ -546,6 +554,7 @@ extern "C" int zksc_tables_free(zksc_tables* t) {
     if (!t) return ZKSC_OK;
     zksc_ctx* ctx = t->ctx;
     cudaSetDevice(ctx->device);
+    copy_finish(t);
     tail_stop(t);
     dev_free(ctx, t->orig); dev_free(ctx, t->work); dev_free(ctx, t->tail);   // stream-ordered: after everything queued so far
     delete t;
@@ -572,9 +581,11 @@ static inline int grid_for(const zksc_ctx* ctx, unsigned long long n, int thread
 }
 
 // copy (and, on a sharded context, stride-pick) the caller's full tables into t->orig
+static int copy_finish(zksc_tables* t);
 static int upload_into(zksc_tables* t, const uint64_t* const* host_tables, bool local) {
     zksc_ctx* ctx = t->ctx;
     CK(cudaSetDevice(ctx->device));
+    TRY(copy_finish(t));
     TRY(quiesce(ctx));
     t->r0_valid = false;
     const uint64_t N = 1ull << t->n_vars;
@@ -628,6 +639,42 @@ extern "C" int zksc_tables_reupload(zksc_tables* t, const uint64_t* const* host_
     if (!host_tables) FAIL(ZKSC_ERR_SHAPE, "host_tables is NULL");
     zksc_tables_reset(t);
     return upload_into(t, host_tables, local != 0);
+}
+
+static int copy_finish(zksc_tables* t) { return t->copy_pending ? zksc_tables_reupload_end(t) : ZKSC_OK; }
+// Double buffering across proofs: refill handle B on a second stream while handle A is being proved on the compute stream.
+extern "C" int zksc_tables_reupload_begin(zksc_tables* t, const uint64_t* const* host_tables, int local) {
+    if (!t) return ZKSC_ERR_STATE;
+    zksc_ctx* ctx = t->ctx;
+    if (!host_tables) FAIL(ZKSC_ERR_SHAPE, "host_tables is NULL");
+    if (t->copy_pending) FAIL(ZKSC_ERR_STATE, "a refill of this handle is already in flight; call zksc_tables_reupload_end first");
+    TRY(zksc_tables_reset(t));      // stops this handle's resident kernel, if any
+    TRY(quiesce(ctx));              // single-threaded API: another handle's resident kernel can only be in its exit phase here
+    if (ctx->n_ranks > 1 && !local) return upload_into(t, host_tables, false);   // the strided shard pick needs the compute stream: synchronous
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->copy_stream) {
+        CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&ctx->copy_event, cudaEventDisableTiming));
+    }
+    t->r0_valid = false;
+    // everything queued on the compute stream so far (earlier uses of this handle, stream-ordered frees) comes first
+    CK(cudaEventRecord(ctx->copy_event, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_event, 0));
+    const uint64_t NL = t->n_local0;
+    const size_t n_tabs = (size_t)t->B * t->Dtot;
+    for (size_t i = 0; i < n_tabs; i++) CK(cudaMemcpyAsync(t->orig + i * NL, host_tables[i], NL * sizeof(Fr), cudaMemcpyHostToDevice, ctx->copy_stream));
+    t->copy_pending = true;
+    return ZKSC_OK;
+}
+
+extern "C" int zksc_tables_reupload_end(zksc_tables* t) {
+    if (!t) return ZKSC_ERR_STATE;
+    zksc_ctx* ctx = t->ctx;
+    if (!t->copy_pending) return ZKSC_OK;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->copy_stream));   // the host buffers are borrowed until here
+    t->copy_pending = false;
+    return ZKSC_OK;
 }
 
 extern "C" int zksc_tables_read_local(zksc_tables* t, uint64_t* out) {
@@ -1088,6 +1135,7 @@ static void finish_round(zksc_tables* t, uint64_t* out, bool skip1, bool full) {
 static int round_evals_impl(zksc_tables* t, uint64_t* out, uint32_t npts_cap) {
     zksc_ctx* ctx = t->ctx;
     CK(cudaSetDevice(ctx->device));
+    TRY(copy_finish(t));
     if (t->vars_left == 0) FAIL(ZKSC_ERR_STATE, "all variables are bound");
     if (t->r0_valid && t->vars_left == t->n_vars && !t->pending && npts_cap > ZKSC_MAX_DEGREE) {
         memcpy(out, t->r0_cache.data(), t->r0_cache.size() * sizeof(uint64_t));
@@ -1602,6 +1650,11 @@ extern "C" int zksc_ml_elementwise(zksc_ctx* ctx, int op, const uint64_t* a, con
     CK(cudaStreamSynchronize(ctx->stream));
     return ZKSC_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// GKR layer driver
+// ------------------------------------------------------------------------------------------------
+#include "gkr_driver.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // host helpers

@@ -138,6 +138,55 @@ def _fill_sparse(tables, index, entries):
     tables.fill_sparse(index, idx, vals)
 
 
+class GKRInstance:
+    """The arguments of zksc_gkr_prove in the form a Rust caller already holds them (`&Circuit`, `&Vec<Vec<F>>` with F in
+    Montgomery limbs): prepared once, so that `prove_raw` is nothing but the C call."""
+
+    def __init__(self, circuit, circuit_evaluation):
+        L = self.n_layers = len(circuit.layers)
+        if len(circuit_evaluation) != L + 1:
+            raise ZkscError(-3, "circuit_evaluation must hold one vector per layer plus the input")
+        gates = [g for l in circuit.layers for g in l.layer]
+        for g in gates:
+            if len(g.inputs) != 2 or min(g.inputs) < 0 or max(g.inputs) >= 1 << 32:
+                raise ZkscError(-3, "a gate takes two input labels")
+        self.n_gates = np.asarray([len(l.layer) for l in circuit.layers], dtype=np.uint32)
+        self.gtype = np.asarray([0 if g.gate_type == GateType.Add else 1 for g in gates], dtype=np.uint8)
+        self.in0 = np.asarray([g.inputs[0] for g in gates], dtype=np.uint32)
+        self.in1 = np.asarray([g.inputs[1] for g in gates], dtype=np.uint32)
+        self.vals = [to_mont([int(v) % R for v in layer]) for layer in circuit_evaluation]
+        self.vlen = np.asarray([len(layer) for layer in circuit_evaluation], dtype=np.uint64)
+        self.ptrs = (_lib._u64p * len(self.vals))(*[_lib.p64(v) for v in self.vals])
+        self.rounds = int(_lib.lib().zksc_gkr_total_rounds(L))
+
+    def prove_raw(self, ctx):
+        L, rounds = self.n_layers, self.rounds
+        out = dict(w0=np.zeros((2, 4), dtype=np.uint64), sums=np.zeros((L, 4), dtype=np.uint64), wb=np.zeros((L, 4), dtype=np.uint64),
+                   wc=np.zeros((L, 4), dtype=np.uint64), msgs=np.zeros((rounds, 6, 4), dtype=np.uint64), lens=np.zeros(rounds, dtype=np.uint32),
+                   chal=np.zeros((rounds, 4), dtype=np.uint64))
+        ctx.check(_lib.lib().zksc_gkr_prove(ctx._h, L, _lib.p32(self.n_gates), _lib.p8(self.gtype), _lib.p32(self.in0), _lib.p32(self.in1), self.ptrs,
+                                            _lib.p64(self.vlen), _lib.p64(out["w0"]), _lib.p64(out["sums"]), _lib.p64(out["wb"]), _lib.p64(out["wc"]),
+                                            _lib.p64(out["msgs"]), _lib.p32(out["lens"]), _lib.p64(out["chal"])))
+        return out
+
+    def parse(self, raw):
+        msgs, lens = raw["msgs"], raw["lens"]
+        proofs, off = [], 0
+        sums_i, all_ints = from_mont(raw["sums"]), from_mont(msgs.reshape(-1, 4))
+        for li in range(self.n_layers):
+            n = 2 * (li + 1)
+            rps = []
+            for r in range(off, off + n):
+                m = int(lens[r])
+                v = all_ints[r * 6:r * 6 + 2 * m]
+                rps.append(SparseUnivariatePolynomial([(v[2 * i], v[2 * i + 1]) for i in range(m)]))
+            proofs.append(MultiComposedProof(rps, sums_i[li], (msgs[off:off + n], lens[off:off + n])))
+            off += n
+        proof = GKRProof(proofs, from_mont(raw["wb"]), from_mont(raw["wc"]), Multilinear(raw["w0"]))
+        proof.challenges = from_mont(raw["chal"])
+        return proof
+
+
 class GKRProtocol:               # gkr/src/protocol.rs:17-195
     @staticmethod
     def _layer(ctx, circuit, layer_index, w_ints, points_and_scales, claimed_sum, transcript, proofs, wb_s, wc_s):
@@ -177,6 +226,14 @@ class GKRProtocol:               # gkr/src/protocol.rs:17-195
 
     @staticmethod
     def prove(circuit, circuit_evaluation, ctx=None):   # :21-113
+        """The whole proof in ONE C call (zksc_gkr_prove): layer loop, table construction, layer sumchecks, W(b*), W(c*) and
+        the outer transcript all inside libzksc.so.  `prove_layerwise` below is the same protocol driven layer by layer
+        from Python over the finer-grained C entry points; both must give the same bytes (tests/test_gpu_gkr.py)."""
+        inst = GKRInstance(circuit, circuit_evaluation)
+        return inst.parse(inst.prove_raw(ctx or default_context()))
+
+    @staticmethod
+    def prove_layerwise(circuit, circuit_evaluation, ctx=None):   # :21-113, one C call per table operation
         ctx = ctx or default_context()
         transcript = FiatShamirTranscript()
         proofs, wb_s, wc_s = [], [], []
