@@ -320,9 +320,46 @@ def run_b200(args):
             ms2 = float(tms.item())
         assert np.array_equal(m2, msgs) and np.array_equal(c2, chal), "e2e proof differs from the resident-table proof"
         d2h = int(m2.nbytes + c2.nbytes + l2.nbytes + 32 * proofs_local)
-        e2e = {"value": evals_per_step * args.steps / (ms2 * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h,
-               "ms_per_step": round(ms2 / args.steps, 4), "host_wall_ms_per_step": round(wall_ms / args.steps, 4),
-               "api": "Tables.reupload(host tables) + Tables.poly_sum() + Tables.prove() = zksc_tables_reupload + zksc_poly_sum + zksc_prove (C ABI, host buffers)"}
+        sequential = {"value": evals_per_step * args.steps / (ms2 * 1e-3), "ms_per_step": round(ms2 / args.steps, 4),
+                      "host_wall_ms_per_step": round(wall_ms / args.steps, 4),
+                      "api": "zksc_tables_reupload + zksc_poly_sum + zksc_prove, one after the other"}
+        # The same K steps double-buffered: the refill of handle B (copy stream) overlaps poly_sum + prove of handle A (compute
+        # stream).  Every step still uploads its own inputs and reads its own proof back inside the timed region.
+        pair = [tables, zk.Tables.alloc(ctx, n, wl["degs"], n_proofs=proofs_local)]
+
+        def e2e_pipelined(steps):
+            pair[0].reupload_begin(views, local=sharded)
+            for k in range(steps):
+                cur = pair[k % 2]
+                cur.reupload_end()
+                if k + 1 < steps:
+                    pair[(k + 1) % 2].reupload_begin(views, local=sharded)
+                res = cur.prove(proto, cur.poly_sum())
+            return res
+
+        e2e_pipelined(2)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record(stream)
+        t0 = time.perf_counter()
+        m3, l3, c3 = e2e_pipelined(args.steps)
+        g1.record(stream)
+        barrier()
+        wall3 = (time.perf_counter() - t0) * 1e3
+        ms3 = max(g0.elapsed_time(g1), 0.0)
+        if dist is not None:
+            tms = torch.tensor([ms3], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            ms3 = float(tms.item())
+        assert np.array_equal(m3, msgs) and np.array_equal(c3, chal), "pipelined e2e proof differs from the resident-table proof"
+        pair[1].free()
+        e2e = {"value": evals_per_step * args.steps / (ms3 * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h,
+               "ms_per_step": round(ms3 / args.steps, 4), "host_wall_ms_per_step": round(wall3 / args.steps, 4),
+               "api": "double-buffered: zksc_tables_reupload_begin(next handle, pinned host tables) on the copy stream || zksc_poly_sum + zksc_prove(current "
+                      "handle) on the compute stream, zksc_tables_reupload_end before a handle is proved (C ABI, host buffers); every step uploads its own tables",
+               "sequential": sequential}
+        if sequential["value"] > e2e["value"]:      # report whichever schedule is faster as the headline, keep both
+            e2e = dict(sequential, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=d2h, pipelined={"value": e2e["value"], "ms_per_step": e2e["ms_per_step"]})
 
     if rank != 0:
         if dist is not None:

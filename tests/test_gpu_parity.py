@@ -396,3 +396,40 @@ def test_full_size_prove_verify_roundtrip(ctx, n, degs, proto):
         zk.lib().zksc_synth_entry(12345, 0, 0, _lib.p64(out))
     finally:
         t.free()
+
+
+def test_double_buffered_refill(ctx):
+    """zksc_tables_reupload_begin / _end: refill one handle on the copy stream while another is being proved; the refilled
+    handle then proves to the same bytes as a freshly uploaded one, also when _end is left to the next call on the handle."""
+    n, degs = 14, [2, 1]
+    seeds = [11, 12, 13]
+    host = []
+    for sd in seeds:
+        t = zk.Tables.synth(ctx, n, degs, sd)
+        host.append(t.read_local().reshape(sum(degs), 1 << n, 4).copy())
+        t.free()
+    want = []
+    for h in host:
+        t = zk.Tables.upload(ctx, n, degs, [h[i] for i in range(h.shape[0])])
+        s = t.poly_sum()
+        want.append((s.copy(), [a.copy() for a in t.prove(zk.PROTO_MULTI_PARTIAL, s)]))
+        t.free()
+    pair = [zk.Tables.alloc(ctx, n, degs), zk.Tables.alloc(ctx, n, degs)]
+    pair[0].reupload_begin([host[0][i] for i in range(3)])
+    for k in range(3):
+        cur = pair[k % 2]
+        if k != 1:
+            cur.reupload_end()            # k == 1: left pending on purpose, poly_sum must finish the refill itself
+        if k + 1 < 3:
+            pair[(k + 1) % 2].reupload_begin([host[k + 1][i] for i in range(3)])
+        s = cur.poly_sum()
+        got = cur.prove(zk.PROTO_MULTI_PARTIAL, s)
+        assert np.array_equal(s, want[k][0])
+        for a, b in zip(got, want[k][1]):
+            assert np.array_equal(a, b)
+    with pytest.raises(zk.ZkscError):
+        pair[0].reupload_begin([host[0][i] for i in range(3)])
+        pair[0].reupload_begin([host[0][i] for i in range(3)])   # second begin without end: STATE error
+    pair[0].reupload_end()
+    for t in pair:
+        t.free()

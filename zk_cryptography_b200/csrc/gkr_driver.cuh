@@ -137,6 +137,7 @@ extern "C" int zksc_gkr_prove(zksc_ctx* ctx, uint32_t n_layers, const uint32_t* 
     for (uint32_t li = 0; li < n_layers; li++) {
         const uint32_t k = li + 1, n = 2 * k;
         const uint64_t nw = 1ull << k;
+        const auto p0 = std::chrono::steady_clock::now();
         // wiring entries: layer one add(n_r, b, c) unscaled (utils.rs:23-24); later alpha add(r_b,.,.) + beta add(r_c,.,.) (protocol.rs:86-88)
         idx_add.clear(); idx_mul.clear(); val_add.clear(); val_mul.clear();
         {
@@ -205,7 +206,9 @@ extern "C" int zksc_gkr_prove(zksc_ctx* ctx, uint32_t n_layers, const uint32_t* 
         uint64_t* msgs = round_msgs + round_off * stride * 4;
         uint32_t* lens = round_len + round_off;
         uint64_t* chal = challenges + round_off * 4;
+        const auto p1 = std::chrono::steady_clock::now();
         TRY(zksc_prove(t, ZKSC_PROTO_MULTI_PARTIAL, sum_m, msgs, lens, chal));
+        const auto p2 = std::chrono::steady_clock::now();
         size_t blen = 0;
         TRY(zksc_proof_to_bytes(ZKSC_PROTO_MULTI_PARTIAL, n, stride, msgs, lens, nullptr, &blen));
         bytes.resize(blen);
@@ -226,6 +229,11 @@ extern "C" int zksc_gkr_prove(zksc_ctx* ctx, uint32_t n_layers, const uint32_t* 
         claimed = host::add(host::mul(alpha, load_h(ev)), host::mul(beta, load_h(ev + 4)));      // :113
         round_off += n;
         gate_off += n_gates[li];
+        if (ctx->profile) {
+            auto us = [](auto a, auto b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+            fprintf(stderr, "[zksc profile] gkr layer %2u: tables %7.1f us  prove %7.1f us  absorb + W(b), W(c) %7.1f us\n", li, us(p0, p1), us(p1, p2),
+                    us(p2, std::chrono::steady_clock::now()));
+        }
     }
     return ZKSC_OK;
 }
