@@ -49,3 +49,11 @@ extern "C" void emu_fr_fold_tab(const uint32_t* a, const uint32_t* b, const uint
     FoldTab W; memcpy(W.w, w64, 256);
     Fr x, y; memcpy(x.l, a, 32); memcpy(y.l, b, 32); Fr z = fr_fold_tab(x, y, W); memcpy(o, z.l, 32);
 }
+extern "C" {
+BIN(emu_fr_add_semi, fr_add_semi)
+BIN(emu_fr_add_lazy, fr_add_lazy)
+}
+extern "C" void emu_fr_fold_tab_semi(const uint32_t* a, const uint32_t* b, const uint32_t* w64, uint32_t* o) {
+    FoldTab W; memcpy(W.w, w64, 256);
+    Fr x, y; memcpy(x.l, a, 32); memcpy(y.l, b, 32); Fr z = fr_fold_tab<true>(x, y, W); memcpy(o, z.l, 32);
+}

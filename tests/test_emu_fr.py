@@ -126,6 +126,18 @@ def test_fixed_multiplicand_fold(emu):
         a, b = rnd(rng, R), rnd(rng, R)
         emu.emu_fr_fold_tab(arr(a, 8), arr(b, 8), W, o8)
         assert val(o8) == (a + r * (b - a)) % R
+        emu.emu_fr_fold_tab_semi(arr(a, 8), arr(b, 8), W, o8)        # fr_fold_tab<true>: single conditional subtraction
+        assert val(o8) == (a + r * (b - a)) % R
+        # the bound fr_add_semi relies on: mul_fixed_rows stays under r + 2^227
+        assert v < R + 2**227
+    # folds of extreme operands through both tails
+    for r in (0, 1, R - 1, R // 2):
+        W = fold_table(r)
+        for a in (0, 1, R - 1):
+            for b in (0, 1, R - 1, R - 2):
+                for fn in (emu.emu_fr_fold_tab, emu.emu_fr_fold_tab_semi):
+                    fn(arr(a, 8), arr(b, 8), W, o8)
+                    assert val(o8) == (a + r * (b - a)) % R
     # extreme table / operand limbs
     for r in (0, 1, R - 1):
         W = fold_table(r)
@@ -133,3 +145,22 @@ def test_fixed_multiplicand_fold(emu):
             emu.emu_mul_fixed(arr(d, 8), W, o8)
             v = val(o8)
             assert v % R == r * d % R and v < 2 * R
+
+
+def test_semi_reduced_add_and_lazy_add(emu):
+    """fr_add_semi (the tail of fr_fold_tab): a < r, v < r + 2^227 -> canonical (a + v) mod r, including the out-of-line branch for
+    v >= r that random folds practically never reach; fr_add_lazy: plain 256-bit sum, no reduction."""
+    rng = random.Random(77)
+    o8 = (ctypes.c_uint32 * 8)()
+    edge_a = [0, 1, R - 1, R - 2, R // 2]
+    edge_v = [0, 1, R - 1, R, R + 1, R + 2**226, R + 2**227 - 1, 2**227]
+    cases = [(a, v) for a in edge_a for v in edge_v]
+    cases += [(rnd(rng, R), rnd(rng, R + 2**227)) for _ in range(300)]
+    cases += [(R - 1 - rnd(rng, 2**40), R + rnd(rng, 2**227)) for _ in range(300)]      # a + v >= 2r: needs the second subtraction
+    for a, v in cases:
+        emu.emu_fr_add_semi(arr(a, 8), arr(v, 8), o8)
+        assert val(o8) == (a + v) % R
+    for _ in range(200):
+        a, b = rnd(rng, R), rnd(rng, R)
+        emu.emu_fr_add_lazy(arr(a, 8), arr(b, 8), o8)
+        assert val(o8) == a + b

@@ -135,6 +135,14 @@ ZKSC_DEV void cond_sub_r(uint32_t (&x)[8]) {
     for (int i = 0; i < 8; i++) x[i] = borrow ? x[i] : t[i];
 }
 
+// the same, out of line: for branches that are (almost) never taken, so that the hot path carries a compare and a branch only
+// (by value: the element travels in registers, nothing is parked in local memory on the hot path)
+#ifndef ZKSC_HOST_EMU
+static __device__ __noinline__ Fr cond_sub_r_rare(Fr x) { cond_sub_r(x.l); return x; }
+#else
+static inline Fr cond_sub_r_rare(Fr x) { cond_sub_r(x.l); return x; }
+#endif
+
 ZKSC_DEV Fr fr_add(const Fr& a, const Fr& b) {  // a,b < r  ->  (a+b) mod r
     Fr s;
     s.l[0] = ptx::add_cc(a.l[0], b.l[0]);
@@ -142,6 +150,17 @@ ZKSC_DEV Fr fr_add(const Fr& a, const Fr& b) {  // a,b < r  ->  (a+b) mod r
     for (int i = 1; i < 7; i++) s.l[i] = ptx::addc_cc(a.l[i], b.l[i]);
     s.l[7] = ptx::addc(a.l[7], b.l[7]);  // a+b < 2r < 2^256: no carry out
     cond_sub_r(s.l);
+    return s;
+}
+
+// a, b < r  ->  a + b < 2r < 2^256, NOT reduced: for operands of mul_wide (any value < 2^256) and for ONE operand of
+// fr_mul (a * b < r * 2^256 holds with the other operand < r)
+ZKSC_DEV Fr fr_add_lazy(const Fr& a, const Fr& b) {
+    Fr s;
+    s.l[0] = ptx::add_cc(a.l[0], b.l[0]);
+#pragma unroll
+    for (int i = 1; i < 7; i++) s.l[i] = ptx::addc_cc(a.l[i], b.l[i]);
+    s.l[7] = ptx::addc(a.l[7], b.l[7]);
     return s;
 }
 
@@ -565,7 +584,27 @@ ZKSC_DEV void mul_fixed_rows(uint32_t (&res)[8], const uint32_t (&d)[8], const F
     for (int i = 2; i < 7; i++) res[i] = addc_cc(res[i], 0u);
     res[7] = addc(res[7], 0u);
 }
+// a < p, v < p + 2^227 (what mul_fixed_rows returns: v < p + 2^226 + p 2^-32)  ->  canonical (a + v) mod p.
+// a + v < 2p + 2^227 < 2^256, so there is no carry out; ONE conditional subtraction leaves s < p + 2^227, and s >= p is then
+// possible only for s in [p, p + 2^227) -- never for practical purposes, but exactness is unconditional: s >= p implies that
+// its top limb is >= p's top limb, and that (almost never taken) branch finishes the job out of line.  17 ALU instructions
+// fewer per fold than cond_sub_r(v) followed by fr_add(a, v).
+ZKSC_DEV Fr fr_add_semi(const Fr& a, const Fr& v) {
+    using namespace ptx;
+    Fr s;
+    s.l[0] = add_cc(a.l[0], v.l[0]);
+#pragma unroll
+    for (int i = 1; i < 7; i++) s.l[i] = addc_cc(a.l[i], v.l[i]);
+    s.l[7] = addc(a.l[7], v.l[7]);
+    cond_sub_r(s.l);
+    if (__builtin_expect(s.l[7] >= ZKSC_P7, 0)) s = cond_sub_r_rare(s);
+    return s;
+}
 // fold through the table: a + r * (b - a), canonical.  a, b < p.
+// SEMI: finish with fr_add_semi (one conditional subtraction + a never-taken branch) instead of cond_sub_r + fr_add.  17 ALU
+// instructions fewer, but measured faster only where ptxas has registers to spare: round_kernel<2, FOLD, SKIP1, 1> 332.5 -> 316.7 us
+// (c2 round 1), while the d = 3 and the 64-proof instantiations lose 1.5-2.7 % to it (profiles/r01_variants_v5.txt).
+template <bool SEMI = false>
 ZKSC_DEV Fr fr_fold_tab(const Fr& a, const Fr& b, const FoldTab& W) {
     using namespace ptx;
     uint32_t d[8];                                     // b - a + p  in (0, 2p): no conditional
@@ -577,8 +616,12 @@ ZKSC_DEV Fr fr_fold_tab(const Fr& a, const Fr& b, const FoldTab& W) {
     d[4] = addc_cc(d[4], ZKSC_P4); d[5] = addc_cc(d[5], ZKSC_P5); d[6] = addc_cc(d[6], ZKSC_P6); d[7] = addc(d[7], ZKSC_P7);
     Fr v;
     mul_fixed_rows(v.l, d, W);
-    cond_sub_r(v.l);
-    return fr_add(a, v);
+    if constexpr (SEMI) {
+        return fr_add_semi(a, v);
+    } else {
+        cond_sub_r(v.l);
+        return fr_add(a, v);
+    }
 }
 
 }  // namespace zksc

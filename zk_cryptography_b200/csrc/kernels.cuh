@@ -266,8 +266,14 @@ ZKSC_DEV void accumulate_points(Acc<Lazy<D>::NL> (&acc)[NP], Fr (&a)[D], Fr (&b)
         for (int k = 0; k < D; k++) delta[k] = fr_sub(b[k], a[k]);
 #pragma unroll
         for (int p = 2; p <= D; p++) {
+            // The last point's values are not walked any further, so they need not be canonical: b + delta < 2r goes straight
+            // into the product -- every factor but the first only ever meets a canonical partner in fr_mul (x * y < r 2^256), the
+            // last one enters mul_wide (any 256-bit value); with D = 2 both factors enter mul_wide.
 #pragma unroll
-            for (int k = 0; k < D; k++) b[k] = fr_add(b[k], delta[k]);
+            for (int k = 0; k < D; k++) {
+                const bool lazy = (p == D) && (k >= 1 || D == 2);
+                b[k] = lazy ? fr_add_lazy(b[k], delta[k]) : fr_add(b[k], delta[k]);
+            }
             if (p < npts) accumulate_product<D>(acc[SKIP1 ? p - 1 : p], b);
         }
     }
@@ -281,9 +287,24 @@ ZKSC_DEV void accumulate_points(Acc<Lazy<D>::NL> (&acc)[NP], Fr (&a)[D], Fr (&b)
 #ifndef ZKSC_FOLD_LOADALL
 #define ZKSC_FOLD_LOADALL 1
 #endif
+#ifndef ZKSC_PREFETCH
+#define ZKSC_PREFETCH 0
+#endif
+ZKSC_DEV void prefetch_line(const void* p) {
+#if ZKSC_PREFETCH == 2
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#endif
+}
 template <int D, bool FOLD, bool SKIP1, int NB>
 __global__ void __launch_bounds__(kThreads, ZKSC_ROUND_MINB) round_kernel(const __grid_constant__ RoundArgsT<NB> args) {
     constexpr int NL = Lazy<D>::NL;
+#ifdef ZKSC_FOLD_TWO_CONDSUB
+    constexpr bool kSemi = false;
+#else
+    constexpr bool kSemi = (D == 2 && NB == 1);   // see fr_fold_tab
+#endif
     constexpr int NP = SKIP1 ? D : D + 1;   // accumulators
     const int proof = (NB == 1) ? 0 : blockIdx.y;
     const Fr* in = args.in + (size_t)proof * args.in_proof_stride;
@@ -301,18 +322,32 @@ __global__ void __launch_bounds__(kThreads, ZKSC_ROUND_MINB) round_kernel(const 
     const unsigned long long stride = (unsigned long long)gridDim.x * kThreads;
     for (unsigned long long x = (unsigned long long)blockIdx.x * kThreads + threadIdx.x; x < half; x += stride) {
         Fr a[D], b[D];
+#if ZKSC_PREFETCH
+        // the next iteration's 4 D entries on their way from HBM while this one computes (no registers held: a prefetch has
+        // no destination); 1 = into L2, 2 = into L1
+        if constexpr (FOLD) {
+            const unsigned long long xn = x + stride;
+            if (xn < half) {
+#pragma unroll
+                for (int k = 0; k < D; k++) {
+                    const Fr* t = in + (size_t)k * args.in_tab_stride + xn;
+                    prefetch_line(t); prefetch_line(t + half); prefetch_line(t + 2 * half); prefetch_line(t + 3 * half);
+                }
+            }
+        }
+#endif
         if constexpr (FOLD && D == 2 && ZKSC_FOLD_LOADALL) {
             // all eight entries of the pair in flight at once: one exposed memory latency per iteration instead of two
             const Fr* t0 = in;
             const Fr* t1 = in + args.in_tab_stride;
             Fr p0 = ld256(t0 + x), p1 = ld256(t0 + x + 2 * half), q0 = ld256(t0 + x + half), q1 = ld256(t0 + x + 3 * half);
             Fr r0 = ld256(t1 + x), r1 = ld256(t1 + x + 2 * half), s0 = ld256(t1 + x + half), s1 = ld256(t1 + x + 3 * half);
-            a[0] = fr_fold_tab(p0, p1, args.tab[proof]);
-            b[0] = fr_fold_tab(q0, q1, args.tab[proof]);
+            a[0] = fr_fold_tab<kSemi>(p0, p1, args.tab[proof]);
+            b[0] = fr_fold_tab<kSemi>(q0, q1, args.tab[proof]);
             st256(out + x, a[0]);
             st256(out + x + half, b[0]);
-            a[1] = fr_fold_tab(r0, r1, args.tab[proof]);
-            b[1] = fr_fold_tab(s0, s1, args.tab[proof]);
+            a[1] = fr_fold_tab<kSemi>(r0, r1, args.tab[proof]);
+            b[1] = fr_fold_tab<kSemi>(s0, s1, args.tab[proof]);
             st256(out + args.out_tab_stride + x, a[1]);
             st256(out + args.out_tab_stride + x + half, b[1]);
         } else
@@ -324,8 +359,8 @@ __global__ void __launch_bounds__(kThreads, ZKSC_ROUND_MINB) round_kernel(const 
                 Fr p0 = ld256(t + x), p1 = ld256(t + x + 2 * half);
                 Fr q0 = ld256(t + x + half), q1 = ld256(t + x + 3 * half);
                 if constexpr (D <= 5) {
-                    a[k] = fr_fold_tab(p0, p1, args.tab[proof]);
-                    b[k] = fr_fold_tab(q0, q1, args.tab[proof]);
+                    a[k] = fr_fold_tab<kSemi>(p0, p1, args.tab[proof]);
+                    b[k] = fr_fold_tab<kSemi>(q0, q1, args.tab[proof]);
                 } else {
                     a[k] = fr_fold_d<D>(p0, p1, r);
                     b[k] = fr_fold_d<D>(q0, q1, r);
