@@ -12,7 +12,7 @@ from oracle import pymodel as pm
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EXE = os.path.join(ROOT, "build", "reference_cases")
-R = pm.R if hasattr(pm, "R") else 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+R = pm.R_MOD
 
 
 def be(vals):

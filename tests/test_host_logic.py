@@ -1,6 +1,7 @@
 """Host-side logic of the product library (no GPU): field helpers, SHA-256 transcript, sparse polynomial,
 transcript replay / verify_partial -- all through the C ABI, checked against the Python model."""
 import hashlib
+import os
 import random
 
 import numpy as np
@@ -11,6 +12,7 @@ from zk_cryptography_b200 import _lib
 from oracle import pymodel as pm
 
 R = pm.R_MOD
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.fixture(scope="module", autouse=True)
@@ -140,3 +142,25 @@ def test_no_cpu_fallback():
     with pytest.raises(zk.ZkscError) as e:
         zk.Context(0)
     assert e.value.code == -1
+
+
+def test_sha256_scalar_and_shani_paths_agree():
+    """The library hashes with the x86 SHA extensions when the CPU has them (host_field.hpp block_shani) and with the portable
+    compression otherwise (ZKSC_NO_SHANI=1 forces it; read once per process, hence the subprocess): both must equal hashlib."""
+    import subprocess, sys
+    code = (
+        "import sys, hashlib, ctypes, numpy as np\n"
+        "sys.path.insert(0, %r)\n"
+        "import zk_cryptography_b200 as zk\n"
+        "L = zk.lib()\n"
+        "for n in list(range(0, 200)) + [255, 256, 1000, 4097]:\n"
+        "    msg = bytes((7 * i + n) & 255 for i in range(n))\n"
+        "    t = L.zksc_transcript_new(); L.zksc_transcript_commit(t, msg, n)\n"
+        "    out = np.zeros(32, dtype=np.uint8); L.zksc_transcript_challenge(t, out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)))\n"
+        "    assert out.tobytes() == hashlib.sha256(msg).digest(), n\n"
+        "    L.zksc_transcript_free(t)\n"
+        "print('ok')\n") % ROOT
+    for env_extra in ({}, {"ZKSC_NO_SHANI": "1"}):
+        env = dict(os.environ, **env_extra)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+        assert r.returncode == 0 and r.stdout.strip() == "ok", r.stderr[-1500:]

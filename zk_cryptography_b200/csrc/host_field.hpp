@@ -13,9 +13,16 @@
 // 4 x u64 little-endian limbs, Montgomery form, R = 2^256.
 #pragma once
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>
+#define ZKSC_HAVE_SHANI 1
+#else
+#define ZKSC_HAVE_SHANI 0
+#endif
 
 namespace zksc {
 namespace host {
@@ -124,13 +131,19 @@ inline FrH from_u64(uint64_t x) {
 // Shift table of a challenge for the device's fixed-multiplicand fold (fr.cuh mul_fixed_rows):
 // w[i] = r * 2^(32 (i + 2)) mod p as 8 little-endian 32-bit limbs, r = the plain value of r_mont.
 inline void fold_table(const FrH& r_mont, uint32_t w[8][8]) {
+    // 2^(32 e) mod p as RAW limbs, e = 2..9 (constants, built once): mul(r R, X) = r X
+    static const std::vector<FrH> X = [] {
+        std::vector<FrH> x(8, kZero);
+        for (int i = 0; i < 8; i++) {
+            const int e = i + 2;
+            if (e < 8) x[i].v[e / 2] = 1ull << (32 * (e % 2));
+            else if (e == 8) x[i] = kOne;              // 2^256 mod p
+            else x[i] = from_u64(1ull << 32);          // 2^288 mod p
+        }
+        return x;
+    }();
     for (int i = 0; i < 8; i++) {
-        const int e = i + 2;                       // 2^(32 e) mod p as RAW limbs: mul(r R, X) = r X
-        FrH x = kZero;
-        if (e < 8) x.v[e / 2] = 1ull << (32 * (e % 2));
-        else if (e == 8) x = kOne;                 // 2^256 mod p
-        else x = from_u64(1ull << 32);             // 2^288 mod p
-        FrH v = mul(r_mont, x);
+        FrH v = mul(r_mont, X[i]);
         memcpy(w[i], v.v, 32);
     }
 }
@@ -211,14 +224,64 @@ class Sha256 {
 
    private:
     static uint32_t rotr(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
-    void block(const uint8_t* p) {
-        static const uint32_t K[64] = {
+    static const uint32_t* round_constants() {
+        alignas(16) static const uint32_t K[64] = {
             0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5, 0xd807aa98, 0x12835b01, 0x243185be,
             0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174, 0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc, 0x2de92c6f, 0x4a7484aa,
             0x5cb0a9dc, 0x76f988da, 0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147, 0x06ca6351, 0x14292967, 0x27b70a85,
             0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85, 0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3,
             0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070, 0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f,
             0x682e6ff3, 0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
+        return K;
+    }
+#if ZKSC_HAVE_SHANI
+    // One compression with the x86 SHA extensions (sha256rnds2 / sha256msg1 / sha256msg2): the per-round host step of every proof
+    // hashes 3-5 blocks, and with 64 batched proofs per launch (c5) the scalar compression was a visible share of the step.
+    // Message schedule per group g of four rounds: W[g] = msg2(msg1(W[g-4], W[g-3]) + alignr(W[g-1], W[g-2], 4), W[g-1]).
+    __attribute__((target("sha,sse4.1,ssse3"))) static void block_shani(uint32_t h[8], const uint8_t* p) {
+        const uint32_t* K = round_constants();
+        const __m128i bswap = _mm_set_epi64x(0x0c0d0e0f08090a0bULL, 0x0405060700010203ULL);
+        __m128i tmp = _mm_loadu_si128((const __m128i*)&h[0]);       // DCBA
+        __m128i st1 = _mm_loadu_si128((const __m128i*)&h[4]);       // HGFE
+        tmp = _mm_shuffle_epi32(tmp, 0xB1);                         // CDAB
+        st1 = _mm_shuffle_epi32(st1, 0x1B);                         // EFGH
+        __m128i st0 = _mm_alignr_epi8(tmp, st1, 8);                 // ABEF
+        st1 = _mm_blend_epi16(st1, tmp, 0xF0);                      // CDGH
+        const __m128i save0 = st0, save1 = st1;
+        __m128i w[16];
+        for (int g = 0; g < 16; g++) {
+            if (g < 4) {
+                w[g] = _mm_shuffle_epi8(_mm_loadu_si128((const __m128i*)(p + 16 * g)), bswap);
+            } else {
+                __m128i x = _mm_sha256msg1_epu32(w[g - 4], w[g - 3]);
+                x = _mm_add_epi32(x, _mm_alignr_epi8(w[g - 1], w[g - 2], 4));
+                w[g] = _mm_sha256msg2_epu32(x, w[g - 1]);
+            }
+            __m128i m = _mm_add_epi32(w[g], _mm_load_si128((const __m128i*)&K[4 * g]));
+            st1 = _mm_sha256rnds2_epu32(st1, st0, m);
+            m = _mm_shuffle_epi32(m, 0x0E);
+            st0 = _mm_sha256rnds2_epu32(st0, st1, m);
+        }
+        st0 = _mm_add_epi32(st0, save0);
+        st1 = _mm_add_epi32(st1, save1);
+        tmp = _mm_shuffle_epi32(st0, 0x1B);                         // FEBA
+        st1 = _mm_shuffle_epi32(st1, 0xB1);                         // DCHG
+        st0 = _mm_blend_epi16(tmp, st1, 0xF0);                      // DCBA
+        st1 = _mm_alignr_epi8(st1, tmp, 8);                         // HGFE
+        _mm_storeu_si128((__m128i*)&h[0], st0);
+        _mm_storeu_si128((__m128i*)&h[4], st1);
+    }
+    static bool have_shani() {
+        static const bool ok = __builtin_cpu_supports("sha") && __builtin_cpu_supports("sse4.1") && __builtin_cpu_supports("ssse3") && !getenv("ZKSC_NO_SHANI");
+        return ok;
+    }
+#endif
+    void block(const uint8_t* p) {
+#if ZKSC_HAVE_SHANI
+        if (have_shani()) { block_shani(h_, p); return; }
+#endif
+        const uint32_t* K = round_constants();
+        
         uint32_t w[64];
         for (int i = 0; i < 16; i++) w[i] = ((uint32_t)p[4 * i] << 24) | ((uint32_t)p[4 * i + 1] << 16) | ((uint32_t)p[4 * i + 2] << 8) | p[4 * i + 3];
         for (int i = 16; i < 64; i++) {
@@ -313,8 +376,7 @@ struct SparseUnivariatePolynomial {
     // ~10 us each -- too slow for a per-round host step).
     static std::vector<FrH> dense_interpolate_evals(const std::vector<FrH>& ys) {
         const size_t n = ys.size();
-        static std::vector<std::vector<FrH>> inv_denoms(64);
-        if (n >= inv_denoms.size()) {
+        if (n >= 64) {
             std::vector<FrH> xs;
             for (size_t i = 0; i < n; i++) xs.push_back(from_u64(i));
             SparseUnivariatePolynomial sp = interpolation(xs, ys);
@@ -322,34 +384,46 @@ struct SparseUnivariatePolynomial {
             for (const auto& m : sp.monomial) { uint64_t e[4]; to_canonical(m.pow, e); dense[e[0]] = m.coeff; }
             return dense;
         }
-        std::vector<FrH>& inv = inv_denoms[n];
-        if (inv.size() != n) {
-            inv.assign(n, kOne);
+        // basis[n][i] = the coefficients of the i-th Lagrange basis polynomial over x = 0..n-1: depends on n only, built once per
+        // thread (one Fermat inversion per basis polynomial, ~10 us each -- far too slow for a per-round host step); a round then
+        // costs n^2 multiplications.
+        static thread_local std::vector<std::vector<std::vector<FrH>>> basis(64);
+        std::vector<std::vector<FrH>>& B = basis[n];
+        if (B.size() != n) {
+            B.assign(n, std::vector<FrH>());
+            std::vector<FrH> l, nl;
             for (size_t i = 0; i < n; i++) {
                 FrH denom = kOne;
-                for (size_t j = 0; j < n; j++)
-                    if (j != i) denom = mul(denom, sub(from_u64(i), from_u64(j)));
-                inv[i] = inverse(denom);
+                l.assign(1, kOne);
+                for (size_t j = 0; j < n; j++) {
+                    if (j == i) continue;
+                    const FrH xj = from_u64(j);
+                    denom = mul(denom, sub(from_u64(i), xj));
+                    nl.assign(l.size() + 1, kZero);
+                    for (size_t k = 0; k < l.size(); k++) {
+                        nl[k] = sub(nl[k], mul(l[k], xj));
+                        nl[k + 1] = add(nl[k + 1], l[k]);
+                    }
+                    l.swap(nl);
+                }
+                const FrH inv = inverse(denom);
+                B[i].resize(n);
+                for (size_t k = 0; k < n; k++) B[i][k] = mul(l[k], inv);
             }
         }
         std::vector<FrH> result(n, kZero);
-        std::vector<FrH> l, nl;
-        for (size_t i = 0; i < n; i++) {
-            l.assign(1, kOne);
-            for (size_t j = 0; j < n; j++) {
-                if (j == i) continue;
-                const FrH xj = from_u64(j);
-                nl.assign(l.size() + 1, kZero);
-                for (size_t k = 0; k < l.size(); k++) {
-                    nl[k] = sub(nl[k], mul(l[k], xj));
-                    nl[k + 1] = add(nl[k + 1], l[k]);
-                }
-                l.swap(nl);
-            }
-            FrH scale = mul(inv[i], ys[i]);
-            for (size_t k = 0; k < l.size(); k++) result[k] = add(result[k], mul(l[k], scale));
-        }
+        for (size_t i = 0; i < n; i++)
+            for (size_t k = 0; k < n; k++) result[k] = add(result[k], mul(B[i][k], ys[i]));
         return result;
+    }
+    // F::from(k) for the small exponents of a round polynomial, Montgomery form, built once
+    static const FrH& small_mont(size_t k) {
+        static const std::vector<FrH> tab = [] {
+            std::vector<FrH> t;
+            for (uint64_t i = 0; i < 64; i++) t.push_back(from_u64(i));
+            return t;
+        }();
+        return tab[k];
     }
     // evaluations at x = 0..d  (sumcheck/src/utils.rs:29-35 convert_round_poly_to_uni_poly_format) ->
     // SparseUnivariatePolynomial::interpolation (:40-63): monomials with a zero coefficient are dropped (:52-60)
@@ -357,7 +431,7 @@ struct SparseUnivariatePolynomial {
         std::vector<FrH> dense = dense_interpolate_evals(ys);
         SparseUnivariatePolynomial p;
         for (size_t k = 0; k < dense.size(); k++)
-            if (dense[k] != kZero) p.monomial.push_back({dense[k], from_u64(k)});
+            if (dense[k] != kZero) p.monomial.push_back({dense[k], k < 64 ? small_mont(k) : from_u64(k)});
         return p;
     }
     // value at `point` of the interpolant through (i, ys[i]): Horner on the dense coefficients
