@@ -349,13 +349,17 @@ def test_tail_kernel_off_gives_identical_proofs():
 
 
 def test_batched_independent_proofs(ctx):
-    """config 5 shape at small size: many independent proofs in one launch per round (incl. > 64 proofs)"""
+    """config 5 shape at small size: many independent proofs in one launch per round (incl. > 64 proofs; from 16 proofs on the
+    per-proof transcript work of a round runs on the library's host worker pool -- every proof is compared with the oracle)"""
     n, degs = 8, [2]
     for B in (3, 70):
         t = zk.Tables.synth(ctx, n, degs, 500, n_proofs=B)
         sums = t.poly_sum()
         msgs, lens, chal = t.prove(zk.PROTO_MULTI_PARTIAL, sums)
-        for b in (0, 1, B - 1):
+        t.reset()
+        again = t.prove(zk.PROTO_MULTI_PARTIAL, sums)
+        assert np.array_equal(again[0], msgs) and np.array_equal(again[2], chal)
+        for b in range(B):
             tabs = np.concatenate([cref.synth_table(500 + b, k, n) for k in range(2)])
             s = cref.poly_sum(n, degs, tabs)
             assert zk.from_mont(sums[b]) == s

@@ -11,7 +11,12 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
 #include <cstdio>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include <cstdlib>
 #include <chrono>
 #include <cstring>
@@ -78,10 +83,85 @@ static NcclApi g_nccl;
 #endif
 
 // ------------------------------------------------------------------------------------------------
+// Host worker pool for the per-proof half of a round when many independent proofs share a launch (c5: 64 transcripts per
+// round).  Each proof's step -- interpolate, serialise, SHA-256, challenge, fold table, claim -- touches only that proof's
+// state, so the proofs of a round are spread over a few threads.  Workers spin only while a zksc_prove call is in
+// progress (a round's host step is ~100 us and must not pay a wake-up) and sleep on a condition variable otherwise.
+class HostPool {
+   public:
+    explicit HostPool(int workers) {
+        for (int i = 0; i < workers; i++) th_.emplace_back([this] { worker(); });
+    }
+    ~HostPool() {
+        { std::lock_guard<std::mutex> lk(m_); quit_ = true; active_.store(false); }
+        cv_.notify_all();
+        for (auto& t : th_) t.join();
+    }
+    void begin() { { std::lock_guard<std::mutex> lk(m_); active_.store(true, std::memory_order_release); } cv_.notify_all(); }
+    void end() { active_.store(false, std::memory_order_release); }
+    // fn(i) for i in [0, n); returns when all are done.  Only between begin() and end().
+    void parallel_for(uint32_t n, const std::function<void(uint32_t)>& fn) {
+        fn_ = &fn; n_ = n;
+        next_.store(0, std::memory_order_relaxed);
+        pending_.store((int)th_.size(), std::memory_order_relaxed);
+        gen_.fetch_add(1, std::memory_order_release);
+        run();
+        while (pending_.load(std::memory_order_acquire) != 0) cpu_relax();
+    }
+    size_t workers() const { return th_.size(); }
+
+   private:
+    static void cpu_relax() {
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+    void run() {
+        for (;;) {
+            const uint32_t i = next_.fetch_add(1, std::memory_order_relaxed);
+            if (i >= n_) break;
+            (*fn_)(i);
+        }
+    }
+    void worker() {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [this] { return quit_ || active_.load(std::memory_order_acquire); });
+                if (quit_) return;
+            }
+            while (active_.load(std::memory_order_acquire)) {
+                const uint64_t g = gen_.load(std::memory_order_acquire);
+                if (g != seen) {
+                    seen = g;
+                    run();
+                    pending_.fetch_sub(1, std::memory_order_acq_rel);
+                } else {
+                    cpu_relax();
+                }
+            }
+        }
+    }
+    std::vector<std::thread> th_;
+    std::mutex m_;
+    std::condition_variable cv_;
+    bool quit_ = false;
+    std::atomic<bool> active_{false};
+    std::atomic<uint64_t> gen_{0};
+    std::atomic<int> pending_{0};
+    std::atomic<uint32_t> next_{0};
+    const std::function<void(uint32_t)>* fn_ = nullptr;
+    uint32_t n_ = 0;
+};
+constexpr uint32_t kPoolMinProofs = 16;   // fewer proofs per round than this: the calling thread does them itself
+
 struct zksc_ctx {
     int device = 0;
     int sms = 0;
     cudaStream_t stream = nullptr;
+    HostPool* pool = nullptr;             // created on first use by a batched zksc_prove (ZKSC_HOST_THREADS, default up to 8 threads)
+    bool pool_active = false;
     cudaStream_t copy_stream = nullptr;   // zksc_tables_reupload_begin: host->device copies that overlap the compute stream
     cudaEvent_t copy_event = nullptr;
     Fr* partials = nullptr;
@@ -283,6 +363,7 @@ extern "C" int zksc_ctx_destroy(zksc_ctx* ctx) {
     cudaFreeHost((void*)ctx->tail_res);
     cudaFree(ctx->tail_relay);
     cudaFree(ctx->tail_sums);
+    delete ctx->pool;
     if (ctx->copy_stream) { cudaStreamDestroy(ctx->copy_stream); cudaEventDestroy(ctx->copy_event); }
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -1260,6 +1341,12 @@ extern "C" int zksc_round_evals(zksc_tables* t, uint64_t* out) {
     return round_evals_impl(t, out, ZKSC_MAX_DEGREE + 1);
 }
 
+// fn(b) for every proof of the handle: on the worker pool while a batched zksc_prove is running, inline otherwise
+static void for_each_proof(zksc_ctx* ctx, uint32_t B, const std::function<void(uint32_t)>& fn) {
+    if (ctx->pool && ctx->pool_active && B >= kPoolMinProofs) ctx->pool->parallel_for(B, fn);
+    else for (uint32_t b = 0; b < B; b++) fn(b);
+}
+
 extern "C" int zksc_bind(zksc_tables* t, const uint64_t* challenges) {
     if (!t || !challenges) return ZKSC_ERR_STATE;
     zksc_ctx* ctx = t->ctx;
@@ -1274,25 +1361,24 @@ extern "C" int zksc_bind(zksc_tables* t, const uint64_t* challenges) {
     if (ctx->n_ranks > 1 && t->where != 2 && t->cur_n == 1) TRY(gather_tail(t));
     t->pending_chal.resize(t->B);
     t->pending_tab.resize(t->B);
-    for (uint32_t b = 0; b < t->B; b++) {
+    // per proof: the fold table of its challenge and, for the next round, the claim = this round's polynomial of every product
+    // at the challenge
+    const bool claims = t->last_evals_valid;
+    if (claims) t->claim.resize((size_t)t->B * t->P);
+    for_each_proof(ctx, t->B, [&](uint32_t b) {
         memcpy(t->pending_chal[b].l, challenges + 4 * b, 32);
         host::fold_table(load_h(challenges + 4 * b), t->pending_tab[b].w);
-    }
+        if (!claims) return;
+        std::vector<FrH> ys;
+        for (uint32_t p = 0; p < t->P; p++) {
+            ys.clear();
+            for (uint32_t i = 0; i <= t->deg[p]; i++) ys.push_back(load_h(&t->last_evals[((size_t)b * t->E + t->eoff[p] + i) * 4]));
+            t->claim[(size_t)b * t->P + p] = host::SparseUnivariatePolynomial::evaluate_evals_at(ys, load_h(challenges + 4 * b));
+        }
+    });
     t->pending = true;
     t->vars_left--;
-    // claim for the next round: this round's polynomial of every product at the challenge
-    t->claim_valid = false;
-    if (t->last_evals_valid) {
-        t->claim.resize((size_t)t->B * t->P);
-        std::vector<FrH> ys;
-        for (uint32_t b = 0; b < t->B; b++)
-            for (uint32_t p = 0; p < t->P; p++) {
-                ys.clear();
-                for (uint32_t i = 0; i <= t->deg[p]; i++) ys.push_back(load_h(&t->last_evals[((size_t)b * t->E + t->eoff[p] + i) * 4]));
-                t->claim[(size_t)b * t->P + p] = host::SparseUnivariatePolynomial::evaluate_evals_at(ys, load_h(challenges + 4 * b));
-            }
-        t->claim_valid = true;
-    }
+    t->claim_valid = claims;
     t->last_evals_valid = false;
     if (t->tail_running) tail_post(t, t->tail_cur + 1);     // the resident kernel folds with it and evaluates the next round
     return ZKSC_OK;
@@ -1414,16 +1500,27 @@ extern "C" int zksc_prove(zksc_tables* t, int protocol, const uint64_t* sums, ui
         for (uint32_t b = 0; b < B; b++) tr[b].commit_field(load_h(sums + 4 * b));  // :70 / sumcheck.rs:34-35
 
     std::vector<uint64_t> ev((size_t)B * t->E * 4), chal((size_t)B * 4);
-    std::vector<uint8_t> bytes;
     memset(round_msgs, 0, (size_t)B * n * stride * 32);
+    // many independent proofs per round: their transcripts go to a few host threads (they spin only during this call)
+    if (B >= kPoolMinProofs && !ctx->pool) {
+        const char* e = getenv("ZKSC_HOST_THREADS");
+        int want = e ? atoi(e) : (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
+        if (want > 1) ctx->pool = new HostPool(want - 1);
+    }
+    struct PoolSession {
+        zksc_ctx* c;
+        explicit PoolSession(zksc_ctx* ctx, bool on) : c(on ? ctx : nullptr) { if (c) { c->pool->begin(); c->pool_active = true; } }
+        ~PoolSession() { if (c) { c->pool_active = false; c->pool->end(); } }
+    } pool_session(ctx, ctx->pool != nullptr && B >= kPoolMinProofs);
     for (uint32_t round = 0; round < n; round++) {
         const auto p0 = std::chrono::steady_clock::now();
         TRY(round_evals_impl(t, ev.data(), ZKSC_MAX_DEGREE + 1));
         const auto p1 = std::chrono::steady_clock::now();
-        for (uint32_t b = 0; b < B; b++) {
+        for_each_proof(ctx, B, [&](uint32_t b) {
             uint64_t* msg = round_msgs + ((size_t)b * n + round) * stride * 4;
             uint32_t* len = round_len + (size_t)b * n + round;
             const uint64_t* e = &ev[(size_t)b * t->E * 4];
+            static thread_local std::vector<uint8_t> bytes;
             bytes.clear();
             if (protocol == ZKSC_PROTO_SUMCHECK || protocol == ZKSC_PROTO_COMPOSED) {
                 const uint32_t cnt = t->deg[0] + 1;
@@ -1452,7 +1549,7 @@ extern "C" int zksc_prove(zksc_tables* t, int protocol, const uint64_t* sums, ui
             FrH r = tr[b].evaluate_challenge_into_field();            // :99
             store_h(&chal[4 * b], r);
             store_h(challenges + ((size_t)b * n + round) * 4, r);
-        }
+        });
         const auto p2 = std::chrono::steady_clock::now();
         TRY(zksc_bind(t, chal.data()));                               // :103-105 (deferred, fused)
         if (ctx->profile) {
