@@ -32,7 +32,7 @@ namespace zksc {
 
 constexpr int kTailThreads = 256;
 constexpr int kTailWarps = kTailThreads / 32;
-constexpr unsigned long long kTailWorkPerCta = 460000;  // start when limb products per round <= this x CTAs of a group (see tail_eligible)
+constexpr unsigned long long kTailWorkPerCta = 920000;  // start when limb products per round <= this x CTAs of a group (see tail_eligible)
 constexpr int kTailMaxCtas = 128;                   // CTAs per (proof, product) group
 constexpr int kTailMaxDegree = 5;                   // table fold (fr.cuh mul_fixed_rows) degrees
 constexpr int kTailMaxProducts = 8;                 // == ZKSC_MAX_PRODUCTS

@@ -183,6 +183,7 @@ struct zksc_ctx {
     int rank = 0, n_ranks = 1;
     // persistent tail kernel (tail_kernel.cuh): mailbox + result units in pinned, device-mapped host memory
     bool tail_enabled = true;            // ZKSC_NO_TAIL=1: every round is its own launch
+    unsigned long long tail_work = kTailWorkPerCta;   // start threshold of the resident kernel (ZKSC_TAIL_WORK overrides, experiments)
     volatile uint64_t* tail_mail = nullptr;    // [tail_proofs_cap][kMailUnits]   {word | seq << 32}
     volatile uint64_t* tail_res = nullptr;     // [tail_units_cap]                {limb | seq << 32}
     unsigned long long* tail_mail_dev = nullptr;
@@ -335,6 +336,7 @@ extern "C" int zksc_ctx_create(int device, zksc_ctx** out) {
     { const char* e_ = getenv("ZKSC_NO_MAPPED"); ctx->mapped_results = !(e_ && e_[0] == '1'); }
     { const char* e_ = getenv("ZKSC_PROFILE"); ctx->profile = (e_ && e_[0] == '1'); }
     { const char* e_ = getenv("ZKSC_NO_TAIL"); ctx->tail_enabled = !(e_ && e_[0] == '1'); }
+    { const char* e_ = getenv("ZKSC_TAIL_WORK"); if (e_ && atoll(e_) > 0) ctx->tail_work = (unsigned long long)atoll(e_); }
     { const char* e_ = getenv("ZKSC_NO_STAGED"); ctx->staged = !(e_ && e_[0] == '1'); }
     { const char* e_ = getenv("ZKSC_STAGED_FOLD"); ctx->staged_fold = (e_ && e_[0] == '1'); }
     *out = ctx;
@@ -1021,7 +1023,7 @@ static bool tail_eligible(const zksc_tables* t, unsigned long long half, bool sh
         // 32x32 limb products per pair of a fused fold + evaluate round: the resident kernel keeps one
         // CTA of 8 warps per SM, so it only wins while a round is latency-bound
         const unsigned long long per_point = d == 1 ? 0 : (d <= 3 ? (d - 2) * 120 + 64 : (d - 1) * 120);
-        if (half * (2 * d * 76 + d * per_point) > kTailWorkPerCta * c) return false;
+        if (half * (2 * d * 76 + d * per_point) > ctx->tail_work * c) return false;
     }
     return true;
 }
