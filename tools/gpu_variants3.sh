@@ -16,5 +16,5 @@ PY
   done
 }
 run plain ZKSC_X=0
-for n in ${VARIANTS:-A B C}; do run $n ZKSC_LIB=$PWD/build/libzksc_$n.so; done
+for n in ${VARIANTS}; do run $n ZKSC_LIB=$PWD/build/libzksc_$n.so; done
 run plain_again ZKSC_X=0
