@@ -89,8 +89,26 @@ ZKSC_DEV Fr fr_fold_d(const Fr& a, const Fr& b, const Fr& r) {
 }
 
 // acc += prod_k f[k]
-template <int D>
-ZKSC_DEV void accumulate_product(Acc<Lazy<D>::NL>& acc, const Fr (&f)[D]) {
+// A per-thread accumulator that lives in shared memory, limb-major ([limb][thread]: conflict-free 32-bit accesses): the
+// registers it frees matter where an instantiation sits at the register cap (experiment: ZKSC_SMEM_ACC).
+template <int NL>
+struct SmemAcc {
+    uint32_t* p;   // &s_acc[slot][0][threadIdx.x]
+};
+template <int NL, int NX>
+ZKSC_DEV void acc_add(SmemAcc<NL>& a, const uint32_t (&x)[NX]) {
+    static_assert(NX <= NL, "");
+    uint32_t v = a.p[0];
+    a.p[0] = ptx::add_cc(v, x[0]);
+#pragma unroll
+    for (int i = 1; i < NL; i++) {
+        const uint32_t xi = (i < NX) ? x[i] : 0u;
+        v = a.p[i * kThreads];
+        a.p[i * kThreads] = (i < NL - 1) ? ptx::addc_cc(v, xi) : ptx::addc(v, xi);
+    }
+}
+template <int D, class A>
+ZKSC_DEV void accumulate_product(A& acc, const Fr (&f)[D]) {
     if constexpr (D == 1) {
         acc_add<9, 8>(acc, f[0].l);
     } else if constexpr (Lazy<D>::wide) {
@@ -254,8 +272,8 @@ ZKSC_DEV void reduce_and_publish(Acc<NL> (&acc)[NP], const RoundBase& args, int 
 }
 
 // acc[] += the products at every evaluation point of one pair (a = even half, b = odd half of each factor)
-template <int D, bool SKIP1, int NP>
-ZKSC_DEV void accumulate_points(Acc<Lazy<D>::NL> (&acc)[NP], Fr (&a)[D], Fr (&b)[D], int npts) {
+template <int D, bool SKIP1, class A, int NP>
+ZKSC_DEV void accumulate_points(A (&acc)[NP], Fr (&a)[D], Fr (&b)[D], int npts) {
     // evaluation points 0 and 1 are the two halves themselves
     accumulate_product<D>(acc[0], a);
     if (!SKIP1 && npts > 1) accumulate_product<D>(acc[1], b);
@@ -300,8 +318,10 @@ ZKSC_DEV void prefetch_line(const void* p) {
 template <int D, bool FOLD, bool SKIP1, int NB>
 __global__ void __launch_bounds__(kThreads, ZKSC_ROUND_MINB) round_kernel(const __grid_constant__ RoundArgsT<NB> args) {
     constexpr int NL = Lazy<D>::NL;
-#ifdef ZKSC_FOLD_TWO_CONDSUB
+#if defined(ZKSC_FOLD_TWO_CONDSUB)
     constexpr bool kSemi = false;
+#elif defined(ZKSC_SEMI_ALL_NB1)
+    constexpr bool kSemi = (NB == 1);             // experiment
 #else
     constexpr bool kSemi = (D == 2 && NB == 1);   // see fr_fold_tab
 #endif
@@ -315,9 +335,25 @@ __global__ void __launch_bounds__(kThreads, ZKSC_ROUND_MINB) round_kernel(const 
     Fr r;
     if constexpr (FOLD && D > 5) r = args.chal[proof];
 
+#ifndef ZKSC_SMEM_ACC
+#define ZKSC_SMEM_ACC 3
+#endif
+    // Accumulators in shared memory for the fold rounds of degree ZKSC_SMEM_ACC (0 = none).  The d = 3 fold keeps 3 x 17 limbs of
+    // sums next to 6 folded entries and sits at the 128-register cap with 144 bytes of spills; with the sums in shared memory
+    // (27-35 KB per CTA) it needs 120 registers, spills nothing and runs 1.2 % faster (profiles/r01_variants_v5.txt).
+    constexpr bool kSmemAcc = (ZKSC_SMEM_ACC != 0) && (D == ZKSC_SMEM_ACC) && FOLD && Lazy<D>::wide;
+    __shared__ uint32_t s_acc[kSmemAcc ? NP * NL * kThreads : 1];
+    SmemAcc<NL> sacc[NP];
     Acc<NL> acc[NP];
 #pragma unroll
-    for (int p = 0; p < NP; p++) acc_zero(acc[p]);
+    for (int p = 0; p < NP; p++) {
+        acc_zero(acc[p]);
+        if constexpr (kSmemAcc) {
+            sacc[p].p = s_acc + (size_t)p * NL * kThreads + threadIdx.x;
+#pragma unroll
+            for (int i = 0; i < NL; i++) sacc[p].p[i * kThreads] = 0u;
+        }
+    }
 
     const unsigned long long stride = (unsigned long long)gridDim.x * kThreads;
     for (unsigned long long x = (unsigned long long)blockIdx.x * kThreads + threadIdx.x; x < half; x += stride) {
@@ -373,7 +409,14 @@ __global__ void __launch_bounds__(kThreads, ZKSC_ROUND_MINB) round_kernel(const 
                 b[k] = ld256_stream(t + x + half);
             }
         }
-        accumulate_points<D, SKIP1>(acc, a, b, npts);
+        if constexpr (kSmemAcc) accumulate_points<D, SKIP1>(sacc, a, b, npts);
+        else accumulate_points<D, SKIP1>(acc, a, b, npts);
+    }
+    if constexpr (kSmemAcc) {
+#pragma unroll
+        for (int p = 0; p < NP; p++)
+#pragma unroll
+            for (int i = 0; i < NL; i++) acc[p].l[i] = sacc[p].p[i * kThreads];
     }
     reduce_and_publish<NL, NP, SKIP1>(acc, args, npts);
 }
