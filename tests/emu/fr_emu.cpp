@@ -57,3 +57,6 @@ extern "C" void emu_fr_fold_tab_semi(const uint32_t* a, const uint32_t* b, const
     FoldTab W; memcpy(W.w, w64, 256);
     Fr x, y; memcpy(x.l, a, 32); memcpy(y.l, b, 32); Fr z = fr_fold_tab<true>(x, y, W); memcpy(o, z.l, 32);
 }
+extern "C" {
+BIN(emu_fr_mul_lazy, fr_mul_lazy)
+}

@@ -164,3 +164,14 @@ def test_semi_reduced_add_and_lazy_add(emu):
         a, b = rnd(rng, R), rnd(rng, R)
         emu.emu_fr_add_lazy(arr(a, 8), arr(b, 8), o8)
         assert val(o8) == a + b
+
+
+def test_lazy_montgomery_product(emu):
+    """fr_mul_lazy: no final conditional subtraction; for a < r, b < 2r (a lazy sum) the result is < 2r and congruent to a b / R"""
+    rng = random.Random(91)
+    o8 = (ctypes.c_uint32 * 8)()
+    cases = [(rnd(rng, R), rnd(rng, 2 * R)) for _ in range(2000)] + [(R - 1, 2 * R - 1), (R - 1, 2 * R - 2), (0, 2 * R - 1), (1, 1), (R - 1, R - 1)]
+    for a, b in cases:
+        emu.emu_fr_mul_lazy(arr(a, 8), arr(b, 8), o8)
+        v = val(o8)
+        assert v < 2 * R and v % R == a * b * RINV % R

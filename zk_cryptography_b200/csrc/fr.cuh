@@ -399,6 +399,16 @@ ZKSC_DEV Fr fr_mul(const Fr& a, const Fr& b) {
     return o;
 }
 
+// Montgomery product WITHOUT the final conditional subtraction: a * b < r * 2^256  ->  a value < 2r congruent to a b / R.
+// For a product that goes straight into mul_wide (which takes any 256-bit operand): 17 ALU instructions saved.
+ZKSC_DEV Fr fr_mul_lazy(const Fr& a, const Fr& b) {
+    Fr o;
+    uint32_t top;
+    mont_mul_rows(o.l, top, a, b);   // < 2r < 2^256: top == 0
+    (void)top;
+    return o;
+}
+
 // Montgomery reduction of a 16-limb T (any T < 2^512): (T + M r) / 2^256, 8 limbs + top.
 // Only used on the once-per-block slow path and in tests.
 ZKSC_DEV void redc_rows(uint32_t (&T)[16], uint32_t& top) {

@@ -114,7 +114,7 @@ ZKSC_DEV void accumulate_product(A& acc, const Fr (&f)[D]) {
     } else if constexpr (Lazy<D>::wide) {
         Fr g = f[0];
 #pragma unroll
-        for (int k = 1; k < D - 1; k++) g = fr_mul(g, f[k]);
+        for (int k = 1; k < D - 1; k++) g = (k == D - 2) ? fr_mul_lazy(g, f[k]) : fr_mul(g, f[k]);   // the one that feeds mul_wide may stay < 2r
         uint32_t T[16];
         mul_wide(T, g, f[D - 1]);      // last multiplication stays unreduced
         acc_add<17, 16>(acc, T);
