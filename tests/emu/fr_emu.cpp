@@ -60,3 +60,6 @@ extern "C" void emu_fr_fold_tab_semi(const uint32_t* a, const uint32_t* b, const
 extern "C" {
 BIN(emu_fr_mul_lazy, fr_mul_lazy)
 }
+extern "C" {
+BIN(emu_fr_sub_lazy, fr_sub_lazy)
+}

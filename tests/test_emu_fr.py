@@ -175,3 +175,12 @@ def test_lazy_montgomery_product(emu):
         emu.emu_fr_mul_lazy(arr(a, 8), arr(b, 8), o8)
         v = val(o8)
         assert v < 2 * R and v % R == a * b * RINV % R
+
+
+def test_lazy_difference(emu):
+    """fr_sub_lazy: a - b + r as a plain 256-bit value in (0, 2r), no borrow test"""
+    rng = random.Random(92)
+    o8 = (ctypes.c_uint32 * 8)()
+    for a, b in [(rnd(rng, R), rnd(rng, R)) for _ in range(500)] + [(0, R - 1), (R - 1, 0), (0, 0), (R - 1, R - 1), (1, 2)]:
+        emu.emu_fr_sub_lazy(arr(a, 8), arr(b, 8), o8)
+        assert val(o8) == a - b + R

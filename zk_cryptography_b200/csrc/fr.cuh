@@ -164,6 +164,19 @@ ZKSC_DEV Fr fr_add_lazy(const Fr& a, const Fr& b) {
     return s;
 }
 
+// a, b < r  ->  a - b + r in (0, 2r), NOT reduced (no borrow test): for operands of mul_wide
+ZKSC_DEV Fr fr_sub_lazy(const Fr& a, const Fr& b) {
+    Fr d;
+    d.l[0] = ptx::sub_cc(a.l[0], b.l[0]);
+#pragma unroll
+    for (int i = 1; i < 7; i++) d.l[i] = ptx::subc_cc(a.l[i], b.l[i]);
+    d.l[7] = ptx::subc(a.l[7], b.l[7]);
+    d.l[0] = ptx::add_cc(d.l[0], ZKSC_P0); d.l[1] = ptx::addc_cc(d.l[1], ZKSC_P1); d.l[2] = ptx::addc_cc(d.l[2], ZKSC_P2);
+    d.l[3] = ptx::addc_cc(d.l[3], ZKSC_P3); d.l[4] = ptx::addc_cc(d.l[4], ZKSC_P4); d.l[5] = ptx::addc_cc(d.l[5], ZKSC_P5);
+    d.l[6] = ptx::addc_cc(d.l[6], ZKSC_P6); d.l[7] = ptx::addc(d.l[7], ZKSC_P7);
+    return d;
+}
+
 ZKSC_DEV Fr fr_sub(const Fr& a, const Fr& b) {  // a,b < r  ->  (a-b) mod r
     Fr d;
     d.l[0] = ptx::sub_cc(a.l[0], b.l[0]);

@@ -277,7 +277,18 @@ ZKSC_DEV void accumulate_points(A (&acc)[NP], Fr (&a)[D], Fr (&b)[D], int npts) 
     // evaluation points 0 and 1 are the two halves themselves
     accumulate_product<D>(acc[0], a);
     if (!SKIP1 && npts > 1) accumulate_product<D>(acc[1], b);
-    if (D >= 2 && npts > 2) {
+    if constexpr (D == 2) {
+        // Degree 2: the third value is the LEADING COEFFICIENT  h(inf) = sum (b_0 - a_0)(b_1 - a_1)  instead of h(2): both factors
+        // enter mul_wide, so the differences may stay unreduced (b - a + r in (0, 2r): 16 ALU instructions per factor instead of
+        // 33 for a canonical difference plus the walk to t = 2).  The host turns it into h(2) = 2 h(1) - h(0) + 2 h(inf)
+        // (zksc.cu finish_round) -- exact field arithmetic, identical canonical value.
+        if (npts > 2) {
+            Fr dl[2];
+#pragma unroll
+            for (int k = 0; k < 2; k++) dl[k] = fr_sub_lazy(b[k], a[k]);
+            accumulate_product<D>(acc[SKIP1 ? 1 : 2], dl);
+        }
+    } else if (D >= 2 && npts > 2) {
         // f_k(t) = a_k + t (b_k - a_k): walk t = 2..D by repeated addition of the difference
         Fr delta[D];
 #pragma unroll

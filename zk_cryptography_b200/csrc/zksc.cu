@@ -1198,7 +1198,7 @@ static int launch_round(const zksc_tables* t, const RoundBase& base, int D, int 
 }
 
 // after the device part of a round: fill in point 1 from the claim, remember the evaluations for the next claim
-static void finish_round(zksc_tables* t, uint64_t* out, bool skip1, bool full) {
+static void finish_round(zksc_tables* t, uint64_t* out, bool skip1, bool full, uint32_t npts_cap) {
     if (skip1) {
         // h_p(1) = claim_p - h_p(0)   (what the verifier checks; exact in the field)
         for (uint32_t b = 0; b < t->B; b++)
@@ -1207,6 +1207,18 @@ static void finish_round(zksc_tables* t, uint64_t* out, bool skip1, bool full) {
                 store_h(e + 4, host::sub(t->claim[(size_t)b * t->P + p], load_h(e)));
             }
     }
+    // degree-2 products: the kernels deliver the leading coefficient h(inf) in the slot of point 2 (kernels.cuh
+    // accumulate_points); h(2) = 2 h(1) - h(0) + 2 h(inf)
+    if (npts_cap > 2)
+        for (uint32_t p = 0; p < t->P; p++) {
+            if (t->deg[p] != 2) continue;
+            for (uint32_t b = 0; b < t->B; b++) {
+                uint64_t* e = out + ((size_t)b * t->E + t->eoff[p]) * 4;
+                const FrH h0 = load_h(e), h1 = load_h(e + 4), hi = load_h(e + 8);
+                const FrH s = host::add(host::sub(h1, h0), hi);       // h(1) - h(0) + h(inf)
+                store_h(e + 8, host::add(host::add(s, s), h0));       // 2 (h(1) - h(0) + h(inf)) + h(0)
+            }
+        }
     t->claim_valid = false;
     if (full) {
         t->last_evals.assign(out, out + (size_t)t->B * t->E * 4);
@@ -1256,7 +1268,7 @@ static int round_evals_impl(zksc_tables* t, uint64_t* out, uint32_t npts_cap) {
         if (rc == ZKSC_OK) {
             ctx->prof_wait = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - w0).count();
             tail_round_done(t);
-            finish_round(t, out, true, true);
+            finish_round(t, out, true, true, npts_cap);
             return ZKSC_OK;
         }
         if (rc != kTailExpired) return rc;
@@ -1334,7 +1346,7 @@ static int round_evals_impl(zksc_tables* t, uint64_t* out, uint32_t npts_cap) {
         }
 #endif
     }
-    finish_round(t, out, skip1, full);
+    finish_round(t, out, skip1, full, npts_cap);
     return ZKSC_OK;
 }
 
