@@ -48,7 +48,14 @@ def set_threads(n):
 
 
 def max_threads():
-    return lib().zkref_max_threads()
+    """All host threads this process may use: the CPUs of its affinity mask, NOT omp_get_max_threads() -- torchrun exports
+    OMP_NUM_THREADS=1 to every rank, which would silently turn the all-cores CPU baseline into a single-thread one."""
+    import os
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    return max(1, n) if lib().zkref_max_threads() >= 1 else 1
 
 
 def synth_table(seed, table, n_vars):
