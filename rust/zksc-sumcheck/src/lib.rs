@@ -157,3 +157,42 @@ pub fn evaluation(m: &Multilinear<Fr>, points: &[Fr]) -> Fr {
     check(ctx, rc);
     fr(&out)
 }
+
+/// GKRProtocol::prove   gkr/src/protocol.rs:21-113 -- the whole proof in one library call (`zksc_gkr_prove`): layer tables
+/// built in HBM, layer sumchecks on the GPU, W(b*), W(c*) on the GPU, outer Fiat-Shamir transcript on the host.
+/// `gates`: per circuit layer (output layer first) the gates as (is_mul, in0, in1)   circuit/src/{gate,circuit}.rs
+/// `circuit_evaluation`: `Circuit::evaluation`'s result (circuit.rs:32-55), [0] = output ... [n] = input.
+/// Returns (sumcheck_proofs, wb_s, wc_s, w_0) -- the fields of the reference's `GKRProof` (protocol.rs:10-15).
+pub fn gkr_prove(gates: &[Vec<(bool, usize, usize)>], circuit_evaluation: &Vec<Vec<Fr>>) -> (Vec<ComposedSumcheckProof>, Vec<Fr>, Vec<Fr>, Vec<Fr>) {
+    let l = gates.len();
+    assert_eq!(circuit_evaluation.len(), l + 1, "circuit_evaluation must hold one vector per layer plus the input");
+    let n_gates: Vec<u32> = gates.iter().map(|g| g.len() as u32).collect();
+    let gate_type: Vec<u8> = gates.iter().flatten().map(|g| g.0 as u8).collect();
+    let in0: Vec<u32> = gates.iter().flatten().map(|g| g.1 as u32).collect();
+    let in1: Vec<u32> = gates.iter().flatten().map(|g| g.2 as u32).collect();
+    let vals: Vec<*const u64> = circuit_evaluation.iter().map(|v| limbs(v)).collect();
+    let vlen: Vec<u64> = circuit_evaluation.iter().map(|v| v.len() as u64).collect();
+    let rounds = unsafe { zksc_gkr_total_rounds(l as u32) } as usize;
+    let (mut w0, mut sums, mut wb, mut wc) = (vec![0u64; 8], vec![0u64; 4 * l], vec![0u64; 4 * l], vec![0u64; 4 * l]);
+    let (mut msgs, mut lens, mut chal) = (vec![0u64; rounds * 6 * 4], vec![0u32; rounds], vec![0u64; rounds * 4]);
+    let ctx = context();
+    let rc = unsafe {
+        zksc_gkr_prove(ctx, l as u32, n_gates.as_ptr(), gate_type.as_ptr(), in0.as_ptr(), in1.as_ptr(), vals.as_ptr(), vlen.as_ptr(), w0.as_mut_ptr(),
+                       sums.as_mut_ptr(), wb.as_mut_ptr(), wc.as_mut_ptr(), msgs.as_mut_ptr(), lens.as_mut_ptr(), chal.as_mut_ptr())
+    };
+    check(ctx, rc);
+    let mut proofs = Vec::with_capacity(l);
+    let mut off = 0usize;
+    for li in 0..l {
+        let n = 2 * (li + 1);
+        let round_polys = (off..off + n).map(|r| SparseUnivariatePolynomial {
+            monomial: (0..lens[r] as usize).map(|m| {
+                let o = (r * 6 + 2 * m) * 4;
+                UnivariateMonomial { coeff: fr(&msgs[o..o + 4]), pow: fr(&msgs[o + 4..o + 8]) }
+            }).collect(),
+        }).collect();
+        proofs.push(ComposedSumcheckProof { round_polys, sum: fr(&sums[4 * li..4 * li + 4]) });
+        off += n;
+    }
+    (proofs, wb.chunks(4).map(fr).collect(), wc.chunks(4).map(fr).collect(), w0.chunks(4).map(fr).collect())
+}

@@ -381,7 +381,8 @@ def test_verifier_oracle_check_on_device(ctx):
 
 
 # ---- full-size, size-independent properties (BASELINE.json configs 1 and 2) -------------------------
-@pytest.mark.parametrize("n,degs,proto", [(20, [1], zk.PROTO_SUMCHECK), (24, [2], zk.PROTO_MULTI_PARTIAL), (22, [3], zk.PROTO_MULTI_PARTIAL)])
+@pytest.mark.parametrize("n,degs,proto", [(20, [1], zk.PROTO_SUMCHECK), (24, [2], zk.PROTO_MULTI_PARTIAL), (22, [3], zk.PROTO_MULTI_PARTIAL),
+                                          (26, [3], zk.PROTO_MULTI_PARTIAL), (20, [2, 2], zk.PROTO_MULTI_PARTIAL)])
 def test_full_size_prove_verify_roundtrip(ctx, n, degs, proto):
     """prove -> transcript replay (p(0)+p(1) chain) -> oracle check by folding the tables at the challenges:
     the three must close, and a second prove on the same resident tables must give identical bytes."""
@@ -436,4 +437,24 @@ def test_double_buffered_refill(ctx):
         pair[0].reupload_begin([host[0][i] for i in range(3)])   # second begin without end: STATE error
     pair[0].reupload_end()
     for t in pair:
+        t.free()
+
+
+def test_batch_of_64_proofs_roundtrip(ctx):
+    """BASELINE config 5 shape (64 independent proofs, batched launches, host worker pool) at 2^16 entries each: every proof's
+    transcript replays, its oracle check closes on the device, and proof 0 / 63 equal the oracle's bytes."""
+    n, degs, B = 16, [2], 64
+    t = zk.Tables.synth(ctx, n, degs, 900, n_proofs=B)
+    try:
+        sums = t.poly_sum()
+        msgs, lens, chal = t.prove(zk.PROTO_MULTI_PARTIAL, sums)
+        vals = t.evaluate(chal)
+        for b in range(B):
+            sub, ch2 = _lib.verify_rounds(zk.PROTO_MULTI_PARTIAL, sums[b], msgs[b], lens[b])
+            assert np.array_equal(ch2, chal[b]) and np.array_equal(vals[b], sub)
+        for b in (0, B - 1):
+            tabs = np.concatenate([cref.synth_table(900 + b, k, n) for k in range(2)])
+            s = cref.poly_sum(n, degs, tabs)
+            assert (_lib.proof_to_bytes(zk.PROTO_MULTI_PARTIAL, msgs[b], lens[b]), zk.from_mont(chal[b])) == cref.prove(2, n, degs, tabs, s)
+    finally:
         t.free()
