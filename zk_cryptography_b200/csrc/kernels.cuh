@@ -48,6 +48,10 @@ struct RoundBase {
     Fr* out;                   // FOLD: where the folded tables go (may alias `in`)
     unsigned long long in_tab_stride, in_proof_stride;    // elements
     unsigned long long out_tab_stride, out_proof_stride;  // elements
+    // gridDim.z > 1: the launch covers that many products of the SAME degree (blockIdx.z = product); element strides
+    // between consecutive products' first tables, and between their result slots
+    unsigned long long in_prod_stride, out_prod_stride;
+    unsigned int res_prod_stride;
     unsigned long long half;   // pairs per table in the round being evaluated (N_j / 2)
     Fr* partials;              // [proof][block][npts] scratch
     unsigned int* counters;    // [proof], zero on entry, zero on exit
@@ -201,13 +205,15 @@ ZKSC_DEV void reduce_and_publish(Acc<NL> (&acc)[NP], const RoundBase& args, int 
     __shared__ bool s_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int proof = blockIdx.y;
+    const unsigned int group = blockIdx.z * gridDim.y + proof;      // (product, proof) of this launch
+    const unsigned int n_groups = gridDim.y * gridDim.z;
 #pragma unroll
     for (int p = 0; p < NP; p++) {
         acc_warp_reduce(acc[p]);
         if (lane == 0) s_warp[warp][p] = acc[p];
     }
     __syncthreads();
-    Fr* my_partials = args.partials + ((size_t)proof * gridDim.x + blockIdx.x) * NP;
+    Fr* my_partials = args.partials + ((size_t)group * gridDim.x + blockIdx.x) * NP;
     if (warp == 0) {
 #pragma unroll
         for (int p = 0; p < NP; p++) {
@@ -222,7 +228,7 @@ ZKSC_DEV void reduce_and_publish(Acc<NL> (&acc)[NP], const RoundBase& args, int 
         }
         if (lane == 0) {
             __threadfence();
-            unsigned int done = atomicAdd(args.counters + proof, 1u);
+            unsigned int done = atomicAdd(args.counters + group, 1u);
             s_last = (done == gridDim.x - 1);
         }
     }
@@ -230,7 +236,7 @@ ZKSC_DEV void reduce_and_publish(Acc<NL> (&acc)[NP], const RoundBase& args, int 
     if (!s_last) return;
     __threadfence();
     // last block of this proof: sum the per-block partials (canonical Montgomery elements)
-    const Fr* all = args.partials + (size_t)proof * gridDim.x * NP;
+    const Fr* all = args.partials + (size_t)group * gridDim.x * NP;
     for (int p = warp; p < NP; p += kWarps) {
         if (point_of(p) >= npts) continue;
         Acc<9> a;
@@ -242,19 +248,19 @@ ZKSC_DEV void reduce_and_publish(Acc<NL> (&acc)[NP], const RoundBase& args, int 
         acc_warp_reduce(a);
         if (lane == 0) {
             Fr v = acc9_reduce(a);
-            st256_2x128(args.result + (size_t)proof * args.res_stride + point_of(p), v);   // may be host-mapped
+            st256_2x128(args.result + (size_t)proof * args.res_stride + (size_t)blockIdx.z * args.res_prod_stride + point_of(p), v);   // may be host-mapped
         }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        args.counters[proof] = 0;
+        args.counters[group] = 0;
         bool final_block = false;
         if (args.flag) {
             __threadfence_system();
-            // one flag word per proof would be wasteful: proofs bump a shared word via the counter slot
-            unsigned int fin = atomicAdd(args.counters + gridDim.y, 1u);
-            if (fin == gridDim.y - 1) {
-                args.counters[gridDim.y] = 0;
+            // one flag word per proof would be wasteful: the groups bump a shared word via the counter slot behind theirs
+            unsigned int fin = atomicAdd(args.counters + n_groups, 1u);
+            if (fin == n_groups - 1) {
+                args.counters[n_groups] = 0;
                 final_block = true;
             }
         }
@@ -353,8 +359,8 @@ __global__ void __launch_bounds__(kThreads, ZKSC_ROUND_MINB) round_kernel(const 
 #endif
     constexpr int NP = SKIP1 ? D : D + 1;   // accumulators
     const int proof = (NB == 1) ? 0 : blockIdx.y;
-    const Fr* in = args.in + (size_t)proof * args.in_proof_stride;
-    Fr* out = args.out + (size_t)proof * args.out_proof_stride;
+    const Fr* in = args.in + (size_t)proof * args.in_proof_stride + (size_t)blockIdx.z * args.in_prod_stride;
+    Fr* out = args.out + (size_t)proof * args.out_proof_stride + (size_t)blockIdx.z * args.out_prod_stride;
     const unsigned long long half = args.half;
     const int npts = args.npts;
 
@@ -514,8 +520,8 @@ __global__ void __launch_bounds__(kThreads, ZKSC_TMA_MINB(D)) round_tma_kernel(c
     __shared__ __align__(8) unsigned long long s_bar[kWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int proof = (NB == 1) ? 0 : blockIdx.y;
-    const Fr* in = args.in + (size_t)proof * args.in_proof_stride;
-    Fr* out = args.out + (size_t)proof * args.out_proof_stride;
+    const Fr* in = args.in + (size_t)proof * args.in_proof_stride + (size_t)blockIdx.z * args.in_prod_stride;
+    Fr* out = args.out + (size_t)proof * args.out_proof_stride + (size_t)blockIdx.z * args.out_prod_stride;
     const unsigned long long half = args.half;
     const int npts = args.npts;
     const unsigned char* my_slot = zksc_slots + warp * SLOT;

@@ -182,6 +182,7 @@ struct zksc_ctx {
     std::string err;
     int rank = 0, n_ranks = 1;
     // persistent tail kernel (tail_kernel.cuh): mailbox + result units in pinned, device-mapped host memory
+    bool fuse_products = true;           // ZKSC_NO_FUSE=1: one launch per product even when the degrees agree
     bool tail_enabled = true;            // ZKSC_NO_TAIL=1: every round is its own launch
     unsigned long long tail_work = kTailWorkPerCta;   // start threshold of the resident kernel (ZKSC_TAIL_WORK overrides, experiments)
     volatile uint64_t* tail_mail = nullptr;    // [tail_proofs_cap][kMailUnits]   {word | seq << 32}
@@ -319,8 +320,8 @@ extern "C" int zksc_ctx_create(int device, zksc_ctx** out) {
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
         cudaGetLastError();
     }
-    if ((e = cudaMalloc(&ctx->counters, (kMaxBatch + 1) * sizeof(unsigned int))) != cudaSuccess) return fail(e, "cudaMalloc");
-    if ((e = cudaMemset(ctx->counters, 0, (kMaxBatch + 1) * sizeof(unsigned int))) != cudaSuccess) return fail(e, "cudaMemset");
+    if ((e = cudaMalloc(&ctx->counters, (kMaxBatch * ZKSC_MAX_PRODUCTS + 1) * sizeof(unsigned int))) != cudaSuccess) return fail(e, "cudaMalloc");
+    if ((e = cudaMemset(ctx->counters, 0, (kMaxBatch * ZKSC_MAX_PRODUCTS + 1) * sizeof(unsigned int))) != cudaSuccess) return fail(e, "cudaMemset");
 #define ZKSC_OCC(D) zksc_prepare_round_##D(); for (int v = 0; v < 6; v++) ctx->occ[D][v] = zksc_occ_round_##D(v);
     ZKSC_OCC(1) ZKSC_OCC(2) ZKSC_OCC(3) ZKSC_OCC(4) ZKSC_OCC(5) ZKSC_OCC(6) ZKSC_OCC(7) ZKSC_OCC(8)
     if ((e = cudaGetLastError()) != cudaSuccess) return fail(e, "occupancy query (is this an sm_100a device?)");
@@ -336,6 +337,7 @@ extern "C" int zksc_ctx_create(int device, zksc_ctx** out) {
     { const char* e_ = getenv("ZKSC_NO_MAPPED"); ctx->mapped_results = !(e_ && e_[0] == '1'); }
     { const char* e_ = getenv("ZKSC_PROFILE"); ctx->profile = (e_ && e_[0] == '1'); }
     { const char* e_ = getenv("ZKSC_NO_TAIL"); ctx->tail_enabled = !(e_ && e_[0] == '1'); }
+    { const char* e_ = getenv("ZKSC_NO_FUSE"); ctx->fuse_products = !(e_ && e_[0] == '1'); }
     { const char* e_ = getenv("ZKSC_TAIL_WORK"); if (e_ && atoll(e_) > 0) ctx->tail_work = (unsigned long long)atoll(e_); }
     { const char* e_ = getenv("ZKSC_NO_STAGED"); ctx->staged = !(e_ && e_[0] == '1'); }
     { const char* e_ = getenv("ZKSC_STAGED_FOLD"); ctx->staged_fold = (e_ && e_[0] == '1'); }
@@ -1298,25 +1300,31 @@ static int round_evals_impl(zksc_tables* t, uint64_t* out, uint32_t npts_cap) {
     const unsigned int seq = ++ctx->flag_seq;
     if (peer) ctx->xch_seq++;
 
+    // products of one degree share a launch (blockIdx.z = product): GKR's two degree-2 products cost one launch per round
+    bool same_degree = t->P > 1 && ctx->fuse_products;
+    for (uint32_t p = 1; p < t->P; p++) same_degree = same_degree && t->deg[p] == t->deg[0];
+    const uint32_t p_step = same_degree ? t->P : 1;
     for (uint32_t b0 = 0; b0 < t->B; b0 += kMaxBatch) {
         uint32_t nb = t->B - b0 < (uint32_t)kMaxBatch ? t->B - b0 : kMaxBatch;
-        for (uint32_t p = 0; p < t->P; p++) {
+        for (uint32_t p = 0; p < t->P; p += p_step) {
             const int D = t->deg[p];
             // the staged kernel works on whole 32-pair warp tiles and pays off once HBM latency matters
             const bool staged = ctx->staged && (variant == 0 || ctx->staged_fold) && ctx->occ[D][3 + variant] > 0 && half % kTilePairs == 0 && half >= 4096;
             int gx = staged ? grid_for(ctx, half / kTilePairs * 32, kThreads, ctx->occ[D][3 + variant]) : grid_for(ctx, half, kThreads, ctx->occ[D][variant]);
-            TRY(ensure_partials(ctx, (size_t)nb * gx * (D + 1)));
+            TRY(ensure_partials(ctx, (size_t)nb * gx * (D + 1) * p_step));
             RoundBase base;
             base.in = gi.base + (size_t)b0 * gi.proof_stride + (size_t)t->koff[p] * gi.tab_stride;
             base.out = go.base + (size_t)b0 * go.proof_stride + (size_t)t->koff[p] * go.tab_stride;
             base.in_tab_stride = gi.tab_stride; base.in_proof_stride = gi.proof_stride;
             base.out_tab_stride = go.tab_stride; base.out_proof_stride = go.proof_stride;
+            base.in_prod_stride = (unsigned long long)D * gi.tab_stride; base.out_prod_stride = (unsigned long long)D * go.tab_stride;
+            base.res_prod_stride = (unsigned int)(D + 1);
             base.half = half;
             base.partials = ctx->partials; base.counters = ctx->counters;
             base.result = res + (size_t)b0 * t->E + t->eoff[p];
             base.res_stride = t->E;
             base.npts = (uint32_t)(D + 1) < npts_cap ? (D + 1) : npts_cap;
-            const bool last_launch = (b0 + nb == t->B) && (p + 1 == t->P);
+            const bool last_launch = (b0 + nb == t->B) && (p + p_step == t->P);
             base.flag = (mapped && last_launch) ? ctx->flag_dev : nullptr;
             base.flag_value = seq;
             base.xch.n_ranks = 0;
@@ -1329,8 +1337,8 @@ static int round_evals_impl(zksc_tables* t, uint64_t* out, uint32_t npts_cap) {
                 x.send = ctx->results_send; x.out = ctx->results_host_dev;
                 x.n_ranks = ctx->n_ranks; x.rank = ctx->rank; x.seq = ctx->xch_seq; x.n_elems = (unsigned int)n_res; x.cap = kXchCap;
             }
-            dim3 grid(gx, nb);
-            TRY(timing_open(ctx, D, fold, half, nb));
+            dim3 grid(gx, nb, p_step);
+            TRY(timing_open(ctx, D, fold, half, (unsigned long long)nb * p_step));
             int rc = (nb == 1) ? launch_round<1>(t, base, D, variant, staged, grid, fold, b0, nb) : launch_round<kMaxBatch>(t, base, D, variant, staged, grid, fold, b0, nb);
             if (rc != ZKSC_OK) FAIL(rc, "degree");
             TRY(timing_close(ctx));
