@@ -17,18 +17,21 @@ namespace zksc {
 // W(point_j), j = blockIdx.x, for tables of at most 2^kGkrSmallLog entries: the first fold reads W from HBM, the
 // remaining ones run in shared memory (Multilinear::evaluation = successive variable-0 folds, evaluation_form.rs:162-175).
 constexpr int kGkrSmallLog = 11;
-__global__ void __launch_bounds__(256) gkr_eval_small_kernel(const Fr* w, unsigned int k, const Fr* points, Fr* out) {
+struct GkrPoints {
+    Fr pt[2][kGkrSmallLog];    // the coordinates travel as kernel parameters: no host->device copy in front of the launch
+};
+__global__ void __launch_bounds__(256) gkr_eval_small_kernel(const Fr* w, unsigned int k, const __grid_constant__ GkrPoints points, Fr* out) {
     __shared__ Fr buf[1 << (kGkrSmallLog - 1)];
-    const Fr* pt = points + (size_t)blockIdx.x * k;
+    const Fr* pt = points.pt[blockIdx.x];
     unsigned int half = 1u << (k - 1);
     {
-        const Fr r = ld256(pt);
+        const Fr r = pt[0];
         for (unsigned int o = threadIdx.x; o < half; o += blockDim.x) buf[o] = fr_fold(ld256(w + o), ld256(w + o + half), r);
     }
     for (unsigned int j = 1; j < k; j++) {
         __syncthreads();
         half >>= 1;
-        const Fr r = ld256(pt + j);
+        const Fr r = pt[j];
         // in place: entry o is read by the thread that writes it and by nobody else (the other operand is o + half >= half)
         for (unsigned int o = threadIdx.x; o < half; o += blockDim.x) {
             const Fr v = fr_fold(buf[o], buf[o + half], r);
@@ -42,10 +45,11 @@ __global__ void __launch_bounds__(256) gkr_eval_small_kernel(const Fr* w, unsign
 }  // namespace zksc
 
 // evaluations of a device-resident multilinear table at n_points points (each of k coordinates, on the device too)
-static int gkr_eval_device(zksc_ctx* ctx, const Fr* d_w, uint32_t k, const Fr* d_points, const uint64_t* h_points, uint32_t n_points, Fr* d_out,
-                           uint64_t* h_out) {
-    if (k >= 1 && k <= (uint32_t)kGkrSmallLog) {
-        gkr_eval_small_kernel<<<n_points, 256, 0, ctx->stream>>>(d_w, k, d_points, d_out);
+static int gkr_eval_device(zksc_ctx* ctx, const Fr* d_w, uint32_t k, const uint64_t* h_points, uint32_t n_points, Fr* d_out, uint64_t* h_out) {
+    if (k >= 1 && k <= (uint32_t)kGkrSmallLog && n_points <= 2) {
+        GkrPoints pts;
+        for (uint32_t q = 0; q < n_points; q++) memcpy(pts.pt[q], h_points + (size_t)q * k * 4, (size_t)k * 32);
+        gkr_eval_small_kernel<<<n_points, 256, 0, ctx->stream>>>(d_w, k, pts, d_out);
         ctx->launches++;
         CK(cudaGetLastError());
     } else {
@@ -164,34 +168,45 @@ extern "C" int zksc_gkr_prove(zksc_ctx* ctx, uint32_t n_layers, const uint32_t* 
         zksc_tables* t = nullptr;
         TRY(tables_alloc(ctx, n, 1, 2, degs, &t));
         struct Guard { zksc_tables* t; ~Guard() { if (t) zksc_tables_free(t); } } guard{t};
-        DevBuf dw(ctx), dv(ctx), dpts(ctx);
+        // one device buffer [W | sparse values | sparse indices | 2 results], filled by ONE copy from a pinned staging buffer
         const size_t n_sp = idx_add.size() + idx_mul.size();
-        CK(dev_alloc(ctx, (void**)&dw.p, nw * sizeof(Fr)));
-        CK(dev_alloc(ctx, (void**)&dv.p, (n_sp + (n_sp + 3) / 4 + 1) * sizeof(Fr)));   // values, then indices
-        CK(dev_alloc(ctx, (void**)&dpts.p, (size_t)(n + 2) * sizeof(Fr)));             // 2k challenge coordinates + 2 results
-        CK(cudaMemcpyAsync(dw.p, layer_values[li + 1], nw * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+        const size_t off_val = nw, off_idx = off_val + n_sp, off_res = off_idx + (n_sp + 3) / 4, n_buf = off_res + 2;
+        DevBuf dbuf(ctx);
+        CK(dev_alloc(ctx, (void**)&dbuf.p, n_buf * sizeof(Fr)));
+        if (ctx->gkr_stage_cap < off_res * 4) {
+            CK(cudaStreamSynchronize(ctx->stream));
+            if (ctx->gkr_stage) cudaFreeHost(ctx->gkr_stage);
+            ctx->gkr_stage = nullptr; ctx->gkr_stage_cap = 0;
+            CK(cudaHostAlloc((void**)&ctx->gkr_stage, off_res * 4 * 2 * sizeof(uint64_t), cudaHostAllocDefault));
+            ctx->gkr_stage_cap = off_res * 4 * 2;
+        }
+        {
+            uint64_t* stage = ctx->gkr_stage;       // free again: the previous layer ended with a stream synchronisation
+            memcpy(stage, layer_values[li + 1], nw * sizeof(Fr));
+            for (size_t i = 0; i < idx_add.size(); i++) store_h(&stage[4 * (off_val + i)], val_add[i]);
+            for (size_t i = 0; i < idx_mul.size(); i++) store_h(&stage[4 * (off_val + idx_add.size() + i)], val_mul[i]);
+            memcpy(&stage[4 * off_idx], idx_add.data(), idx_add.size() * 8);
+            memcpy(&stage[4 * off_idx + idx_add.size()], idx_mul.data(), idx_mul.size() * 8);
+            CK(cudaMemcpyAsync(dbuf.p, stage, off_res * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+        }
+        const Fr* d_w = dbuf.p;
         Fr* tab = t->orig;
         const uint64_t N = t->n_local0;
         // W(b) + W(c), W(b) W(c)                                                             protocol.rs:80-81
-        outer_fill_kernel<<<grid_for(ctx, N, 256, 8), 256, 0, ctx->stream>>>(0, dw.p, dw.p, nw, tab + 1 * N, N, 0, 1);
-        outer_fill_kernel<<<grid_for(ctx, N, 256, 8), 256, 0, ctx->stream>>>(1, dw.p, dw.p, nw, tab + 3 * N, N, 0, 1);
+        outer_fill_kernel<<<grid_for(ctx, N, 256, 8), 256, 0, ctx->stream>>>(0, d_w, d_w, nw, tab + 1 * N, N, 0, 1);
+        outer_fill_kernel<<<grid_for(ctx, N, 256, 8), 256, 0, ctx->stream>>>(1, d_w, d_w, nw, tab + 3 * N, N, 0, 1);
         ctx->launches += 2;
         CK(cudaMemsetAsync(tab, 0, N * sizeof(Fr), ctx->stream));
         CK(cudaMemsetAsync(tab + 2 * N, 0, N * sizeof(Fr), ctx->stream));
         if (n_sp) {
-            std::vector<uint64_t> stage(n_sp * 4 + n_sp);
-            for (size_t i = 0; i < idx_add.size(); i++) store_h(&stage[4 * i], val_add[i]);
-            for (size_t i = 0; i < idx_mul.size(); i++) store_h(&stage[4 * (idx_add.size() + i)], val_mul[i]);
-            memcpy(&stage[4 * n_sp], idx_add.data(), idx_add.size() * 8);
-            memcpy(&stage[4 * n_sp + idx_add.size()], idx_mul.data(), idx_mul.size() * 8);
-            CK(cudaMemcpyAsync(dv.p, stage.data(), stage.size() * 8, cudaMemcpyHostToDevice, ctx->stream));   // pageable: staged before the call returns
-            const unsigned long long* didx = (const unsigned long long*)(dv.p + n_sp);
+            const Fr* d_val = dbuf.p + off_val;
+            const unsigned long long* didx = (const unsigned long long*)(dbuf.p + off_idx);
             if (!idx_add.empty()) {
-                scatter_kernel<<<(unsigned int)((idx_add.size() + 255) / 256), 256, 0, ctx->stream>>>(didx, dv.p, idx_add.size(), tab, 0, 1);
+                scatter_kernel<<<(unsigned int)((idx_add.size() + 255) / 256), 256, 0, ctx->stream>>>(didx, d_val, idx_add.size(), tab, 0, 1);
                 ctx->launches++;
             }
             if (!idx_mul.empty()) {
-                scatter_kernel<<<(unsigned int)((idx_mul.size() + 255) / 256), 256, 0, ctx->stream>>>(didx + idx_add.size(), dv.p + idx_add.size(), idx_mul.size(),
+                scatter_kernel<<<(unsigned int)((idx_mul.size() + 255) / 256), 256, 0, ctx->stream>>>(didx + idx_add.size(), d_val + idx_add.size(), idx_mul.size(),
                                                                                                        tab + 2 * N, 0, 1);
                 ctx->launches++;
             }
@@ -219,9 +234,8 @@ extern "C" int zksc_gkr_prove(zksc_ctx* ctx, uint32_t n_layers, const uint32_t* 
         // (b, c) = challenges.split_at(len / 2); W(b), W(c)                                    protocol.rs:100-105
         r_b.clear(); r_c.clear();
         for (uint32_t j = 0; j < k; j++) { r_b.push_back(load_h(chal + 4 * j)); r_c.push_back(load_h(chal + 4 * (k + j))); }
-        CK(cudaMemcpyAsync(dpts.p, chal, (size_t)n * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
         uint64_t ev[8];
-        TRY(gkr_eval_device(ctx, dw.p, k, dpts.p, chal, 2, dpts.p + n, ev));
+        TRY(gkr_eval_device(ctx, d_w, k, chal, 2, dbuf.p + off_res, ev));
         memcpy(wb_s + 4 * li, ev, 32);
         memcpy(wc_s + 4 * li, ev + 4, 32);
         alpha = transcript.evaluate_challenge_into_field();                                      // protocol.rs:110-111

@@ -160,6 +160,8 @@ struct zksc_ctx {
     int device = 0;
     int sms = 0;
     cudaStream_t stream = nullptr;
+    uint64_t* gkr_stage = nullptr;        // pinned staging buffer of zksc_gkr_prove (one host->device copy per layer)
+    size_t gkr_stage_cap = 0;             // in uint64_t
     HostPool* pool = nullptr;             // created on first use by a batched zksc_prove (ZKSC_HOST_THREADS, default up to 8 threads)
     bool pool_active = false;
     cudaStream_t copy_stream = nullptr;   // zksc_tables_reupload_begin: host->device copies that overlap the compute stream
@@ -368,6 +370,7 @@ extern "C" int zksc_ctx_destroy(zksc_ctx* ctx) {
     cudaFree(ctx->tail_relay);
     cudaFree(ctx->tail_sums);
     delete ctx->pool;
+    if (ctx->gkr_stage) cudaFreeHost(ctx->gkr_stage);
     if (ctx->copy_stream) { cudaStreamDestroy(ctx->copy_stream); cudaEventDestroy(ctx->copy_event); }
     cudaStreamDestroy(ctx->stream);
     delete ctx;
