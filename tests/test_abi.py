@@ -39,3 +39,19 @@ def test_rust_ffi_is_in_sync_with_the_header(built):
     ffi = open(os.path.join(ROOT, "rust", "zksc-sys", "src", "ffi.rs")).read()
     rust = set(re.findall(r"pub fn (zksc_[a-z0-9_]+)\(", ffi))
     assert rust == set(declared_symbols())
+
+
+def test_headers_compile_cleanly():
+    """include/zksc.h is plain C (C99, no CUDA or C++ types in the signatures); include/zksc.hpp and the restated reference tests
+    compile without warnings under -Wall -Wextra -Wpedantic."""
+    import shutil
+    import subprocess
+    import pytest
+    if not shutil.which("gcc") or not shutil.which("g++"):
+        pytest.skip("no host compiler")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Wpedantic", "-Werror", "-fsyntax-only", "-x", "c", os.path.join(ROOT, "include", "zksc.h")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run(["g++", "-std=c++17", "-Wall", "-Wextra", "-Wpedantic", "-Werror", "-fsyntax-only", os.path.join(ROOT, "tests", "cpp", "reference_cases.cpp")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
