@@ -120,6 +120,20 @@ ZKSC_DEV bool tail_read_elem(const unsigned long long* u, unsigned int seq, Fr& 
     }
 }
 
+// Debug timeline (-DZKSC_TAIL_TRACE, tools/trace_tail.py): thread 0 of CTA 0 and of CTA 1 of group 0 record %globaltimer at the
+// phase boundaries of every round into g_tail_trace[round][cta][phase]; read back with zksc_debug_tail_trace.  Off by default.
+#ifdef ZKSC_TAIL_TRACE
+constexpr int kTraceRounds = 64, kTracePhases = 8;
+__device__ unsigned long long g_tail_trace[kTraceRounds * 2 * kTracePhases];
+#define ZKSC_TRACE(phase)                                                                                                              \
+    do {                                                                                                                               \
+        if (threadIdx.x == 0 && cta < 2 && group == 0 && round < (unsigned int)kTraceRounds)                                           \
+            g_tail_trace[(round * 2 + cta) * kTracePhases + (phase)] = global_timer_ns();                                              \
+    } while (0)
+#else
+#define ZKSC_TRACE(phase) do { } while (0)
+#endif
+
 // One CTA of the group of (proof, product), degree D: all rounds.
 template <int D>
 ZKSC_DEV void tail_body(const TailArgs& args, const int proof, const int product, FoldTab& s_tab, int& s_state) {
@@ -146,6 +160,7 @@ ZKSC_DEV void tail_body(const TailArgs& args, const int proof, const int product
         unsigned long long want = (half + kTailThreads - 1) / kTailThreads;
         const unsigned int n_active = want < n_ctas ? (unsigned int)want : n_ctas;
         if (cta >= n_active) return;            // no share of the table in this or any later round
+        ZKSC_TRACE(0);
         // ---- 1. the challenge of the previous round
         if (warp == 0) {
             // only CTA 0 decides that the host has gone away (and then tells the others through the relay)
@@ -164,7 +179,9 @@ ZKSC_DEV void tail_body(const TailArgs& args, const int proof, const int product
             if (s_state == 2 && cta == 0 && threadIdx.x < 8 * (D + 1)) st_unit(res + threadIdx.x, 0u, kTailTimeout);
             return;
         }
+        ZKSC_TRACE(1);
         if (n_ctas > 1) fence_acq_rel_gpu();     // acquire: tables written by other CTAs before they handed in their sums
+        ZKSC_TRACE(2);
         // ---- 2. fold + evaluate this CTA's share
         Acc<NL> acc[NP];
 #pragma unroll
@@ -184,7 +201,9 @@ ZKSC_DEV void tail_body(const TailArgs& args, const int proof, const int product
             }
             accumulate_points<D, true>(acc, a, b, D + 1);
         }
+        ZKSC_TRACE(3);
         if (n_active > 1) fence_acq_rel_gpu();   // release: this thread's table stores, before the CTA's sums go out
+        ZKSC_TRACE(4);
         // ---- 3. reduce inside the CTA
 #pragma unroll
         for (int p = 0; p < NP; p++) {
@@ -193,27 +212,29 @@ ZKSC_DEV void tail_body(const TailArgs& args, const int proof, const int product
         }
         __syncthreads();      // (s_tab may be rewritten from here on)
         bool ok = true;
-        if (warp == 0) {
+        static_assert(NP <= kTailWarps, "one warp per evaluation point");
+        if (warp < NP) {
+            // warp p finishes point p: the NP reductions (each ends in two Montgomery products) run side by side instead of one
+            // after the other in warp 0 -- this step was 3.4-3.8 us of every resident round (profiles/r01_tail_trace_c2_v10.txt)
+            const int p = warp;
+            Acc<NL> a;
+            if (lane < kTailWarps) a = s_warp[lane][p];
+            else acc_zero(a);
+            acc_warp_reduce(a);
+            const Fr v = acc_finish<NL>(a);                    // lane 0 holds the CTA's total
+            if (n_active > 1) {
 #pragma unroll
-            for (int p = 0; p < NP; p++) {
-                Acc<NL> a;
-                if (lane < kTailWarps) a = s_warp[lane][p];
-                else acc_zero(a);
-                acc_warp_reduce(a);
-                const Fr v = acc_finish<NL>(a);                    // lane 0 holds the CTA's total
-                if (n_active > 1) {
-#pragma unroll
-                    for (int l = 0; l < 8; l++) {
-                        const uint32_t limb = __shfl_sync(0xffffffffu, v.l[l], 0);
-                        if (lane == l) st_unit(sums + ((size_t)cta * kTailMaxDegree + p) * 8 + l, limb, seq);
-                    }
-                } else if (lane == 0) {
-                    s_tot[p] = v;
+                for (int l = 0; l < 8; l++) {
+                    const uint32_t limb = __shfl_sync(0xffffffffu, v.l[l], 0);
+                    if (lane == l) st_unit(sums + ((size_t)cta * kTailMaxDegree + p) * 8 + l, limb, seq);
                 }
+            } else if (lane == 0) {
+                s_tot[p] = v;
             }
         }
         in = out;
         in_stride = args.out_tab_stride;
+        ZKSC_TRACE(5);
         if (cta != 0) continue;
         // ---- 4. CTA 0: the other CTAs' sums (warp p collects point slot p)
         if (n_active > 1) {
@@ -231,6 +252,7 @@ ZKSC_DEV void tail_body(const TailArgs& args, const int proof, const int product
             fence_acq_rel_gpu();               // acquire the other CTAs' table stores; the relay / host messages release them
         }
         __syncthreads();
+        ZKSC_TRACE(6);
         // ---- 5. sharded contexts: all-to-all of the group's sums through peer memory, modular sum
         if (args.n_ranks > 1) {
             const unsigned int G = args.n_ranks, slot = (seq & 1u) * G;
@@ -266,6 +288,7 @@ ZKSC_DEV void tail_body(const TailArgs& args, const int proof, const int product
             const int p = threadIdx.x >> 3, l = threadIdx.x & 7;
             st_unit(res + (p == 0 ? 0 : p + 1) * 8 + l, s_tot[p].l[l], seq);
         }
+        ZKSC_TRACE(7);
     }
 }
 
