@@ -458,3 +458,23 @@ def test_batch_of_64_proofs_roundtrip(ctx):
             assert (_lib.proof_to_bytes(zk.PROTO_MULTI_PARTIAL, msgs[b], lens[b]), zk.from_mont(chal[b])) == cref.prove(2, n, degs, tabs, s)
     finally:
         t.free()
+
+
+def test_sumcheck_utils_helpers():  # sumcheck/src/utils.rs
+    """the byte / hypercube helpers of the reference's sumcheck::utils, device-backed, against the Python model"""
+    from zk_cryptography_b200 import utils as U
+    rng = random.Random(5)
+    assert U.convert_field_to_byte(1) == bytes(31) + b"\x01" and U.convert_field_to_byte(100)[-1] == 100      # utils.rs tests
+    assert U.boolean_hypercube(2) == [[0, 0], [0, 1], [1, 0], [1, 1]]
+    ev = [rng.randrange(R) for _ in range(16)]
+    f = ML(ev)
+    got = U.skip_first_and_sum_all(f)
+    assert got.to_ints() == [sum(ev[:8]) % R, sum(ev[8:]) % R] == f.split_poly_into_two_and_sum_each_part().to_ints()
+    assert U.skip_first_and_sum_all(ML([0, 0, 2, 7, 3, 3, 6, 11])).to_ints() == [9, 23]      # evaluation_form.rs:408-438 values
+    a, b = [rng.randrange(R) for _ in range(8)], [rng.randrange(R) for _ in range(8)]
+    polys = [zk.ComposedMultilinear([ML(a), ML(b)]), zk.ComposedMultilinear([ML(b)])]
+    opolys = [pm.ComposedMultilinear([pm.Multilinear(a), pm.Multilinear(b)]), pm.ComposedMultilinear([pm.Multilinear(b)])]
+    assert U.sum_over_boolean_hypercube(polys) == pm.sum_over_boolean_hypercube(opolys)
+    assert U.composed_poly_to_bytes(polys) == pm.composed_poly_to_bytes(opolys)
+    assert U.vec_to_bytes(a) == pm.vec_to_bytes(a)
+    assert U.convert_round_poly_to_uni_poly_format([5, 6, 7]) == [(0, 5), (1, 6), (2, 7)]

@@ -17,5 +17,6 @@ from .api import (Multilinear, ComposedMultilinear, Sumcheck, SumcheckProof, Com
                   MultiComposedSumcheckProver, MultiComposedSumcheckVerifier, MultiComposedProof, SubClaim,
                   FiatShamirTranscript, SparseUnivariatePolynomial, default_context, set_default_context)
 from .gkr import Gate, GateType, CircuitLayer, Circuit, GKRProof, GKRProtocol, GKRInstance
+from . import utils
 
 __all__ = [n for n in dir() if not n.startswith("_")]
