@@ -241,6 +241,11 @@ uint32_t zksc_sparse_interpolate(const uint64_t* ys, uint32_t n, uint64_t* out_m
 uint32_t zksc_sparse_add(const uint64_t* a_mono, uint32_t na, const uint64_t* b_mono, uint32_t nb, uint64_t* out_mono);
 /* SparseUnivariatePolynomial::evaluate (sparse_univariate.rs:90-106) */
 void zksc_sparse_evaluate(const uint64_t* mono, uint32_t n, const uint64_t point[4], uint64_t out[4]);
+/* What the round kernels deliver for one product -> its evaluations at 0..degree, in place (degree + 1 Montgomery elements).
+ * The kernels evaluate degree-2 products at {0, 1, inf} and degree-3 products at {0, 1, -1, inf} (cheaper operands than 2 and 3;
+ * inf = the leading coefficient); zksc_round_evals / zksc_prove apply this conversion themselves -- it is exported so that the
+ * identity can be tested without a device.  Other degrees are left as they are. */
+void zksc_round_slots_to_evals(uint32_t degree, uint64_t* values);
 /* Seeded synthetic table entry (canonical value -> Montgomery), same convention as the device generator */
 void zksc_synth_entry(uint64_t seed, uint64_t table, uint64_t index, uint64_t out[4]);
 

@@ -164,3 +164,26 @@ def test_sha256_scalar_and_shani_paths_agree():
         env = dict(os.environ, **env_extra)
         r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
         assert r.returncode == 0 and r.stdout.strip() == "ok", r.stderr[-1500:]
+
+
+def test_round_slots_to_evals():
+    """host::round_slots_to_evals (what finish_round applies to every round's device results): degree-2 products arrive as
+    (h(0), h(1), h(inf)), degree-3 products as (h(0), h(1), h(-1), h(inf)); the helper must return the evaluations at 0..d --
+    checked on random polynomials with Python big integers; other degrees pass through untouched."""
+    rng = random.Random(31)
+    L = zk.lib()
+    for trial in range(200):
+        for d in (2, 3):
+            c = [rng.randrange(R) for _ in range(d + 1)]
+            if trial < 4:
+                c = [[0] * (d + 1), [R - 1] * (d + 1), [1] + [0] * d, [0] * d + [1]][trial]
+            h = lambda t: sum(ci * pow(t, i, R) for i, ci in enumerate(c)) % R
+            slots = [h(0), h(1), c[2]] if d == 2 else [h(0), h(1), h(R - 1), c[3]]
+            arr = zk.to_mont(slots)
+            L.zksc_round_slots_to_evals(d, _lib.p64(arr))
+            assert zk.from_mont(arr) == [h(t) for t in range(d + 1)]
+    for d in (1, 4, 5):
+        vals = [rng.randrange(R) for _ in range(d + 1)]
+        arr = zk.to_mont(vals)
+        L.zksc_round_slots_to_evals(d, _lib.p64(arr))
+        assert zk.from_mont(arr) == vals

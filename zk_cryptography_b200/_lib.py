@@ -102,6 +102,7 @@ def lib():
         "zksc_sparse_interpolate": (ctypes.c_uint32, [_u64p, ctypes.c_uint32, _u64p]),
         "zksc_sparse_add": (ctypes.c_uint32, [_u64p, ctypes.c_uint32, _u64p, ctypes.c_uint32, _u64p]),
         "zksc_sparse_evaluate": (None, [_u64p, ctypes.c_uint32, _u64p, _u64p]),
+        "zksc_round_slots_to_evals": (None, [ctypes.c_uint32, _u64p]),
         "zksc_synth_entry": (None, [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, _u64p]),
     }
     for name, (res, args) in sig.items():

@@ -184,6 +184,33 @@ inline int cmp_canonical(const FrH& a, const FrH& b) {
     return 0;
 }
 
+// What the round kernels deliver per product (kernels.cuh accumulate_points) -> the evaluations h(0..d) the protocol speaks of.
+// `e` holds degree + 1 elements (4 x u64 each), slots 0 and 1 = h(0), h(1) for every degree.
+//   degree 2: slot 2 = the leading coefficient h(inf);            h(2) = 2 h(1) - h(0) + 2 h(inf)
+//   degree 3: slots 2, 3 = h(-1), h(inf).  With h(t) = c0 + c1 t + c2 t^2 + c3 t^3:
+//             c0 = h(0), c3 = h(inf), c2 = (h(1) + h(-1)) / 2 - c0, c1 = (h(1) - h(-1)) / 2 - c3,
+//             h(2) = c0 + 2 c1 + 4 c2 + 8 c3,  h(3) = c0 + 3 c1 + 9 c2 + 27 c3
+//   other degrees: the slots are the evaluations already.
+// Exact field arithmetic: the canonical values are those of evaluating at 2 (and 3) directly.
+inline void round_slots_to_evals(uint32_t degree, uint64_t* e) {
+    auto ld = [](const uint64_t* p) { FrH h; memcpy(h.v, p, 32); return h; };
+    auto st = [](uint64_t* p, const FrH& h) { memcpy(p, h.v, 32); };
+    if (degree == 3) {
+        static const FrH inv2 = inverse(from_u64(2));
+        static const FrH k3 = from_u64(3), k4 = from_u64(4), k8 = from_u64(8), k9 = from_u64(9), k27 = from_u64(27);
+        const FrH c0 = ld(e), h1 = ld(e + 4), hm = ld(e + 8), c3 = ld(e + 12);
+        const FrH c2 = sub(mul(add(h1, hm), inv2), c0);
+        const FrH c1 = sub(mul(sub(h1, hm), inv2), c3);
+        const FrH c1_2 = add(c1, c1);
+        st(e + 8, add(add(c0, c1_2), add(mul(c2, k4), mul(c3, k8))));
+        st(e + 12, add(add(c0, mul(c1, k3)), add(mul(c2, k9), mul(c3, k27))));
+    } else if (degree == 2) {
+        const FrH h0 = ld(e), h1 = ld(e + 4), hi = ld(e + 8);
+        const FrH s = add(sub(h1, h0), hi);       // h(1) - h(0) + h(inf)
+        st(e + 8, add(add(s, s), h0));            // 2 (h(1) - h(0) + h(inf)) + h(0)
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // SHA-256 (FIPS 180-4), streaming.  Replaces sha2 0.10.8 `Sha256::{new,update,finalize_reset}`.
 // ------------------------------------------------------------------------------------------------

@@ -1212,36 +1212,13 @@ static void finish_round(zksc_tables* t, uint64_t* out, bool skip1, bool full, u
                 store_h(e + 4, host::sub(t->claim[(size_t)b * t->P + p], load_h(e)));
             }
     }
-    // degree-2 products: the kernels deliver the leading coefficient h(inf) in the slot of point 2 (kernels.cuh
-    // accumulate_points); h(2) = 2 h(1) - h(0) + 2 h(inf)
-    // degree-3 products: slots 2 and 3 hold h(-1) and h(inf).  With h(t) = c0 + c1 t + c2 t^2 + c3 t^3:
-    //   c0 = h(0), c3 = h(inf), c2 = (h(1) + h(-1)) / 2 - c0, c1 = (h(1) - h(-1)) / 2 - c3,
-    //   h(2) = c0 + 2 c1 + 4 c2 + 8 c3,  h(3) = c0 + 3 c1 + 9 c2 + 27 c3      (exact in the field: identical canonical values)
-    if (npts_cap > 3)
-        for (uint32_t p = 0; p < t->P; p++) {
-            if (t->deg[p] != 3) continue;
-            static const FrH inv2 = host::inverse(host::from_u64(2));
-            static const FrH k3 = host::from_u64(3), k4 = host::from_u64(4), k8 = host::from_u64(8), k9 = host::from_u64(9), k27 = host::from_u64(27);
-            for (uint32_t b = 0; b < t->B; b++) {
-                uint64_t* e = out + ((size_t)b * t->E + t->eoff[p]) * 4;
-                const FrH c0 = load_h(e), h1 = load_h(e + 4), hm = load_h(e + 8), c3 = load_h(e + 12);
-                const FrH c2 = host::sub(host::mul(host::add(h1, hm), inv2), c0);
-                const FrH c1 = host::sub(host::mul(host::sub(h1, hm), inv2), c3);
-                const FrH c1_2 = host::add(c1, c1);
-                store_h(e + 8, host::add(host::add(c0, c1_2), host::add(host::mul(c2, k4), host::mul(c3, k8))));
-                store_h(e + 12, host::add(host::add(c0, host::mul(c1, k3)), host::add(host::mul(c2, k9), host::mul(c3, k27))));
-            }
-        }
-    if (npts_cap > 2)
-        for (uint32_t p = 0; p < t->P; p++) {
-            if (t->deg[p] != 2) continue;
-            for (uint32_t b = 0; b < t->B; b++) {
-                uint64_t* e = out + ((size_t)b * t->E + t->eoff[p]) * 4;
-                const FrH h0 = load_h(e), h1 = load_h(e + 4), hi = load_h(e + 8);
-                const FrH s = host::add(host::sub(h1, h0), hi);       // h(1) - h(0) + h(inf)
-                store_h(e + 8, host::add(host::add(s, s), h0));       // 2 (h(1) - h(0) + h(inf)) + h(0)
-            }
-        }
+    // degree-2 and degree-3 products: the kernels deliver h(inf) (and h(-1)) instead of h(2) (and h(3)); see
+    // host::round_slots_to_evals.  Every caller asks for all degree + 1 values (npts_cap = ZKSC_MAX_DEGREE + 1).
+    for (uint32_t p = 0; p < t->P; p++) {
+        const uint32_t d = t->deg[p];
+        if ((d != 2 && d != 3) || npts_cap <= d) continue;
+        for (uint32_t b = 0; b < t->B; b++) host::round_slots_to_evals(d, out + ((size_t)b * t->E + t->eoff[p]) * 4);
+    }
     t->claim_valid = false;
     if (full) {
         t->last_evals.assign(out, out + (size_t)t->B * t->E * 4);
@@ -1835,6 +1812,7 @@ static host::SparseUnivariatePolynomial load_poly(const uint64_t* mono, uint32_t
     for (uint32_t i = 0; i < n; i++) p.monomial.push_back({load_h(mono + 8 * i), load_h(mono + 8 * i + 4)});
     return p;
 }
+extern "C" void zksc_round_slots_to_evals(uint32_t degree, uint64_t* values) { host::round_slots_to_evals(degree, values); }
 extern "C" uint32_t zksc_sparse_interpolate(const uint64_t* ys, uint32_t n, uint64_t* out_mono) {
     std::vector<FrH> y;
     for (uint32_t i = 0; i < n; i++) y.push_back(load_h(ys + 4 * i));
