@@ -145,6 +145,140 @@ def limb_products(rec):
     return (fold + points * per_point) * rec["pairs"] * rec["proofs"]
 
 
+def proof_digest(proto, msgs, lens, chal):
+    """sha256 over the proof bytes (what the reference's transcript absorbs) followed by the challenges, for proof 0."""
+    import hashlib
+    import numpy as np
+    from zk_cryptography_b200 import _lib
+    h = hashlib.sha256()
+    h.update(_lib.proof_to_bytes(proto, msgs[0], lens[0]))
+    h.update(np.ascontiguousarray(chal[0]).tobytes())
+    return h.hexdigest()
+
+
+def round_rows(n, degs, G, round_us, poly_sum_us, hbm_peak, int_tops, gather_at=None):
+    """Every round of one proof against its binding roof.  round_us: host wall time per round of zksc_prove (the device pass,
+    the transcript step and the bind, so that the rounds add up to the step); round 0's device pass happens inside
+    calculate_poly_sum (prove reuses its evaluations), so poly_sum_us is added to round 0.  A sharded proof works on
+    2^(n-1-j)/G pairs per rank in round j until the shards are gathered (the last rounds run replicated on all ranks)."""
+    rows = []
+    lgG = int(math.log2(G))
+    for j, us in enumerate(round_us):
+        pairs_total = 1 << (n - 1 - j)
+        sharded = G > 1 and (n - j) > lgG and (gather_at is None or (1 << (n - j)) > gather_at)
+        pairs = pairs_total // G if sharded else pairs_total
+        t = us + (poly_sum_us if j == 0 else 0.0)
+        t_hbm = t_int = 0.0
+        for d in degs:
+            rec = {"degree": d, "fold": 1 if j else 0, "pairs": pairs, "proofs": 1}
+            t_hbm += algorithmic_bytes(rec) / (hbm_peak * 1e9) * 1e6
+            t_int += limb_products(rec) / (int_tops * 1e12) * 1e6
+        t_min = max(t_hbm, t_int)
+        rows.append({"round": j, "pairs": pairs, "us": round(t, 2), "binding": "hbm" if t_hbm >= t_int else "int32-multiply",
+                     "min_us": round(t_min, 3), "frac": round(t_min / t, 4) if t > 0 else None})
+    return rows
+
+
+def parity_check(zk, ctx, rank, G, degs, proto_name, n=20):
+    """A proof on the SAME context (sharded when the benchmark's is) against the CPU oracle, outside any timed region:
+    hypercube sum, proof bytes and challenges must be identical (oracle/zkref.c = the restatement of
+    multi_composed_sumcheck.rs:64-120 / sumcheck.rs:29-61).  Every rank proves; rank 0 compares."""
+    from zk_cryptography_b200 import _lib
+    proto = {"multi_partial": zk.PROTO_MULTI_PARTIAL, "sumcheck": zk.PROTO_SUMCHECK}[proto_name]
+    seed = SEED + 17
+    t = zk.Tables.synth(ctx, n, degs, seed)
+    s = t.poly_sum()
+    msgs, lens, chal = t.prove(proto, s)
+    t.free()
+    if rank != 0:
+        return None
+    import numpy as np
+    from oracle import cref
+    cref.set_threads(cref.max_threads())
+    tabs = np.concatenate([cref.synth_table(seed, k, n) for k in range(sum(degs))])
+    osum = cref.poly_sum(n, degs, tabs)
+    obytes, och = cref.prove({"multi_partial": 2, "sumcheck": 0}[proto_name], n, degs, tabs, osum)
+    got = _lib.proof_to_bytes(proto, msgs[0], lens[0])
+    ok = zk.from_mont(s[0]) == osum and got == obytes and zk.from_mont(chal[0]) == och
+    return {"ok": bool(ok), "n_vars": n, "degrees": degs, "n_gpus": G, "proof_bytes": len(got),
+            "against": "oracle/zkref.c prove (sum, proof bytes, challenges byte for byte) on the benchmark's own context"}
+
+
+def target_c3(zk, torch, dist, ctx, rank, G, args, hbm_peak, int_tops):
+    """BASELINE config 3 / the north_star target at every --gpus N: ONE degree-3 product of 2^28 entries in total, sharded over
+    the N ranks (strong scaling: the proof is the same for every N, so its hash must be too).  Timed like the headline
+    (tables resident, CUDA events on the library's stream, max over ranks), then -- outside the timed region -- every
+    rank's proof hash is compared and rank 0 has the ORACLE verify the proof (verifier replay + its own streamed evaluation
+    of the 2^28-entry tables at the challenges: oracle/cref.py verify_synth_proof)."""
+    import numpy as np
+    from zk_cryptography_b200 import _lib
+    n, degs, seed = args.target_n, [3], SEED + 3
+    tables = zk.Tables.synth(ctx, n, degs, seed)
+    stream = torch.cuda.ExternalStream(ctx.stream_handle(), device=torch.device("cuda", torch.cuda.current_device()))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    steps, warm = max(3, min(args.steps, 5)), 3
+    ps_us, rounds = [], []
+
+    def step(record):
+        tables.reset()
+        t0 = time.perf_counter()
+        s = tables.poly_sum()
+        t1 = time.perf_counter()
+        out = tables.prove(zk.PROTO_MULTI_PARTIAL, s)
+        if record:
+            ps_us.append((t1 - t0) * 1e6)
+            rounds.append(ctx.round_times())
+        return s, out
+
+    for _ in range(warm):
+        step(False)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = ctx.launch_count()
+    e0.record(stream)
+    for _ in range(steps):
+        s, (msgs, lens, chal) = step(True)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.launch_count() - launches0
+    if dist is not None:
+        tms = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    sha = proof_digest(zk.PROTO_MULTI_PARTIAL, msgs, lens, chal)
+    shas = [sha]
+    if dist is not None:
+        shas = [None] * G
+        dist.all_gather_object(shas, sha)
+    tables.free()
+    if rank != 0:
+        return None
+    avg_round = [sum(r[j] for r in rounds) / len(rounds) for j in range(n)]
+    rows = round_rows(n, degs, G, avg_round, sum(ps_us) / len(ps_us), hbm_peak, int_tops, gather_at=ctx.gather_entries() if G > 1 else None)
+    t_min = sum(r["min_us"] for r in rows)
+    out = {"workload": "c3: MultiComposedSumcheckProver calculate_poly_sum + prove_partial, one degree-3 product, 2^%d entries in total, sharded over %d GPU(s)" % (n, G),
+           "n_vars": n, "n_gpus": G, "scaling": "strong", "steps": steps, "warmup": warm, "ms": round(ms / steps, 4), "evals_per_s": (1 << n) * steps / (ms * 1e-3),
+           "gpu_launches": int(launches), "proof_sha256": sha, "ranks_agree": len(set(shas)) == 1,
+           "whole_step": {"min_ms": round(t_min * 1e-3, 4), "frac": round(t_min * 1e-3 / (ms / steps), 4)},
+           "rounds_at_or_above_0.60": sum(1 for r in rows if r["frac"] is not None and r["frac"] >= 0.6),
+           "per_round": rows, "per_round_clock": "host wall clock inside zksc_prove (device pass + transcript + bind; calculate_poly_sum added to round 0), averaged over the timed steps"}
+    if not args.no_cpu:
+        from oracle import cref
+        cref.set_threads(cref.max_threads())
+        t0 = time.perf_counter()
+        ok, why = cref.verify_synth_proof(n, 3, seed, zk.from_mont(s[0]), _lib.proof_to_bytes(zk.PROTO_MULTI_PARTIAL, msgs[0], lens[0]), zk.from_mont(chal[0]))
+        out["oracle_verified"] = {"ok": bool(ok), "detail": why, "seconds": round(time.perf_counter() - t0, 2), "threads": cref.max_threads(),
+                                  "how": "oracle verifier replays the transcript from the proof bytes (challenges, p(0)+p(1) chain), then evaluates the "
+                                         "three 2^%d-entry seeded tables at the challenges itself (streamed) and compares with the final claim" % n}
+    return out
+
+
 def run_b200(args):
     import numpy as np
     import torch
@@ -188,12 +322,17 @@ def run_b200(args):
     proto = {"multi_partial": zk.PROTO_MULTI_PARTIAL, "sumcheck": zk.PROTO_SUMCHECK}[wl["proto"]]
     seed = SEED + (rank * proofs_local if wl["proofs"] > 1 else 0)
     tables = zk.Tables.synth(ctx, n, wl["degs"], seed, n_proofs=proofs_local)
+    n_tables, n_evals = tables.n_tables, tables.n_evals
 
     stream = torch.cuda.ExternalStream(ctx.stream_handle(), device=torch.device("cuda", local_rank))
 
+    ps_clock = [0.0]
+
     def step():
         tables.reset()
+        t0 = time.perf_counter()
         s = tables.poly_sum()                     # calculate_poly_sum (round-0 pass; its evaluations are reused by prove)
+        ps_clock[0] = (time.perf_counter() - t0) * 1e6
         return tables.prove(proto, s)             # prove_partial: n rounds, transcript on the host
 
     def barrier():
@@ -218,11 +357,16 @@ def run_b200(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.start()
     e0.record(stream)
+    acc_rounds, acc_ps = None, 0.0
     for _ in range(args.steps):
         msgs, lens, chal = step()
+        rt = ctx.round_times()
+        acc_rounds = rt if acc_rounds is None else [a + b for a, b in zip(acc_rounds, rt)]
+        acc_ps += ps_clock[0]
     e1.record(stream)
     barrier()
     sampler.stop_flag = True
+    last_rounds, last_ps_us = [a / args.steps for a in acc_rounds], acc_ps / args.steps
     ms = e0.elapsed_time(e1)
     launches = ctx.launch_count() - launches0
     recs = ctx.timing_read(cap=1 << 16)
@@ -236,6 +380,11 @@ def run_b200(args):
 
     # ---- roofline of the dominant kernel (live CUDA events around every launch of the timed region) ----
     hbm_peak, peak_src, int_peak = read_peaks()
+    # the integer roof is measured NOW, on this GPU, by the library's own IMAD.WIDE microbenchmark (zksc_int_peak);
+    # profiles/int_peak.json (an earlier run of tools/ubench2.cu) is kept next to it for comparison only
+    live = ctx.int_peak() / 1e12
+    int_peak = {"imad_wide_Tops": round(live, 3), "source": "measured in this run: zksc_int_peak (8 independent mad.wide.u32 per thread, all SMs full)",
+                "recorded_earlier": (int_peak or {}).get("imad_wide_Tops")}
     groups = {}
     for r in recs:
         g = groups.setdefault((r["degree"], r["fold"]), dict(ms=0.0, bytes=0, modmuls=0, launches=0, largest=None))
@@ -286,12 +435,20 @@ def run_b200(args):
                                "frac": round(max(t_hbm, t_int) / (big_ms * 1e-3), 4)}
         # whole proof: every timed launch against its own binding roof
         t_min = sum(max(algorithmic_bytes(r) / (hbm_peak * 1e9), limb_products(r) / (int_peak["imad_wide_Tops"] * 1e12)) for r in recs)
-        roofline["whole_step"] = {"min_ms_per_step": round(t_min * 1e3 / args.steps, 5), "frac_of_step": round(t_min * 1e3 / ms, 4)}
+        roofline["whole_step"] = {"min_ms_per_step": round(t_min * 1e3 / args.steps, 5), "frac_of_step": round(t_min * 1e3 / ms, 4),
+                                  "note": "launch-timed rounds only; per_round below covers every round"}
+    proof_sha = proof_digest(proto, msgs, lens, chal)
+    per_round = None
+    if proofs_local == 1:
+        per_round = round_rows(n, wl["degs"], G if sharded else 1, last_rounds, last_ps_us, hbm_peak, int_peak["imad_wide_Tops"],
+                               gather_at=ctx.gather_entries() if sharded else None)
+        roofline["whole_step"]["all_rounds_min_ms"] = round(sum(r["min_us"] for r in per_round) * 1e-3, 5)
+        roofline["whole_step"]["all_rounds_frac"] = round(sum(r["min_us"] for r in per_round) * 1e-3 / (ms / args.steps), 4)
 
     # ---- e2e: host tables in pinned memory -> upload -> poly_sum + prove -> proof on the host ----
     e2e = None
     if not args.no_e2e:
-        host = torch.empty((proofs_local * tables.n_tables, (1 << n) // (G if sharded else 1), 4), dtype=torch.int64).pin_memory()
+        host = torch.empty((proofs_local * n_tables, (1 << n) // (G if sharded else 1), 4), dtype=torch.int64).pin_memory()
         hnp = host.numpy().view(np.uint64)
         hnp[...] = tables.read_local().reshape(hnp.shape)
         views = [hnp[i] for i in range(hnp.shape[0])]
@@ -361,6 +518,15 @@ def run_b200(args):
         if sequential["value"] > e2e["value"]:      # report whichever schedule is faster as the headline, keep both
             e2e = dict(sequential, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=d2h, pipelined={"value": e2e["value"], "ms_per_step": e2e["ms_per_step"]})
 
+    # ---- correctness under the same roof as the numbers (outside every timed region) ----
+    parity = None
+    if not args.no_cpu and proofs_local == 1:
+        parity = parity_check(zk, ctx, rank, G if sharded else 1, wl["degs"], wl["proto"], n=args.parity_n)
+    target = None
+    if args.workload == "c2" and not args.no_target:
+        tables.free()
+        target = target_c3(zk, torch, dist, ctx, rank, G, args, hbm_peak, int_peak["imad_wide_Tops"])
+
     if rank != 0:
         if dist is not None:
             dist.barrier()
@@ -370,21 +536,17 @@ def run_b200(args):
     # ---- CPU baseline (oracle port; N=1 only) ----
     cpu = None
     if G == 1 and not args.no_cpu:
-        cpu = cpu_baseline(args.workload, sample_n=args.cpu_n)
+        cpu = cpu_baseline(args.workload, sample_n=cpu_sample_n(args))
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": G, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": wl["scaling"] if wl["scaling"] != "replicas" else "weak",
         "vs_baseline": None, "dtype": "u32 limbs (256-bit modular integer, BLS12-381 Fr, Montgomery)", "data": "synthetic (seeded splitmix64 tables generated on the device)",
-        "config": {"workload": "%s: %s" % (args.workload, wl["desc"]), "n_vars": n, "degrees": wl["degs"], "proofs": proofs_total,
-                   "table_bytes_per_gpu": int(proofs_local * tables.n_tables * ((1 << n) // (G if sharded else 1)) * 32),
-                   "l2_policy": "inputs_exceed_l2" if proofs_local * tables.n_tables * ((1 << n) // (G if sharded else 1)) * 32 > 126e6 * 2 else "inputs_fit_l2_no_flush",
-                   "sharding": ("index mod %d (last-bound variables); per round %d field elements per rank exchanged %s" % (
-                                   G, tables.n_evals, "through NVLink peer memory inside the round kernel" if ctx.peer_exchange() else "by ncclAllGather + host sum")) if sharded else
-                               ("replicas" if G > 1 else "single GPU"),
-                   "proof_bytes": len(_lib.proof_to_bytes(proto, msgs[0], lens[0]))},
+        "config": workload_config(args.workload, G, len(_lib.proof_to_bytes(proto, msgs[0], lens[0]))),
+        "exchange": ("per round %d field elements per rank, %s" % (n_evals, "through NVLink peer memory inside the round kernels" if ctx.peer_exchange()
+                                                                     else "by ncclAllGather + host sum")) if sharded else None,
         "clocks": sampler.summary(), "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline, "int_roofline": int_roofline,
-        "cpu_baseline": cpu,
+        "cpu_baseline": cpu, "proof_sha256": proof_sha, "parity": parity, "per_round": per_round, "target_c3": target,
     }
     if args.round_profile:
         out["round_profile"] = round_profile
@@ -486,6 +648,28 @@ def run_gkr(args, wl, world, rank, local_rank, dist):
         dist.destroy_process_group()
 
 
+def workload_config(workload, G, proof_bytes):
+    """The `config` object of a line: a function of the workload and the GPU count only, so that both arms print the same one."""
+    wl = WORKLOADS[workload]
+    lgG = int(math.log2(G))
+    sharded = wl["scaling"] in ("weak", "strong") and wl["proofs"] == 1 and G > 1
+    n = wl["n"] + (lgG if wl["scaling"] == "weak" else 0)
+    proofs_local = wl["proofs"] // G if wl["proofs"] > 1 else 1
+    per_gpu = proofs_local * sum(wl["degs"]) * ((1 << n) // (G if sharded else 1)) * 32
+    return {"workload": "%s: %s" % (workload, wl["desc"]), "n_vars": n, "degrees": wl["degs"], "proofs": wl["proofs"], "table_bytes_per_gpu": int(per_gpu),
+            "l2_policy": "inputs_exceed_l2" if per_gpu > 126e6 * 2 else "inputs_fit_l2_no_flush",
+            "sharding": ("index mod %d (the variables bound last); per-round exchange of the partial evaluations" % G) if sharded else ("replicas" if G > 1 else "single GPU"),
+            "proof_bytes": int(proof_bytes)}
+
+
+def cpu_sample_n(args):
+    """n_vars of the CPU sample: the workload's own size for c1 / c2 (a step is ~2 s on 16 threads: same config as the GPU
+    arm), a bounded sample (n = 22, stated in the line) for the workloads that would take minutes per step (c3, c5)."""
+    if args.cpu_n is not None:
+        return args.cpu_n
+    return WORKLOADS[args.workload]["n"] if args.workload in ("c1", "c2") else 22
+
+
 def cpu_workload(workload, sample_n):
     import numpy as np
     from oracle import cref
@@ -526,7 +710,7 @@ def run_reference(args):
         return
     if WORKLOADS[args.workload]["proto"] == "gkr":
         return run_reference_gkr(args)
-    cref, wl, n, tabs, proto = cpu_workload(args.workload, args.cpu_n)
+    cref, wl, n, tabs, proto = cpu_workload(args.workload, cpu_sample_n(args))
     th = cref.max_threads()
     cref.set_threads(th)
 
@@ -534,19 +718,24 @@ def run_reference(args):
         s = cref.poly_sum(n, wl["degs"], tabs)
         cref.prove(proto, n, wl["degs"], tabs, s)
 
+    pbytes, _ = cref.prove(proto, n, wl["degs"], tabs, cref.poly_sum(n, wl["degs"], tabs)) if args.warmup == 0 else (None, None)
     for _ in range(args.warmup):
-        step()
+        s0 = cref.poly_sum(n, wl["degs"], tabs)
+        pbytes, _ = cref.prove(proto, n, wl["degs"], tabs, s0)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step()
     dt = time.perf_counter() - t0
     value = (1 << n) * args.steps / dt
-    sample = "oracle/zkref.c on %d OpenMP threads; each step = calculate_poly_sum + prove at n_vars=%d (bounded sample of %s; cost is linear in 2^n)" % (th, n, args.workload)
+    full = n == wl["n"]
+    sample = "oracle/zkref.c on %d OpenMP threads; each step = calculate_poly_sum + prove at n_vars=%d (%s)" % (
+        th, n, "the workload's own size" if full else "bounded sample of %s; cost is linear in 2^n" % args.workload)
     out = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt * 1e3 / args.steps, "higher_is_better": True, "scaling": WORKLOADS[args.workload]["scaling"] if WORKLOADS[args.workload]["scaling"] != "replicas" else "weak",
         "vs_baseline": None, "dtype": "u64 limbs (256-bit modular integer, BLS12-381 Fr, Montgomery)", "data": "synthetic (same seeded tables)",
-        "config": {"workload": "%s: %s" % (args.workload, WORKLOADS[args.workload]["desc"]), "n_vars": n, "degrees": wl["degs"]},
+        "config": workload_config(args.workload, args.gpus, len(pbytes) * (wl["n"] + (int(math.log2(args.gpus)) if wl["scaling"] == "weak" else 0)) // max(n, 1)),
+        "cpu_sample_n_vars": n,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": th, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -594,7 +783,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--cpu-n", type=int, default=22, help="n_vars of the bounded CPU sample")
+    ap.add_argument("--cpu-n", type=int, default=None, help="n_vars of the CPU sample (default: the workload's own n for c1/c2, 22 otherwise)")
+    ap.add_argument("--parity-n", type=int, default=20, help="n_vars of the out-of-band parity proof against the oracle")
+    ap.add_argument("--target-n", type=int, default=28, help="n_vars of the target_c3 leg (BASELINE config 3: 28)")
+    ap.add_argument("--no-target", action="store_true", help="skip the target_c3 leg (degree 3, 2^28 entries, strong scaling)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--round-profile", action="store_true", help="add the per-launch-shape average durations to the JSON line")

@@ -57,6 +57,9 @@ int zksc_ctx_rank(const zksc_ctx* ctx, int* rank, int* n_ranks);
 /* 1 when the per-round partial evaluations of a sharded context travel through peer memory (CUDA IPC over
  * NVLink) inside the round kernel, 0 when they go through ncclAllGather + a host sum (single rank: 0). */
 int zksc_ctx_peer_exchange(const zksc_ctx* ctx);
+/* Sharded contexts: the table size (entries IN TOTAL over all ranks) at which the shards are gathered and the remaining rounds run
+ * replicated on every rank, without a per-round exchange (1 on a single-rank context). */
+uint64_t zksc_ctx_gather_entries(const zksc_ctx* ctx);
 int zksc_ctx_synchronize(zksc_ctx* ctx);
 /* Measurement hooks (bench.py; no reference counterpart).  zksc_ctx_stream: the cudaStream_t every kernel
  * of this context is launched on (so callers can record their own events on it).  zksc_ctx_launch_count:
@@ -69,6 +72,12 @@ unsigned long long zksc_ctx_launch_count(const zksc_ctx* ctx);
 int zksc_ctx_timing(zksc_ctx* ctx, int enable);
 int zksc_ctx_timing_read(zksc_ctx* ctx, uint32_t cap, uint32_t* n_out, float* ms, uint32_t* degree, uint32_t* fold, uint64_t* pairs,
                          uint64_t* proofs);
+/* Host wall time, in microseconds, of every round of the latest zksc_prove on this context (device pass + transcript + bind:
+ * the rounds add up to the call); at most cap values, *n_out = how many. */
+int zksc_ctx_round_times(const zksc_ctx* ctx, uint32_t cap, uint32_t* n_out, double* us);
+/* The integer-multiply roof of this device, measured now: 32 x 32 -> 64 bit multiply-adds (IMAD.WIDE.U32, what every limb product of
+ * the field arithmetic compiles to) per second with all SMs full and nothing else in the loop (about 1 ms of GPU time). */
+int zksc_int_peak(zksc_ctx* ctx, double* limb_products_per_second);
 
 /* ---- device-resident evaluation tables --------------------------------------------------------
  * A `zksc_tables` is `n_proofs` independent instances of  sum_p prod_k f_{p,k}  : for each proof,

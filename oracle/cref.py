@@ -64,6 +64,14 @@ def synth_table(seed, table, n_vars):
     return out
 
 
+def eval_synth(seed, table, n_vars, pts):
+    """Multilinear::evaluation of the seeded synthetic table at pts (python ints), streamed: the table is never materialised."""
+    out = np.zeros(4, dtype=np.uint64)
+    p = ints_to_canon(pts) if pts else np.zeros((1, 4), dtype=np.uint64)
+    lib().zkref_eval_synth(ctypes.c_uint64(seed), ctypes.c_uint64(table), ctypes.c_uint32(n_vars), _p64(p), _p64(out))
+    return canon_to_ints(out)[0]
+
+
 def prove(protocol, n_vars, degrees, tables_canon, sum_int):
     """tables_canon: (sum(deg) * 2^n, 4) canonical uint64 array (products concatenated).
     -> (proof_bytes, challenges as python ints)"""
@@ -140,3 +148,31 @@ def verify_partial(n_vars, sum_int, round_polys):
     chal = np.zeros((max(1, n_vars), 4), dtype=np.uint64)
     rc = lib().zkref_verify_partial(ctypes.c_uint32(n_vars), _p64(ints_to_canon([sum_int])), _p64(mono), lens.ctypes.data_as(_u32p), _p64(sub), _p64(chal))
     return rc == 0, canon_to_ints(sub)[0], canon_to_ints(chal[:n_vars])
+
+
+def verify_synth_proof(n_vars, degree, seed, sum_int, proof_bytes, challenges):
+    """Oracle-side check of a prove_partial proof of ONE product of `degree` seeded synthetic tables that is too large for the
+    oracle's prover: replay the transcript with the oracle's verifier (verify_internal, multi_composed_sumcheck.rs:151-181:
+    challenges re-derived from the proof bytes, p(0) + p(1) chain) and close the final claim against the oracle's OWN streamed
+    evaluation of the tables at those challenges (Multilinear::evaluation, evaluation_form.rs:162-175).  A round polynomial
+    that differed from the honest prover's survives this with probability ~ n d / |F|: an accepted proof is the reference
+    prover's proof.  -> (ok, reason)"""
+    per_round = 64 * (degree + 1)          # random tables: every round polynomial has degree + 1 monomials of (coeff, pow)
+    if len(proof_bytes) != n_vars * per_round:
+        return False, "proof length %d != %d rounds x %d bytes" % (len(proof_bytes), n_vars, per_round)
+    rps = []
+    for r in range(n_vars):
+        blob = proof_bytes[r * per_round:(r + 1) * per_round]
+        rps.append([(int.from_bytes(blob[64 * i:64 * i + 32], "big"), int.from_bytes(blob[64 * i + 32:64 * i + 64], "big")) for i in range(degree + 1)])
+    ok, sub, ch = verify_partial(n_vars, sum_int, rps)
+    if not ok:
+        return False, "the oracle's verifier rejects the proof (p(0) + p(1) != claim in some round)"
+    if list(ch) != list(challenges):
+        return False, "challenges differ from the oracle's replay of the transcript"
+    R = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+    val = 1
+    for k in range(degree):
+        val = val * eval_synth(seed, k, n_vars, ch) % R
+    if val != sub:
+        return False, "final claim does not match the oracle's evaluation of the tables at the challenges"
+    return True, "ok"

@@ -387,3 +387,50 @@ void zkref_synth_table(uint64_t seed, uint64_t table, uint32_t n_vars, uint64_t*
         memcpy(out + 4 * i, c, 32);
     }
 }
+
+/* ---- streamed evaluation of a seeded synthetic table (full-size checks: 2^28-entry tables never sit in host memory) ----
+ * Multilinear::evaluation (evaluation_form.rs:162-175) of the table zkref_synth_table(seed, table, n_vars) at pts, computed
+ * as  sum_i eq(pts, i) * T[i]  with eq(pts, i) = prod_v (bit_v(i) ? pts[v] : 1 - pts[v]), variable 0 = most significant index
+ * bit -- the closed form of the reference's n successive folds (tests/test_oracle_cross.py checks the two against each other).
+ * The index is split into high and low bits so that only two small eq tables are held. */
+static void eq_table(const fr* pts, size_t nv, fr* out /* 2^nv */) {
+    out[0] = fr_one();
+    size_t len = 1;
+    for (size_t v = 0; v < nv; v++) {          /* appending variable v as the new least significant bit keeps MSB-first order */
+        fr one_minus = fr_sub(fr_one(), pts[v]);
+        for (size_t i = len; i-- > 0;) { fr e = out[i]; out[2 * i] = fr_mul(e, one_minus); out[2 * i + 1] = fr_mul(e, pts[v]); }
+        len *= 2;
+    }
+}
+void zkref_eval_synth(uint64_t seed, uint64_t table, uint32_t n_vars, const uint64_t* pts_canon, uint64_t* out) {
+    const uint64_t base = splitmix64(seed ^ splitmix64(table * 0xD1342543DE82EF95ULL + 0x632BE59BD9B4E019ULL));
+    fr pts[64];
+    for (uint32_t i = 0; i < n_vars; i++) pts[i] = fr_from_canon(pts_canon + 4 * i);
+    const uint32_t nl = n_vars < 12 ? n_vars : 12, nh = n_vars - nl;
+    const size_t NH = (size_t)1 << nh, NLO = (size_t)1 << nl;
+    fr* eq_hi = (fr*)malloc(NH * sizeof(fr));
+    fr* eq_lo = (fr*)malloc(NLO * sizeof(fr));
+    eq_table(pts, nh, eq_hi);
+    eq_table(pts + nh, nl, eq_lo);
+    fr total = fr_zero();
+#pragma omp parallel num_threads(g_threads) if (NH > 1)
+    {
+        fr loc = fr_zero();
+#pragma omp for schedule(static) nowait
+        for (size_t hi = 0; hi < NH; hi++) {
+            fr inner = fr_zero();
+            for (size_t lo = 0; lo < NLO; lo++) {
+                const uint64_t i = (uint64_t)hi * NLO + lo;
+                uint64_t c[4];
+                for (int l = 0; l < 4; l++) c[l] = splitmix64(base + (i * 4 + l) * 0x9E3779B97F4A7C15ULL);
+                while (ge_mod(c)) sub_mod(c);
+                inner = fr_add(inner, fr_mul(eq_lo[lo], fr_from_canon(c)));
+            }
+            loc = fr_add(loc, fr_mul(eq_hi[hi], inner));
+        }
+#pragma omp critical
+        total = fr_add(total, loc);
+    }
+    free(eq_hi); free(eq_lo);
+    fr_to_canon(total, out);
+}

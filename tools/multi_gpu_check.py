@@ -6,7 +6,8 @@
 Every rank builds its shard (index mod G) of the seeded synthetic tables, the G ranks prove together
 (per-round exchange of the partial evaluations, residual gather for the last log2 G rounds), and rank 0
 compares the proof bytes and challenges with (1) the same proof computed on ONE GPU by an unsharded context
-and (2) the CPU oracle, for several shapes.  Prints one line per case and "MULTI-GPU PARITY OK".
+and (2) the CPU oracle -- its prover byte for byte up to 2^24 entries, its verifier plus its own evaluation of the tables
+at 2^26 and 2^28 (degree 3: BASELINE config 3).  ZKSC_CHECK_MAX_N caps the sizes.  Prints one line per case and "MULTI-GPU PARITY OK".
 """
 import os
 import sys
@@ -20,9 +21,11 @@ sys.path.insert(0, ROOT)
 import zk_cryptography_b200 as zk  # noqa: E402
 from zk_cryptography_b200._lib import proof_to_bytes  # noqa: E402
 
-CASES = [  # (n_vars, degrees, seed, oracle?)
-    (1, [1], 5, True), (3, [2], 6, True), (4, [2, 3], 7, True), (10, [1], 8, True), (12, [2, 2], 9, True), (13, [3], 10, True),
-    (14, [5, 1], 11, True), (18, [2], 12, False), (20, [3], 13, False), (22, [2, 2], 14, False),
+CASES = [  # (n_vars, degrees, seed, check): "bytes" = the oracle's prover, byte for byte; "verify" = the oracle's verifier + its own
+    # streamed evaluation of the tables at the challenges (tests/test_gpu_parity_large.py oracle_verifies); both also compare with one GPU
+    (1, [1], 5, "bytes"), (3, [2], 6, "bytes"), (4, [2, 3], 7, "bytes"), (10, [1], 8, "bytes"), (12, [2, 2], 9, "bytes"), (13, [3], 10, "bytes"),
+    (14, [5, 1], 11, "bytes"), (18, [2], 12, "bytes"), (20, [3], 13, "bytes"), (22, [2, 2], 14, "bytes"), (24, [2], 15, "bytes"),
+    (26, [3], 16, "verify"), (28, [3], 17, "verify"),
 ]
 
 
@@ -42,8 +45,9 @@ def main():
         print("peer-memory exchange:", ctx.peer_exchange(), flush=True)
     lg = world.bit_length() - 1
     ok = True
-    for n, degs, seed, use_oracle in CASES:
-        if n < lg:
+    max_n = int(os.environ.get("ZKSC_CHECK_MAX_N", "28"))
+    for n, degs, seed, check in CASES:
+        if n < lg or n > max_n:
             continue
         t = zk.Tables.synth(ctx, n, degs, seed)
         s = t.poly_sum()
@@ -61,13 +65,24 @@ def main():
             want = proof_to_bytes(zk.PROTO_MULTI_PARTIAL, m1[0], l1[0])
             t1.free()
             good = (got == want) and np.array_equal(s, s1) and np.array_equal(chal, c1) and same_again
-            if use_oracle:
-                from oracle import cref
+            from oracle import cref
+            cref.set_threads(cref.max_threads())
+            if check == "bytes":
                 tabs = np.concatenate([cref.synth_table(seed, k, n) for k in range(sum(degs))])
                 osum = cref.poly_sum(n, degs, tabs)
                 obytes, och = cref.prove(2, n, degs, tabs, osum)
                 good = good and zk.from_mont(s[0]) == osum and got == obytes and zk.from_mont(chal[0]) == och
-            print("case n=%d degs=%s G=%d: %s (%d proof bytes)" % (n, degs, world, "ok" if good else "MISMATCH", len(got)), flush=True)
+            else:
+                sys.path.insert(0, os.path.join(ROOT, "tests"))
+                from test_gpu_parity_large import oracle_verifies
+                try:
+                    oracle_verifies(n, degs, seed, zk.from_mont(s[0]), got, zk.from_mont(chal[0]))
+                except AssertionError as e:
+                    print("oracle verification failed:", e, flush=True)
+                    good = False
+            import hashlib
+            print("case n=%d degs=%s G=%d [%s]: %s (%d proof bytes, sha256 %s)" % (n, degs, world, check, "ok" if good else "MISMATCH", len(got),
+                                                                                 hashlib.sha256(got).hexdigest()[:16]), flush=True)
             ok = ok and good
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)

@@ -54,6 +54,9 @@ def lib():
         "zksc_ctx_peer_exchange": (ctypes.c_int, [vp]),
         "zksc_ctx_timing": (ctypes.c_int, [vp, ctypes.c_int]),
         "zksc_ctx_timing_read": (ctypes.c_int, [vp, ctypes.c_uint32, _u32p, ctypes.POINTER(ctypes.c_float), _u32p, _u32p, _u64p, _u64p]),
+        "zksc_ctx_gather_entries": (ctypes.c_uint64, [vp]),
+        "zksc_ctx_round_times": (ctypes.c_int, [vp, ctypes.c_uint32, _u32p, ctypes.POINTER(ctypes.c_double)]),
+        "zksc_int_peak": (ctypes.c_int, [vp, ctypes.POINTER(ctypes.c_double)]),
         "zksc_tables_reupload": (ctypes.c_int, [vp, ctypes.POINTER(_u64p), ctypes.c_int]),
         "zksc_tables_reupload_begin": (ctypes.c_int, [vp, ctypes.POINTER(_u64p), ctypes.c_int]),
         "zksc_tables_reupload_end": (ctypes.c_int, [vp]),
@@ -215,6 +218,22 @@ class Context:
         self.check(lib().zksc_ctx_timing_read(self._h, cap, ctypes.byref(n), ms.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), p32(deg), p32(fold),
                                               p64(pairs), p64(proofs)))
         return [dict(ms=float(ms[i]), degree=int(deg[i]), fold=int(fold[i]), pairs=int(pairs[i]), proofs=int(proofs[i])) for i in range(n.value)]
+
+    def gather_entries(self):
+        return int(lib().zksc_ctx_gather_entries(self._h))
+
+    def round_times(self, cap=64):
+        """-> host wall time (us) of every round of the latest prove on this context."""
+        n = ctypes.c_uint32()
+        us = np.zeros(cap, dtype=np.float64)
+        self.check(lib().zksc_ctx_round_times(self._h, cap, ctypes.byref(n), us.ctypes.data_as(ctypes.POINTER(ctypes.c_double))))
+        return [float(x) for x in us[:n.value]]
+
+    def int_peak(self):
+        """-> measured IMAD.WIDE.U32 rate of this device, limb products per second."""
+        v = ctypes.c_double()
+        self.check(lib().zksc_int_peak(self._h, ctypes.byref(v)))
+        return v.value
 
     def close(self):
         if self._h:

@@ -270,13 +270,34 @@ class SparseUnivariatePolynomial:  # sparse_univariate.rs
 
 
 # ---- sumcheck/src/sumcheck.rs ---------------------------------------------------------------------
+def _pack_rounds(rows, per=1):
+    """Public proof fields -> the (msgs, lens) arrays of the C ABI.  rows: per round, the list of canonical ints the round
+    message holds (evaluations, or coeff/pow pairs flattened when per = 2).  The proof objects keep NO hidden copy of the
+    prover's output: what a verifier checks (and what to_bytes serialises) is exactly what the public fields say, as in the
+    reference, whose verifiers read proof.round_polys / proof.univariate_poly."""
+    n = len(rows)
+    stride = max([len(r) for r in rows] + [per])
+    msgs = np.zeros((n, stride, 4), dtype=np.uint64)
+    lens = np.zeros(n, dtype=np.uint32)
+    for i, r in enumerate(rows):
+        if len(r) % per:
+            raise ZkscError(-3, "malformed round message")
+        if r:
+            msgs[i, :len(r)] = to_mont([int(v) for v in r])
+        lens[i] = len(r) // per
+    return msgs, lens
+
+
 class SumcheckProof:  # :11-15
-    def __init__(self, poly, s, univariate_poly, raw):
-        self.poly, self.sum, self.univariate_poly, self._raw = poly, s, univariate_poly, raw
+    def __init__(self, poly, s, univariate_poly):
+        self.poly, self.sum, self.univariate_poly = poly, s, univariate_poly
+
+    def _rounds(self):
+        return _pack_rounds([u.to_ints() for u in self.univariate_poly])
 
     def to_bytes(self):
         """concatenation of the per-round messages as absorbed by the transcript"""
-        return _lib.proof_to_bytes(PROTO_SUMCHECK, self._raw[0], self._raw[1])
+        return _lib.proof_to_bytes(PROTO_SUMCHECK, *self._rounds())
 
 
 class Sumcheck:
@@ -296,11 +317,11 @@ class Sumcheck:
         finally:
             t.free()
         unis = [Multilinear(msgs[0, r, :2]) for r in range(self.poly.n_vars)]
-        return SumcheckProof(self.poly, self.sum, unis, (msgs[0], lens[0])), from_mont(chal[0]) if self.poly.n_vars else []
+        return SumcheckProof(self.poly, self.sum, unis), from_mont(chal[0]) if self.poly.n_vars else []
 
     def verify(self, proof):  # :63-95
         try:
-            sub, chal = _lib.verify_rounds(PROTO_SUMCHECK, to_mont(proof.sum), proof._raw[0], proof._raw[1])
+            sub, chal = _lib.verify_rounds(PROTO_SUMCHECK, to_mont(proof.sum), *proof._rounds())
         except ZkscError as e:
             if e.code == -7:
                 return False
@@ -310,11 +331,14 @@ class Sumcheck:
 
 # ---- sumcheck/src/composed/composed_sumcheck.rs ------------------------------------------------------
 class ComposedSumcheckProof:  # :15-18
-    def __init__(self, poly, round_polys, raw):
-        self.poly, self.round_polys, self._raw = poly, round_polys, raw
+    def __init__(self, poly, round_polys):
+        self.poly, self.round_polys = poly, round_polys
+
+    def _rounds(self):
+        return _pack_rounds(self.round_polys)
 
     def to_bytes(self):
-        return _lib.proof_to_bytes(PROTO_COMPOSED, self._raw[0], self._raw[1])
+        return _lib.proof_to_bytes(PROTO_COMPOSED, *self._rounds())
 
 
 class ComposedSumcheck:
@@ -340,11 +364,11 @@ class ComposedSumcheck:
             t.free()
         n, d = self.poly.n_vars(), self.poly.max_degree()
         rps = [from_mont(msgs[0, r, :d + 1]) for r in range(n)]
-        return ComposedSumcheckProof(self.poly, rps, (msgs[0], lens[0])), from_mont(chal[0]) if n else []
+        return ComposedSumcheckProof(self.poly, rps), from_mont(chal[0]) if n else []
 
     def verify(self, proof, s):  # :69-95
         try:
-            sub, chal = _lib.verify_rounds(PROTO_COMPOSED, to_mont(s), proof._raw[0], proof._raw[1])
+            sub, chal = _lib.verify_rounds(PROTO_COMPOSED, to_mont(s), *proof._rounds())
         except ZkscError as e:
             if e.code == -7:
                 return False
@@ -356,11 +380,14 @@ class ComposedSumcheck:
 class MultiComposedProof:
     """ComposedSumcheckProof of multi_composed_sumcheck.rs:12-16 (round_polys: sparse polynomials, sum)."""
 
-    def __init__(self, round_polys, s, raw):
-        self.round_polys, self.sum, self._raw = round_polys, s, raw
+    def __init__(self, round_polys, s):
+        self.round_polys, self.sum = round_polys, s
+
+    def _rounds(self):
+        return _pack_rounds([[v for cp in rp.monomial for v in cp] for rp in self.round_polys], per=2)
 
     def to_bytes(self):  # :24-32
-        return _lib.proof_to_bytes(PROTO_MULTI_PARTIAL, self._raw[0], self._raw[1])
+        return _lib.proof_to_bytes(PROTO_MULTI_PARTIAL, *self._rounds())
 
 
 class SubClaim:  # :18-22
@@ -390,7 +417,7 @@ class MultiComposedSumcheckProver:
             k = int(lens[0, r])
             v = from_mont(msgs[0, r, :2 * k]) if k else []
             rps.append(SparseUnivariatePolynomial([(v[2 * i], v[2 * i + 1]) for i in range(k)]))
-        return MultiComposedProof(rps, s % _lib.R_MOD, (msgs[0], lens[0])), (from_mont(chal[0]) if n else [])
+        return MultiComposedProof(rps, s % _lib.R_MOD), (from_mont(chal[0]) if n else [])
 
     @staticmethod
     def prove(poly, s):  # :47-54
@@ -405,7 +432,7 @@ class MultiComposedSumcheckVerifier:
     @staticmethod
     def verify(poly, proof):  # :126-142
         prefix = b"".join(p.to_bytes() for p in poly)  # composed_poly_to_bytes
-        sub, chal = _lib.verify_rounds(PROTO_MULTI_FULL, to_mont(proof.sum), proof._raw[0], proof._raw[1], prefix)
+        sub, chal = _lib.verify_rounds(PROTO_MULTI_FULL, to_mont(proof.sum), *proof._rounds(), prefix)
         t = _upload(poly)
         try:
             val = from_mont(t.evaluate(chal)[0]) if len(chal) else from_mont(t.poly_sum()[0])
@@ -415,5 +442,5 @@ class MultiComposedSumcheckVerifier:
 
     @staticmethod
     def verify_partial(proof):  # :143-149
-        sub, chal = _lib.verify_rounds(PROTO_MULTI_PARTIAL, to_mont(proof.sum), proof._raw[0], proof._raw[1])
+        sub, chal = _lib.verify_rounds(PROTO_MULTI_PARTIAL, to_mont(proof.sum), *proof._rounds())
         return SubClaim(from_mont(sub), from_mont(chal) if len(chal) else [])

@@ -183,6 +183,7 @@ struct zksc_ctx {
     bool staged_fold = false;     // ... also for the fused fold+evaluate rounds (ZKSC_STAGED_FOLD=1; slower today: DESIGN.md)
     std::string err;
     int rank = 0, n_ranks = 1;
+    unsigned long long gather_entries = 1;   // sharded contexts: the shards are gathered when a table is down to this many entries IN TOTAL
     // persistent tail kernel (tail_kernel.cuh): mailbox + result units in pinned, device-mapped host memory
     bool fuse_products = true;           // ZKSC_NO_FUSE=1: one launch per product even when the degrees agree
     bool tail_enabled = true;            // ZKSC_NO_TAIL=1: every round is its own launch
@@ -213,6 +214,7 @@ struct zksc_ctx {
     struct LaunchRec { cudaEvent_t e0, e1; unsigned int degree, fold; unsigned long long pairs, proofs; };
     std::vector<LaunchRec> recs;       // used entries: [0, n_recs)
     size_t n_recs = 0;
+    std::vector<double> round_us;      // host wall time of every round of the latest zksc_prove (evaluations + transcript + bind)
 };
 
 struct zksc_tables {
@@ -396,6 +398,8 @@ extern "C" int zksc_ctx_rank(const zksc_ctx* ctx, int* rank, int* n_ranks) {
 
 extern "C" int zksc_ctx_peer_exchange(const zksc_ctx* ctx) { return (ctx && ctx->p2p) ? 1 : 0; }
 
+extern "C" uint64_t zksc_ctx_gather_entries(const zksc_ctx* ctx) { return ctx ? (uint64_t)ctx->gather_entries : 0; }
+
 extern "C" void* zksc_ctx_stream(zksc_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
 extern "C" unsigned long long zksc_ctx_launch_count(const zksc_ctx* ctx) { return ctx ? ctx->launches : 0; }
@@ -427,6 +431,61 @@ extern "C" int zksc_ctx_timing_read(zksc_ctx* ctx, uint32_t cap, uint32_t* n_out
     }
     *n_out = n;
     ctx->n_recs = 0;
+    return ZKSC_OK;
+}
+
+extern "C" int zksc_ctx_round_times(const zksc_ctx* ctx, uint32_t cap, uint32_t* n_out, double* us) {
+    if (!ctx || !n_out) return ZKSC_ERR_STATE;
+    uint32_t n = 0;
+    for (; n < cap && n < ctx->round_us.size(); n++)
+        if (us) us[n] = ctx->round_us[n];
+    *n_out = n;
+    return ZKSC_OK;
+}
+
+// The integer roof of this device, measured: 8 independent 32 x 32 -> 64 multiply-adds (IMAD.WIDE.U32, the instruction every limb
+// product of fr.cuh compiles to) per thread and iteration, nothing else in the loop, all SMs full.
+__global__ void __launch_bounds__(256) int_peak_kernel(uint32_t* out, int iters, uint32_t seed) {
+    uint32_t a = threadIdx.x * 2654435761u + seed;
+    uint32_t c[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) c[i] = a + i;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            asm volatile("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.u32 %1, %2, %3, %1;" : "+r"(c[2 * i]), "+r"(c[2 * i + 1]) : "r"(c[(2 * i + 3) & 15]), "r"(c[(2 * i + 6) & 15]));
+    }
+    uint32_t x = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) x ^= c[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x;
+}
+extern "C" int zksc_int_peak(zksc_ctx* ctx, double* limb_products_per_second) {
+    if (!ctx || !limb_products_per_second) return ZKSC_ERR_STATE;
+    CK(cudaSetDevice(ctx->device));
+    TRY(quiesce(ctx));
+    const int blocks = ctx->sms * 8, iters = 4096;
+    uint32_t* buf = nullptr;
+    CK(cudaMallocAsync((void**)&buf, (size_t)blocks * 256 * sizeof(uint32_t), ctx->stream));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 6; rep++) {          // the first one warms up
+        CK(cudaEventRecord(e0, ctx->stream));
+        int_peak_kernel<<<blocks, 256, 0, ctx->stream>>>(buf, iters, 1u);
+        CK(cudaEventRecord(e1, ctx->stream));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    ctx->launches += 6;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFreeAsync(buf, ctx->stream);
+    CK(cudaGetLastError());
+    *limb_products_per_second = (double)blocks * 256 * iters * 8 / (best * 1e-3);
     return ZKSC_OK;
 }
 
@@ -535,6 +594,7 @@ extern "C" int zksc_comm_init(zksc_ctx* ctx, int n_ranks, int rank, const uint8_
     if (r != ncclSuccess) FAIL(ZKSC_ERR_COMM, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r));
     ctx->rank = rank;
     ctx->n_ranks = n_ranks;
+    ctx->gather_entries = (unsigned long long)n_ranks;
     // result buffers are sized per rank count: drop them so the next use re-allocates
     cudaFree(ctx->results_dev); cudaFree(ctx->results_send); cudaFreeHost(ctx->results_host);
     ctx->results_dev = nullptr; ctx->results_send = nullptr; ctx->results_host = nullptr; ctx->results_cap = 0;
@@ -814,7 +874,11 @@ extern "C" int zksc_tables_fill_outer(zksc_tables* t, uint32_t table, int mul, c
     if (!t) return ZKSC_ERR_STATE;
     zksc_ctx* ctx = t->ctx;
     if (!a || !b || !na || !nb) FAIL(ZKSC_ERR_SHAPE, "empty operand");
-    if (na * nb != (1ull << t->n_vars)) FAIL(ZKSC_ERR_SHAPE, "add_distinct / mul_distinct: the operand sizes must multiply to 2^n_vars");
+    {
+        unsigned long long prod = 0;
+        if ((na & (na - 1)) || (nb & (nb - 1)) || __builtin_umulll_overflow(na, nb, &prod) || prod != (1ull << t->n_vars))
+            FAIL(ZKSC_ERR_SHAPE, "add_distinct / mul_distinct: the operand sizes must be powers of two that multiply to 2^n_vars");
+    }
     TRY(fill_prepare(t, table));
     DevBuf da(ctx), db(ctx);
     CK(dev_alloc(ctx, (void**)&da.p, na * sizeof(Fr)));
@@ -1532,6 +1596,7 @@ extern "C" int zksc_prove(zksc_tables* t, int protocol, const uint64_t* sums, ui
         explicit PoolSession(zksc_ctx* ctx, bool on) : c(on ? ctx : nullptr) { if (c) { c->pool->begin(); c->pool_active = true; } }
         ~PoolSession() { if (c) { c->pool_active = false; c->pool->end(); } }
     } pool_session(ctx, ctx->pool != nullptr && B >= kPoolMinProofs);
+    ctx->round_us.assign(n, 0.0);
     for (uint32_t round = 0; round < n; round++) {
         const auto p0 = std::chrono::steady_clock::now();
         TRY(round_evals_impl(t, ev.data(), ZKSC_MAX_DEGREE + 1));
@@ -1572,8 +1637,9 @@ extern "C" int zksc_prove(zksc_tables* t, int protocol, const uint64_t* sums, ui
         });
         const auto p2 = std::chrono::steady_clock::now();
         TRY(zksc_bind(t, chal.data()));                               // :103-105 (deferred, fused)
+        const auto p3 = std::chrono::steady_clock::now();
+        ctx->round_us[round] = std::chrono::duration<double, std::micro>(p3 - p0).count();
         if (ctx->profile) {
-            const auto p3 = std::chrono::steady_clock::now();
             auto us = [](auto a, auto b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
             fprintf(stderr, "[zksc profile] round %2u: evals %7.1f us (launch %6.1f, wait %7.1f)  transcript %5.1f  bind %5.1f\n", round, us(p0, p1),
                     ctx->prof_launch, ctx->prof_wait, us(p1, p2), us(p2, p3));
@@ -1584,10 +1650,11 @@ extern "C" int zksc_prove(zksc_tables* t, int protocol, const uint64_t* sums, ui
 
 extern "C" int zksc_proof_to_bytes(int protocol, uint32_t n_vars, uint32_t msg_stride, const uint64_t* round_msgs, const uint32_t* round_len,
                                    uint8_t* out, size_t* out_len) {
-    if (!round_msgs || !round_len || !out_len) return ZKSC_ERR_SHAPE;
+    if (!out_len || (n_vars && (!round_msgs || !round_len))) return ZKSC_ERR_SHAPE;
     const uint32_t per = (protocol == ZKSC_PROTO_MULTI_PARTIAL || protocol == ZKSC_PROTO_MULTI_FULL) ? 2 : 1;
     size_t n = 0;
     for (uint32_t r = 0; r < n_vars; r++) {
+        if ((uint64_t)round_len[r] * per > msg_stride) return ZKSC_ERR_SHAPE;   // a round message never exceeds its slot
         for (uint32_t i = 0; i < round_len[r] * per; i++) {
             if (out) host::to_be_bytes(load_h(round_msgs + ((size_t)r * msg_stride + i) * 4), out + n);
             n += 32;
@@ -1600,7 +1667,13 @@ extern "C" int zksc_proof_to_bytes(int protocol, uint32_t n_vars, uint32_t msg_s
 extern "C" int zksc_verify_rounds(int protocol, uint32_t n_vars, uint32_t msg_stride, const uint64_t* sum, const uint64_t* round_msgs,
                                   const uint32_t* round_len, const uint8_t* absorbed_prefix, size_t prefix_len, uint64_t* subclaim_sum,
                                   uint64_t* challenges) {
-    if (!round_msgs || !round_len || !sum || !subclaim_sum || !challenges) return ZKSC_ERR_SHAPE;
+    if (!sum || !subclaim_sum || !challenges || (n_vars && (!round_msgs || !round_len))) return ZKSC_ERR_SHAPE;
+    if (protocol < ZKSC_PROTO_SUMCHECK || protocol > ZKSC_PROTO_MULTI_FULL) return ZKSC_ERR_SHAPE;
+    {   // the proof is untrusted input: every round message must fit the slot the caller's stride gives it
+        const uint32_t per = (protocol == ZKSC_PROTO_MULTI_PARTIAL || protocol == ZKSC_PROTO_MULTI_FULL) ? 2 : 1;
+        for (uint32_t r = 0; r < n_vars; r++)
+            if ((uint64_t)round_len[r] * per > msg_stride) return ZKSC_ERR_SHAPE;
+    }
     host::FiatShamirTranscript tr;
     if (absorbed_prefix && prefix_len) tr.commit(absorbed_prefix, prefix_len);
     FrH claimed = load_h(sum);
@@ -1679,7 +1752,11 @@ extern "C" int zksc_ml_partial_evaluation(zksc_ctx* ctx, const uint64_t* evals, 
     if (!ctx) return ZKSC_ERR_STATE;
     if (!evals || !r || !out) FAIL(ZKSC_ERR_SHAPE, "NULL argument");
     if (n < 2 || (n & (n - 1))) FAIL(ZKSC_ERR_SHAPE, "Number of evaluations must be a power of 2 (and at least 2 to bind a variable)");
-    if (n % 2 != 0 || variable_index >= n / 2 || (n >> (variable_index + 1)) == 0) FAIL(ZKSC_ERR_SHAPE, "variable_index must be less than n/2 and name an existing variable");
+    uint32_t n_vars_ml = 0;
+    while ((1ull << n_vars_ml) < n) n_vars_ml++;
+    // the reference asserts variable_index < n/2 (polynomial/src/utils.rs:30-34); an index past the last variable would pair nothing
+    // (and a shift by >= 64 would be undefined), so it is rejected before any shift
+    if (variable_index >= n_vars_ml) FAIL(ZKSC_ERR_SHAPE, "variable_index must be less than n/2 and name an existing variable");
     CK(cudaSetDevice(ctx->device));
     TRY(quiesce(ctx));
     DevBuf in(ctx), o(ctx);
@@ -1729,8 +1806,8 @@ extern "C" int zksc_ml_evaluation(zksc_ctx* ctx, const uint64_t* evals, uint64_t
 extern "C" int zksc_ml_outer(zksc_ctx* ctx, int mul, const uint64_t* a, uint64_t na, const uint64_t* b, uint64_t nb, uint64_t* out) {
     if (!ctx) return ZKSC_ERR_STATE;
     if (!a || !b || !out || !na || !nb) FAIL(ZKSC_ERR_SHAPE, "empty operand");
-    uint64_t n = na * nb;
-    if (n & (n - 1)) FAIL(ZKSC_ERR_SHAPE, "Number of evaluations must be a power of 2");
+    unsigned long long n = 0;
+    if (__builtin_umulll_overflow(na, nb, &n) || (n & (n - 1))) FAIL(ZKSC_ERR_SHAPE, "Number of evaluations must be a power of 2");
     CK(cudaSetDevice(ctx->device));
     TRY(quiesce(ctx));
     DevBuf da(ctx), db(ctx), dout(ctx);

@@ -180,7 +180,7 @@ class GKRInstance:
                 m = int(lens[r])
                 v = all_ints[r * 6:r * 6 + 2 * m]
                 rps.append(SparseUnivariatePolynomial([(v[2 * i], v[2 * i + 1]) for i in range(m)]))
-            proofs.append(MultiComposedProof(rps, sums_i[li], (msgs[off:off + n], lens[off:off + n])))
+            proofs.append(MultiComposedProof(rps, sums_i[li]))
             off += n
         proof = GKRProof(proofs, from_mont(raw["wb"]), from_mont(raw["wc"]), Multilinear(raw["w0"]))
         proof.challenges = from_mont(raw["chal"])
@@ -212,7 +212,7 @@ class GKRProtocol:               # gkr/src/protocol.rs:17-195
             m = int(lens[0, r])
             v = from_mont(msgs[0, r, :2 * m]) if m else []
             rps.append(SparseUnivariatePolynomial([(v[2 * i], v[2 * i + 1]) for i in range(m)]))
-        proof = MultiComposedProof(rps, claimed_sum % R, (msgs[0], lens[0]))
+        proof = MultiComposedProof(rps, claimed_sum % R)
         transcript.commit(proof.to_bytes())
         proofs.append(proof)
         ch = from_mont(chal[0]) if n else []
