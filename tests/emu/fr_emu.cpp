@@ -57,6 +57,12 @@ extern "C" void emu_fr_fold_tab_semi(const uint32_t* a, const uint32_t* b, const
     FoldTab W; memcpy(W.w, w64, 256);
     Fr x, y; memcpy(x.l, a, 32); memcpy(y.l, b, 32); Fr z = fr_fold_tab<true>(x, y, W); memcpy(o, z.l, 32);
 }
+// the resident kernel's form: the same table in shared-memory order (FoldTabS, rows permuted for LDS.128)
+extern "C" void emu_fr_fold_tabs_semi(const uint32_t* a, const uint32_t* b, const uint32_t* w64, uint32_t* o) {
+    FoldTabS W;
+    for (int i = 0; i < 8; i++) for (int j = 0; j < 8; j++) W.w[foldtabs_index(i, j)] = w64[8 * i + j];
+    Fr x, y; memcpy(x.l, a, 32); memcpy(y.l, b, 32); Fr z = fr_fold_tab<true>(x, y, W); memcpy(o, z.l, 32);
+}
 extern "C" {
 BIN(emu_fr_mul_lazy, fr_mul_lazy)
 }

@@ -135,7 +135,7 @@ def test_fixed_multiplicand_fold(emu):
         W = fold_table(r)
         for a in (0, 1, R - 1):
             for b in (0, 1, R - 1, R - 2):
-                for fn in (emu.emu_fr_fold_tab, emu.emu_fr_fold_tab_semi):
+                for fn in (emu.emu_fr_fold_tab, emu.emu_fr_fold_tab_semi, emu.emu_fr_fold_tabs_semi):
                     fn(arr(a, 8), arr(b, 8), W, o8)
                     assert val(o8) == (a + r * (b - a)) % R
     # extreme table / operand limbs

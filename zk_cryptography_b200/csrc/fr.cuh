@@ -517,6 +517,27 @@ ZKSC_DEV Fr acc17_reduce(const Acc<17>& a) {
     return fr_add(fr_add(r0, r1), r2);
 }
 
+#ifndef ZKSC_HOST_EMU
+// The same, called by a WHOLE warp with the sum in lane 0: the two Montgomery products run side by side in lanes 0 and 1 (one
+// instruction stream, two operand sets) instead of one after the other -- a lone warp finishing a round's sum is pure dependency
+// latency (~4 cycles per instruction of the carry chains), so this halves the ~2 us the serial form cost every round
+// (profiles/r02_trace_resident_c2_v2.txt).  The result is meaningful in lane 0.
+ZKSC_DEV Fr acc17_reduce_warp(const Acc<17>& a) {
+    const int lane = threadIdx.x & 31;
+    Fr lo, mid, x = fr_zero(), y = fr_zero();
+#pragma unroll
+    for (int i = 0; i < 8; i++) { lo.l[i] = a.l[i]; mid.l[i] = a.l[8 + i]; }
+    const uint32_t h = __shfl_sync(0xffffffffu, a.l[16], 0);
+    if (lane == 0) { x = fr_canon(lo); y.l[0] = 1u; }
+    if (lane == 1) { x.l[0] = h; y = fr_r2(); }
+    Fr r = fr_mul(x, y);
+    Fr r2;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r2.l[i] = __shfl_sync(0xffffffffu, r.l[i], 1);
+    return fr_add(fr_add(r, fr_canon(mid)), r2);
+}
+#endif
+
 // fold: a + r * (b - a)   (== r*b + (1-r)*a, polynomial/src/multilinear/evaluation_form.rs:133)
 ZKSC_DEV Fr fr_fold(const Fr& a, const Fr& b, const Fr& r) {
     return fr_add(a, fr_mul(r, fr_sub(b, a)));
@@ -566,8 +587,34 @@ ZKSC_DEV void chain3(uint32_t* X, int pos, uint32_t v0, uint32_t v2, uint32_t v4
     X[pos + 4] = madc_lo_cc(x, v4, X[pos + 4]); X[pos + 5] = madc_hi_cc(x, v4, X[pos + 5]);
     X[pos + 6] = addc(X[pos + 6], 0u);
 }
+// The same table for kernels that receive the challenge AFTER they were launched (the resident rounds kernel): it lives in
+// shared memory, rows permuted to (w0, w2, w4, w6 | w1, w3, w5, w7) so that the four multipliers of each carry chain arrive
+// with one LDS.128.
+struct FoldTabS {
+    uint32_t w[64];
+};
+#ifndef ZKSC_HOST_EMU
+__host__ __device__
+#endif
+constexpr int foldtabs_index(int i, int j) { return i * 8 + (j & 1) * 4 + (j >> 1); }   // where w[i][j] of a FoldTab sits
+ZKSC_DEV void fold_row(const FoldTab& W, int i, uint32_t (&e)[4], uint32_t (&o)[4]) {
+    e[0] = W.w[i][0]; e[1] = W.w[i][2]; e[2] = W.w[i][4]; e[3] = W.w[i][6];
+    o[0] = W.w[i][1]; o[1] = W.w[i][3]; o[2] = W.w[i][5]; o[3] = W.w[i][7];
+}
+#ifndef ZKSC_HOST_EMU
+ZKSC_DEV void fold_row(const FoldTabS& W, int i, uint32_t (&e)[4], uint32_t (&o)[4]) {
+    const uint4 a = *reinterpret_cast<const uint4*>(&W.w[8 * i]), b = *reinterpret_cast<const uint4*>(&W.w[8 * i + 4]);
+    e[0] = a.x; e[1] = a.y; e[2] = a.z; e[3] = a.w;
+    o[0] = b.x; o[1] = b.y; o[2] = b.z; o[3] = b.w;
+}
+#else
+ZKSC_DEV void fold_row(const FoldTabS& W, int i, uint32_t (&e)[4], uint32_t (&o)[4]) {
+    for (int k = 0; k < 4; k++) { e[k] = W.w[8 * i + k]; o[k] = W.w[8 * i + 4 + k]; }
+}
+#endif
 // res (8 limbs, < 2p) == r * d (mod p) for ANY d < 2^256, W the shift table of r.
-ZKSC_DEV void mul_fixed_rows(uint32_t (&res)[8], const uint32_t (&d)[8], const FoldTab& W) {
+template <class TAB>
+ZKSC_DEV void mul_fixed_rows(uint32_t (&res)[8], const uint32_t (&d)[8], const TAB& W) {
     using namespace ptx;
     uint32_t E[11], O[11];
 #pragma unroll
@@ -576,8 +623,10 @@ ZKSC_DEV void mul_fixed_rows(uint32_t (&res)[8], const uint32_t (&d)[8], const F
     E[6] = FoldQ<6>::v; E[7] = FoldQ<7>::v; E[8] = FoldQ<8>::v; E[9] = FoldQ<9>::v; E[10] = 0;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-        chain4<false>(E, 0, W.w[i][0], W.w[i][2], W.w[i][4], W.w[i][6], d[i]);
-        chain4<false>(O, 1, W.w[i][1], W.w[i][3], W.w[i][5], W.w[i][7], d[i]);
+        uint32_t we[4], wo[4];
+        fold_row(W, i, we, wo);
+        chain4<false>(E, 0, we[0], we[1], we[2], we[3], d[i]);
+        chain4<false>(O, 1, wo[0], wo[1], wo[2], wo[3], d[i]);
     }
     // limbs 0 and 1 of T, the two digits, and what the low 64 bits leave behind at limb 2
     const uint32_t t0 = E[0];
@@ -627,8 +676,8 @@ ZKSC_DEV Fr fr_add_semi(const Fr& a, const Fr& v) {
 // SEMI: finish with fr_add_semi (one conditional subtraction + a never-taken branch) instead of cond_sub_r + fr_add.  17 ALU
 // instructions fewer, but measured faster only where ptxas has registers to spare: round_kernel<2, FOLD, SKIP1, 1> 332.5 -> 316.7 us
 // (c2 round 1), while the d = 3 and the 64-proof instantiations lose 1.5-2.7 % to it (profiles/r01_variants_v5.txt).
-template <bool SEMI = false>
-ZKSC_DEV Fr fr_fold_tab(const Fr& a, const Fr& b, const FoldTab& W) {
+template <bool SEMI = false, class TAB = FoldTab>
+ZKSC_DEV Fr fr_fold_tab(const Fr& a, const Fr& b, const TAB& W) {
     using namespace ptx;
     uint32_t d[8];                                     // b - a + p  in (0, 2p): no conditional
     d[0] = sub_cc(b.l[0], a.l[0]);

@@ -135,6 +135,12 @@ ZKSC_DEV Fr acc_finish(const Acc<NL>& a) {
     if constexpr (NL == 9) return acc9_reduce(a);
     else return acc17_reduce(a);
 }
+// called by a whole warp, the sum in lane 0, the result in lane 0
+template <int NL>
+ZKSC_DEV Fr acc_finish_warp(const Acc<NL>& a) {
+    if constexpr (NL == 9) return acc9_reduce(a);
+    else return acc17_reduce_warp(a);
+}
 
 ZKSC_DEV Fr ld256_volatile(const Fr* p) {
     Fr v;
@@ -195,6 +201,44 @@ static __device__ __noinline__ bool exchange_partials(const XchArgs& x) {
     return true;
 }
 
+ZKSC_DEV Fr ld256_cg(const Fr* p) {     // L2 only: for data another SM wrote while this kernel was already running
+    Fr v;
+    asm volatile("ld.global.cg.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v.l[0]), "=r"(v.l[1]), "=r"(v.l[2]), "=r"(v.l[3]), "=r"(v.l[4]), "=r"(v.l[5]), "=r"(v.l[6]), "=r"(v.l[7])
+                 : "l"(p)
+                 : "memory");
+    return v;
+}
+// The whole CTA (kThreads threads) sums n canonical elements  base[i * elem_stride],  i < n, into an unreduced 9-limb accumulator
+// per warp: s_red[warp].  Five loads per thread are issued before the first one is consumed -- the last block of a round walks
+// up to 148 x 4 per-block partials per evaluation point, and one load per dependent iteration made that walk ~5 us long.
+ZKSC_DEV void cta_sum_elems(const Fr* base, size_t elem_stride, unsigned int n, Acc<9>* s_red) {
+    constexpr int KB = 5;
+    Acc<9> a;
+    acc_zero(a);
+    for (unsigned int b0 = 0; b0 < n; b0 += KB * kThreads) {
+        Fr v[KB];
+#pragma unroll
+        for (int k = 0; k < KB; k++) {
+            const unsigned int c = b0 + k * kThreads + threadIdx.x;
+            v[k] = (c < n) ? ld256_cg(base + (size_t)c * elem_stride) : fr_zero();
+        }
+#pragma unroll
+        for (int k = 0; k < KB; k++) acc_add<9, 8>(a, v[k].l);
+    }
+    acc_warp_reduce(a);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = a;
+}
+// ... and one warp finishes: the canonical total of what cta_sum_elems left in s_red (call after a __syncthreads)
+ZKSC_DEV Fr warp_finish_sum(const Acc<9>* s_red) {
+    const int lane = threadIdx.x & 31;
+    Acc<9> a;
+    if (lane < kWarps) a = s_red[lane];
+    else acc_zero(a);
+    acc_warp_reduce(a);
+    return acc9_reduce(a);      // meaningful in lane 0
+}
+
 // Block-level reduction of NP accumulators, publication of the block partial, and -- in the last
 // block of each proof to arrive -- the final cross-block sum.
 // Accumulator slot s holds evaluation point s, or with SKIP1 point (s == 0 ? 0 : s + 1).
@@ -221,10 +265,8 @@ ZKSC_DEV void reduce_and_publish(Acc<NL> (&acc)[NP], const RoundBase& args, int 
             if (lane < kWarps) a = s_warp[lane][p];
             else acc_zero(a);
             acc_warp_reduce(a);
-            if (lane == 0 && point_of(p) < npts) {
-                Fr v = acc_finish<NL>(a);
-                st256(my_partials + p, v);
-            }
+            const Fr v = acc_finish_warp<NL>(a);
+            if (lane == 0 && point_of(p) < npts) st256(my_partials + p, v);
         }
         if (lane == 0) {
             __threadfence();
@@ -237,19 +279,14 @@ ZKSC_DEV void reduce_and_publish(Acc<NL> (&acc)[NP], const RoundBase& args, int 
     __threadfence();
     // last block of this proof: sum the per-block partials (canonical Montgomery elements)
     const Fr* all = args.partials + (size_t)group * gridDim.x * NP;
+    __shared__ Acc<9> s_red[NP][kWarps];
+#pragma unroll 1
+    for (int p = 0; p < NP; p++) cta_sum_elems(all + p, NP, gridDim.x, s_red[p]);
+    __syncthreads();
     for (int p = warp; p < NP; p += kWarps) {
-        if (point_of(p) >= npts) continue;
-        Acc<9> a;
-        acc_zero(a);
-        for (unsigned int blk = lane; blk < gridDim.x; blk += 32) {
-            Fr v = ld256(all + (size_t)blk * NP + p);
-            acc_add<9, 8>(a, v.l);
-        }
-        acc_warp_reduce(a);
-        if (lane == 0) {
-            Fr v = acc9_reduce(a);
+        const Fr v = warp_finish_sum(s_red[p]);
+        if (lane == 0 && point_of(p) < npts)
             st256_2x128(args.result + (size_t)proof * args.res_stride + (size_t)blockIdx.z * args.res_prod_stride + point_of(p), v);   // may be host-mapped
-        }
     }
     __syncthreads();
     if (threadIdx.x == 0) {

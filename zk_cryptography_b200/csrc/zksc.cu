@@ -27,7 +27,7 @@
 #include "host_field.hpp"
 #include "aux_kernels.cuh"
 #include "kernels.cuh"
-#include "tail_kernel.cuh"
+#include "resident_kernel.cuh"
 
 #if __has_include(<nccl.h>)
 #include <nccl.h>
@@ -40,16 +40,22 @@ using namespace zksc;
 using zksc::host::FrH;
 
 static_assert(kMaxDegree == ZKSC_MAX_DEGREE, "header / kernel limits differ");
-static_assert(kTailMaxProducts == ZKSC_MAX_PRODUCTS, "header / tail kernel limits differ");
-void zksc_launch_tail(dim3 grid, cudaStream_t s, const TailArgs& a);   // tail_inst.cu
+static_assert(kResMaxProducts == ZKSC_MAX_PRODUCTS, "header / resident kernel limits differ");
+cudaError_t zksc_launch_resident(int dsel, unsigned int ctas, cudaStream_t s, const ResArgs& a);   // res_inst.cu
+int zksc_resident_occ(int dsel);
 
 static thread_local std::string g_create_error;
 
 constexpr size_t kXchTagBytes = 256;               // 2 * kMaxRanks tags, padded
 constexpr unsigned int kXchCap = 2048;             // elements per (slot, rank): rounds with more partials use NCCL
-// exchange buffer of a rank: tags[2][G] | data[2][G][kXchCap] elements (round kernels) | units[2][G][kXchCap][8] (resident kernel)
+constexpr size_t kXchStageElems = 1u << 15;        // gather stage of a rank: its folded shard of every table, read by the peers (1 MiB)
+constexpr unsigned long long kGatherDefault = 2048;   // sharded contexts: gather the shards when a table is down to this many entries in total
+constexpr unsigned long long kTailWorkDefault = 1000ull * 1000 * 1000;   // resident kernel from the round with at most this many limb products per rank
+// exchange buffer of a rank: tags[2][G] | data[2][G][kXchCap] elements (round kernels) | units[2][G][kXchCap][8] (resident kernel) |
+// stage[kXchStageElems] elements (resident kernel, gather)
 static inline size_t kXchUnitsOffset(int G) { return kXchTagBytes + (size_t)2 * G * kXchCap * 32; }
 static inline size_t kXchUnitsBytes(int G) { return (size_t)2 * G * kXchCap * 64; }
+static inline size_t kXchStageOffset(int G) { return kXchUnitsOffset(G) + kXchUnitsBytes(G); }
 
 // ------------------------------------------------------------------------------------------------
 // NCCL, loaded at run time (single-GPU use must not depend on libnccl being present)
@@ -184,17 +190,19 @@ struct zksc_ctx {
     std::string err;
     int rank = 0, n_ranks = 1;
     unsigned long long gather_entries = 1;   // sharded contexts: the shards are gathered when a table is down to this many entries IN TOTAL
-    // persistent tail kernel (tail_kernel.cuh): mailbox + result units in pinned, device-mapped host memory
+    // resident rounds kernel (resident_kernel.cuh): mailbox + result units in pinned, device-mapped host memory
     bool fuse_products = true;           // ZKSC_NO_FUSE=1: one launch per product even when the degrees agree
     bool tail_enabled = true;            // ZKSC_NO_TAIL=1: every round is its own launch
-    unsigned long long tail_work = kTailWorkPerCta;   // start threshold of the resident kernel (ZKSC_TAIL_WORK overrides, experiments)
+    unsigned long long tail_work = kTailWorkDefault;   // start threshold of the resident kernel (ZKSC_TAIL_WORK overrides, experiments)
+    int res_occ[kResMaxDegree + 1] = {};       // resident CTAs per SM of resident_kernel<dsel>
     volatile uint64_t* tail_mail = nullptr;    // [tail_proofs_cap][kMailUnits]   {word | seq << 32}
     volatile uint64_t* tail_res = nullptr;     // [tail_units_cap]                {limb | seq << 32}
     unsigned long long* tail_mail_dev = nullptr;
     unsigned long long* tail_res_dev = nullptr;
-    unsigned long long* tail_relay = nullptr;  // HBM [tail_groups_cap][kMailUnits]
-    unsigned long long* tail_sums = nullptr;   // HBM [tail_sums_cap] units
-    size_t tail_proofs_cap = 0, tail_units_cap = 0, tail_groups_cap = 0, tail_sums_cap = 0;
+    unsigned long long* tail_relay = nullptr;  // HBM [2][tail_proofs_cap][kMailUnits] units, then [2][tail_proofs_cap] tags (32-bit)
+    Fr* tail_partials = nullptr;               // HBM [tail_part_cap] elements
+    unsigned int* tail_counters = nullptr;     // HBM [tail_groups_cap]
+    size_t tail_proofs_cap = 0, tail_units_cap = 0, tail_groups_cap = 0, tail_part_cap = 0;
     unsigned int tail_seq = 0;           // last sequence number handed out
     struct zksc_tables* active_tail = nullptr;   // the handle whose tail kernel is resident on `stream` (at most one)
     // ZKSC_PROFILE=1: host-side wall-clock split of every round of zksc_prove, printed to stderr (ns)
@@ -248,6 +256,11 @@ struct zksc_tables {
     bool tail_posted = false;           // a challenge has been posted whose round result has not been collected
     unsigned int tail_left = 0;         // rounds whose result has not been collected
     unsigned int tail_cur = 0;          // sequence number of the round posted last
+    unsigned int tail_done = 0;         // rounds of the running resident kernel whose result has been collected
+    std::chrono::steady_clock::time_point tail_seen;   // when the latest round's results were collected (the kernel has been waiting since)
+    unsigned int tail_gather_round = kNoGather;   // sharded: its round (counted from its first) after which the shards are gathered
+    unsigned long long tail_gather_local = 0;     // ... entries per local table at that point
+    uint64_t tail_stride = 0;           // elements per table of `tail`
     bool copy_pending = false;          // zksc_tables_reupload_begin without its _end: `orig` is being written by the copy stream
 };
 
@@ -345,6 +358,13 @@ extern "C" int zksc_ctx_create(int device, zksc_ctx** out) {
     { const char* e_ = getenv("ZKSC_TAIL_WORK"); if (e_ && atoll(e_) > 0) ctx->tail_work = (unsigned long long)atoll(e_); }
     { const char* e_ = getenv("ZKSC_NO_STAGED"); ctx->staged = !(e_ && e_[0] == '1'); }
     { const char* e_ = getenv("ZKSC_STAGED_FOLD"); ctx->staged_fold = (e_ && e_[0] == '1'); }
+    for (int d = 0; d <= kResMaxDegree; d++) ctx->res_occ[d] = zksc_resident_occ(d);
+    {
+        int coop = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+        if (!coop) ctx->tail_enabled = false;     // the resident kernel's CTAs wait for each other: only with guaranteed co-residency
+    }
+    if ((e = cudaGetLastError()) != cudaSuccess) return fail(e, "occupancy query (resident kernel)");
     *out = ctx;
     return ZKSC_OK;
 }
@@ -370,7 +390,8 @@ extern "C" int zksc_ctx_destroy(zksc_ctx* ctx) {
     cudaFreeHost((void*)ctx->tail_mail);
     cudaFreeHost((void*)ctx->tail_res);
     cudaFree(ctx->tail_relay);
-    cudaFree(ctx->tail_sums);
+    cudaFree(ctx->tail_partials);
+    cudaFree(ctx->tail_counters);
     delete ctx->pool;
     if (ctx->gkr_stage) cudaFreeHost(ctx->gkr_stage);
     if (ctx->copy_stream) { cudaStreamDestroy(ctx->copy_stream); cudaEventDestroy(ctx->copy_event); }
@@ -534,7 +555,7 @@ static int setup_peer_exchange(zksc_ctx* ctx) {
     const int G = ctx->n_ranks;
     { const char* e_ = getenv("ZKSC_NO_P2P"); if (e_ && e_[0] == '1') return ZKSC_OK; }
     if (G > kMaxRanks) return ZKSC_OK;
-    const size_t bytes = kXchUnitsOffset(G) + kXchUnitsBytes(G);
+    const size_t bytes = kXchStageOffset(G) + kXchStageElems * sizeof(Fr);
     struct Msg { cudaIpcMemHandle_t h; unsigned int ok; unsigned int pad[15]; };
     static_assert(sizeof(Msg) == 128, "exchange handle message");
     Msg mine;
@@ -594,7 +615,14 @@ extern "C" int zksc_comm_init(zksc_ctx* ctx, int n_ranks, int rank, const uint8_
     if (r != ncclSuccess) FAIL(ZKSC_ERR_COMM, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r));
     ctx->rank = rank;
     ctx->n_ranks = n_ranks;
-    ctx->gather_entries = (unsigned long long)n_ranks;
+    {
+        unsigned long long g = kGatherDefault;
+        const char* e_ = getenv("ZKSC_GATHER_ENTRIES");
+        if (e_ && atoll(e_) > 0) g = (unsigned long long)atoll(e_);
+        while (g & (g - 1)) g &= g - 1;                     // a power of two ...
+        if (g < 2ull * n_ranks) g = 2ull * n_ranks;         // ... with at least one pair per rank left
+        ctx->gather_entries = g;
+    }
     // result buffers are sized per rank count: drop them so the next use re-allocates
     cudaFree(ctx->results_dev); cudaFree(ctx->results_send); cudaFreeHost(ctx->results_host);
     ctx->results_dev = nullptr; ctx->results_send = nullptr; ctx->results_host = nullptr; ctx->results_cap = 0;
@@ -665,7 +693,8 @@ static int tables_alloc(zksc_ctx* ctx, uint32_t n_vars, uint32_t B, uint32_t P, 
     size_t n_work = (size_t)B * t->Dtot * (t->n_local0 > 1 ? t->n_local0 / 2 : 1);
     cudaError_t e = dev_alloc(ctx, (void**)&t->orig, n_orig * sizeof(Fr));
     if (e == cudaSuccess) e = dev_alloc(ctx, (void**)&t->work, n_work * sizeof(Fr));
-    if (e == cudaSuccess && ctx->n_ranks > 1) e = dev_alloc(ctx, (void**)&t->tail, (size_t)B * t->Dtot * ctx->n_ranks * sizeof(Fr));
+    if (ctx->n_ranks > 1) t->tail_stride = std::max<uint64_t>(ctx->gather_entries, (uint64_t)ctx->n_ranks);
+    if (e == cudaSuccess && ctx->n_ranks > 1) e = dev_alloc(ctx, (void**)&t->tail, (size_t)B * t->Dtot * t->tail_stride * sizeof(Fr));
     if (e != cudaSuccess) {
         dev_free(ctx, t->orig); dev_free(ctx, t->work); dev_free(ctx, t->tail);
         delete t;
@@ -947,21 +976,22 @@ static Geo geo_of(const zksc_tables* t, int where) {
     Geo g;
     if (where == 0) { g.base = t->orig; g.tab_stride = t->n_local0; }
     else if (where == 1) { g.base = t->work; g.tab_stride = t->n_local0 > 1 ? t->n_local0 / 2 : 1; }
-    else { g.base = t->tail; g.tab_stride = t->ctx->n_ranks; }
+    else { g.base = t->tail; g.tab_stride = t->tail_stride; }
     g.proof_stride = g.tab_stride * t->Dtot;
     return g;
 }
 
 
 // ------------------------------------------------------------------------------------------------
-// persistent tail kernel: host side (tail_kernel.cuh has the protocol)
+// resident rounds kernel: host side (resident_kernel.cuh has the protocol)
 // ------------------------------------------------------------------------------------------------
-static int tail_ensure(zksc_ctx* ctx, size_t proofs, size_t units, size_t groups, size_t sums) {
-    if (proofs <= ctx->tail_proofs_cap && units <= ctx->tail_units_cap && groups <= ctx->tail_groups_cap && sums <= ctx->tail_sums_cap) return ZKSC_OK;
+static int tail_ensure(zksc_ctx* ctx, size_t proofs, size_t units, size_t groups, size_t partials) {
+    if (proofs <= ctx->tail_proofs_cap && units <= ctx->tail_units_cap && groups <= ctx->tail_groups_cap && partials <= ctx->tail_part_cap) return ZKSC_OK;
     CK(cudaStreamSynchronize(ctx->stream));
-    cudaFreeHost((void*)ctx->tail_mail); cudaFreeHost((void*)ctx->tail_res); cudaFree(ctx->tail_relay); cudaFree(ctx->tail_sums);
-    ctx->tail_mail = nullptr; ctx->tail_res = nullptr; ctx->tail_relay = nullptr; ctx->tail_sums = nullptr;
-    ctx->tail_proofs_cap = ctx->tail_units_cap = ctx->tail_groups_cap = ctx->tail_sums_cap = 0;
+    cudaFreeHost((void*)ctx->tail_mail); cudaFreeHost((void*)ctx->tail_res); cudaFree(ctx->tail_relay); cudaFree(ctx->tail_partials); cudaFree(ctx->tail_counters);
+    ctx->tail_mail = nullptr; ctx->tail_res = nullptr; ctx->tail_relay = nullptr; ctx->tail_partials = nullptr; ctx->tail_counters = nullptr;
+    ctx->tail_proofs_cap = ctx->tail_units_cap = ctx->tail_groups_cap = ctx->tail_part_cap = 0;
+    proofs = std::max(proofs, ctx->tail_proofs_cap); units = std::max(units, ctx->tail_units_cap);
     void *m = nullptr, *r = nullptr, *d = nullptr;
     CK(cudaHostAlloc(&m, proofs * kMailUnits * 8, cudaHostAllocMapped));
     CK(cudaHostAlloc(&r, units * 8, cudaHostAllocMapped));
@@ -970,87 +1000,134 @@ static int tail_ensure(zksc_ctx* ctx, size_t proofs, size_t units, size_t groups
     ctx->tail_mail = (volatile uint64_t*)m; ctx->tail_res = (volatile uint64_t*)r;
     CK(cudaHostGetDevicePointer(&d, m, 0)); ctx->tail_mail_dev = (unsigned long long*)d;
     CK(cudaHostGetDevicePointer(&d, r, 0)); ctx->tail_res_dev = (unsigned long long*)d;
-    CK(cudaMalloc(&ctx->tail_relay, groups * kMailUnits * 8));
-    CK(cudaMalloc(&ctx->tail_sums, sums * 8));
-    CK(cudaMemsetAsync(ctx->tail_relay, 0, groups * kMailUnits * 8, ctx->stream));
-    CK(cudaMemsetAsync(ctx->tail_sums, 0, sums * 8, ctx->stream));
-    ctx->tail_proofs_cap = proofs; ctx->tail_units_cap = units; ctx->tail_groups_cap = groups; ctx->tail_sums_cap = sums;
+    const size_t relay_words = 2 * proofs * (kMailUnits + 1);
+    CK(cudaMalloc(&ctx->tail_relay, relay_words * sizeof(unsigned long long)));
+    CK(cudaMalloc(&ctx->tail_partials, partials * sizeof(Fr)));
+    CK(cudaMalloc(&ctx->tail_counters, groups * sizeof(unsigned int)));
+    CK(cudaMemsetAsync(ctx->tail_relay, 0, relay_words * sizeof(unsigned long long), ctx->stream));
+    CK(cudaMemsetAsync(ctx->tail_counters, 0, groups * sizeof(unsigned int), ctx->stream));
+    ctx->tail_proofs_cap = proofs; ctx->tail_units_cap = units; ctx->tail_groups_cap = groups; ctx->tail_part_cap = partials;
     return ZKSC_OK;
 }
 
-// post the pending challenges' fold tables as round `seq` of every proof
+// post the pending challenges' fold tables as round `seq` of every proof (words in FoldTabS order: fr.cuh foldtabs_index)
 static void tail_post(zksc_tables* t, unsigned int seq) {
     zksc_ctx* ctx = t->ctx;
     for (uint32_t b = 0; b < t->B; b++) {
-        const uint32_t* w = &t->pending_tab[b].w[0][0];
+        const FoldTab& w = t->pending_tab[b];
         volatile uint64_t* m = ctx->tail_mail + (size_t)b * kMailUnits;
-        for (int u = 0; u < kMailUnits; u++) m[u] = (uint64_t)w[u] | ((uint64_t)seq << 32);
+        for (int i = 0; i < 8; i++)
+            for (int j = 0; j < 8; j++) m[foldtabs_index(i, j)] = (uint64_t)w.w[i][j] | ((uint64_t)seq << 32);
     }
     t->tail_cur = seq;
     t->tail_posted = true;
 }
 
 constexpr int kTailExpired = 1;   // internal status of tail_wait (never crosses the C ABI)
-// The kernel left on its own (mailbox timeout): forget it; the pending challenge is still unapplied.  This happens
-// when kernel launches are synchronous (under Nsight Compute every launch blocks until the kernel has ended, so the
-// host can never answer a resident kernel) or when the host thread was stopped for seconds: the context goes back
-// to one launch per round for good.
-static int tail_expired(zksc_tables* t) {
+// Forget a resident kernel that is gone or unusable and leave the context in a state from which ordinary launches work: the
+// handle's and the context's bookkeeping is cleared whatever happened, the kernel (if it is still there) is told to leave, the
+// stream is drained and every message buffer is wiped, so that no stale sequence number or failure tag survives.
+static int tail_forget(zksc_tables* t, bool disable) {
     zksc_ctx* ctx = t->ctx;
-    ctx->tail_enabled = false;
+    if (ctx->tail_mail)
+        for (uint32_t b = 0; b < t->B && b < ctx->tail_proofs_cap; b++) ctx->tail_mail[(size_t)b * kMailUnits] = (uint64_t)kTailAbort << 32;
     t->tail_running = false; t->tail_posted = false; t->tail_left = 0;
     if (ctx->active_tail == t) ctx->active_tail = nullptr;
-    CK(cudaStreamSynchronize(ctx->stream));
+    if (disable) ctx->tail_enabled = false;
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (ctx->tail_mail) memset((void*)ctx->tail_mail, 0, ctx->tail_proofs_cap * kMailUnits * 8);
+    if (ctx->tail_res) memset((void*)ctx->tail_res, 0, ctx->tail_units_cap * 8);
+    ctx->tail_seq = 0;
+    if (e == cudaSuccess && ctx->tail_relay) e = cudaMemsetAsync(ctx->tail_relay, 0, 2 * ctx->tail_proofs_cap * (kMailUnits + 1) * sizeof(unsigned long long), ctx->stream);
+    if (e == cudaSuccess && ctx->tail_counters) e = cudaMemsetAsync(ctx->tail_counters, 0, ctx->tail_groups_cap * sizeof(unsigned int), ctx->stream);
+    if (e == cudaSuccess && ctx->xch_local) e = cudaMemsetAsync(ctx->xch_local + kXchUnitsOffset(ctx->n_ranks), 0, kXchUnitsBytes(ctx->n_ranks), ctx->stream);
+    if (e != cudaSuccess) { ctx->err = std::string("resident kernel clean-up: ") + cudaGetErrorString(e); return ZKSC_ERR_CUDA; }
     return ZKSC_OK;
+}
+// The kernel left on its own (mailbox timeout) before folding anything of the posted round: the pending challenge is still
+// unapplied.  This happens when kernel launches are synchronous (under Nsight Compute every launch blocks until the kernel has
+// ended, so the host can never answer a resident kernel) or when the host thread was stopped for a second: the context goes back
+// to one launch per round for good.  The recovered round is evaluated in full -- point 1 included, not derived from the claim.
+static int tail_expired(zksc_tables* t) {
+    t->claim_valid = false;
+    return tail_forget(t, true);
 }
 // wait for round `seq` of every (proof, product); copy the evaluations (all points but 1) to out when given
 static int tail_wait(zksc_tables* t, unsigned int seq, uint64_t* out) {
     zksc_ctx* ctx = t->ctx;
     unsigned long long spins = 0;
-    for (uint32_t b = 0; b < t->B; b++)
-        for (uint32_t p = 0; p < t->P; p++)
-            for (uint32_t pt = 0; pt <= t->deg[p]; pt++) {
+    uint32_t timed_out = 0, done = 0;
+    for (uint32_t b = 0; b < t->B; b++) {
+        bool proof_timed_out = false;
+        for (uint32_t p = 0; p < t->P && !proof_timed_out; p++)
+            for (uint32_t pt = 0; pt <= t->deg[p] && !proof_timed_out; pt++) {
                 if (pt == 1) continue;
                 const size_t e = (size_t)b * t->E + t->eoff[p] + pt;
                 uint32_t limbs[8];
-                for (int l = 0; l < 8; l++) {
+                for (int l = 0; l < 8 && !proof_timed_out; l++) {
                     volatile uint64_t* u = ctx->tail_res + e * 8 + l;
                     for (;;) {
                         const uint64_t v = *u;
                         const uint32_t tag = (uint32_t)(v >> 32);
                         if (tag == seq) { limbs[l] = (uint32_t)v; break; }
-                        if (tag == kTailTimeout) return kTailExpired;   // the kernel gave up waiting and left; nothing was folded
-                        if (tag == kTailFailed) FAIL(ZKSC_ERR_COMM, "resident rounds kernel: a CTA or a peer GPU went missing mid-round; the tables are undefined (reset them)");
+                        if (tag == kTailTimeout) { proof_timed_out = true; break; }   // this proof's CTAs gave up waiting and left; nothing of it was folded
+                        if (tag == kTailFailed) {
+                            tail_forget(t, true);
+                            FAIL(ZKSC_ERR_COMM, "resident rounds kernel: a CTA or a peer GPU went missing mid-round; the tables are undefined (reset them)");
+                        }
 #if defined(__x86_64__)
                         __builtin_ia32_pause();
 #endif
                         if ((++spins & 0xfffff) == 0) {
                             cudaError_t q = cudaStreamQuery(ctx->stream);
-                            if (q != cudaErrorNotReady && q != cudaSuccess) { ctx->err = std::string("tail kernel: ") + cudaGetErrorString(q); return ZKSC_ERR_CUDA; }
-                            if (q == cudaSuccess && (uint32_t)(*u >> 32) != seq) FAIL(ZKSC_ERR_CUDA, "tail kernel ended without publishing its results");
+                            if (q != cudaErrorNotReady && q != cudaSuccess) {
+                                std::string msg = std::string("resident kernel: ") + cudaGetErrorString(q);
+                                tail_forget(t, true);
+                                ctx->err = msg;
+                                return ZKSC_ERR_CUDA;
+                            }
+                            if (q == cudaSuccess && (uint32_t)(*u >> 32) != seq && (uint32_t)(*u >> 32) != kTailTimeout) {
+                                tail_forget(t, true);
+                                FAIL(ZKSC_ERR_CUDA, "resident kernel ended without publishing its results");
+                            }
                         }
                     }
                 }
-                if (out) memcpy(out + e * 4, limbs, 32);
+                if (!proof_timed_out && out) memcpy(out + e * 4, limbs, 32);
             }
-    return ZKSC_OK;
+        if (proof_timed_out) timed_out++;
+        else done++;
+    }
+    if (timed_out == 0) return ZKSC_OK;
+    if (done == 0) return kTailExpired;
+    // The time-out is decided per proof (by its first CTA): some proofs of the batch folded this round and others did not, so
+    // there is no single state to resume from.
+    tail_forget(t, true);
+    FAIL(ZKSC_ERR_COMM, "resident rounds kernel: the host's challenge reached only part of the batch in time; the tables are undefined (reset them)");
 }
 
-// bookkeeping after a tail round's result has been collected: its fold has been applied
+// bookkeeping after a resident round's result has been collected: its fold has been applied
 static void tail_round_done(zksc_tables* t) {
     zksc_ctx* ctx = t->ctx;
+    const unsigned int idx = t->tail_done++;
     if (t->where == 0) t->where = 1;
     t->cur_n /= 2;
+    if (t->tail_gather_round != kNoGather && idx == t->tail_gather_round + 1) {
+        // that round pulled every rank's shard into `tail` and folded it: replicated from here on
+        t->where = 2;
+        t->cur_n = t->tail_gather_local * ctx->n_ranks / 2;
+    }
     t->pending = false;
     t->tail_posted = false;
+    t->tail_seen = std::chrono::steady_clock::now();
     if (--t->tail_left == 0) {
         t->tail_running = false;          // the kernel leaves by itself after its last round
         if (ctx->active_tail == t) ctx->active_tail = nullptr;
     }
 }
 
-// Stop a resident tail kernel (anything else that wants the stream, the tables or a device-wide call must do
-// this first).  A posted round is completed and accounted for; its evaluations are dropped.
+// Stop a resident kernel (anything else that wants the stream, the tables or a device-wide call must do this first).  A posted
+// round is completed and accounted for; its evaluations are dropped.
 static int tail_stop(zksc_tables* t) {
     if (!t || !t->tail_running) return ZKSC_OK;
     zksc_ctx* ctx = t->ctx;
@@ -1058,7 +1135,7 @@ static int tail_stop(zksc_tables* t) {
     if (t->tail_posted) {
         const int rc = tail_wait(t, t->tail_cur, nullptr);
         if (rc == kTailExpired) return tail_expired(t);
-        if (rc != ZKSC_OK) return rc;
+        if (rc != ZKSC_OK) return rc;          // tail_wait has cleaned up
         tail_round_done(t);
         t->claim_valid = false;
         t->last_evals_valid = false;
@@ -1074,74 +1151,119 @@ static int tail_stop(zksc_tables* t) {
 }
 static int quiesce(zksc_ctx* ctx) { return ctx && ctx->active_tail ? tail_stop(ctx->active_tail) : ZKSC_OK; }
 
-// CTAs per (proof, product) group the resident kernel may use: every CTA must be co-resident (1 per SM)
+// which instantiation of the resident kernel serves this handle: its products' common degree, 0 when they differ
+static int tail_dsel(const zksc_tables* t) {
+    for (uint32_t p = 1; p < t->P; p++)
+        if (t->deg[p] != t->deg[0]) return 0;
+    return (int)t->deg[0];
+}
+// CTAs per (proof, product) group: the whole grid must be co-resident (cooperative launch), every group gets the same share
 static unsigned int tail_group_ctas(const zksc_tables* t) {
+    const zksc_ctx* ctx = t->ctx;
+    const int dsel = tail_dsel(t);
+    if (dsel > kResMaxDegree) return 0;
     const size_t groups = (size_t)t->B * t->P;
-    size_t c = groups ? (size_t)t->ctx->sms / groups : 0;
-    if (c > (size_t)kTailMaxCtas) c = kTailMaxCtas;
-    return (unsigned int)c;
+    const size_t cap = (size_t)ctx->sms * (size_t)std::max(ctx->res_occ[dsel], 0);
+    return groups ? (unsigned int)(cap / groups) : 0;
+}
+// 32 x 32 limb products per pair of a fused fold + evaluate round
+static unsigned long long round_products_per_pair(unsigned long long d) {
+    const unsigned long long per_point = d == 1 ? 0 : (d <= 3 ? (d - 2) * 120 + 64 : (d - 1) * 120);
+    return 2 * d * 76 + d * per_point;
 }
 static bool tail_eligible(const zksc_tables* t, unsigned long long half, bool sharded) {
     const zksc_ctx* ctx = t->ctx;
-    const unsigned int c = tail_group_ctas(t);
-    if (!ctx->tail_enabled || c == 0) return false;
-    if (sharded && (!ctx->p2p || (size_t)t->B * t->E > kXchCap)) return false;
-    for (uint32_t p = 0; p < t->P; p++) {
-        const unsigned long long d = t->deg[p];
-        if (d > (unsigned long long)kTailMaxDegree) return false;
-        // 32x32 limb products per pair of a fused fold + evaluate round: the resident kernel keeps one
-        // CTA of 8 warps per SM, so it only wins while a round is latency-bound
-        const unsigned long long per_point = d == 1 ? 0 : (d <= 3 ? (d - 2) * 120 + 64 : (d - 1) * 120);
-        if (half * (2 * d * 76 + d * per_point) > ctx->tail_work * c) return false;
+    if (!ctx->tail_enabled || tail_group_ctas(t) == 0) return false;
+    if (half >= (1ull << 29) || geo_of(t, 0).tab_stride >= (1ull << 31)) return false;     // the kernel indexes with 32 bits
+    if (sharded) {
+        if (!ctx->p2p || (size_t)t->B * t->E > kXchCap) return false;
+        if ((size_t)t->B * t->Dtot * 2 > kXchStageElems) return false;                      // the gather stage must hold at least one pair per table
     }
-    return true;
+    // the resident kernel reads the fold table from shared memory instead of the constant bank and keeps fewer loads in flight: a few
+    // per cent slower per pair than the ordinary launch, so it takes over where a round's fixed costs outweigh that
+    unsigned long long work = 0;
+    for (uint32_t p = 0; p < t->P; p++) {
+        if (t->deg[p] > (uint32_t)kResMaxDegree) return false;
+        work += half * round_products_per_pair(t->deg[p]);
+    }
+    return work * t->B <= ctx->tail_work;
 }
 
-// Launch the resident kernel for all remaining rounds of this phase; the pending challenge is its first mailbox message.
+// Launch the resident kernel for all remaining rounds; the pending challenge is its first mailbox message.
 static int tail_start(zksc_tables* t, unsigned long long half, bool sharded) {
     zksc_ctx* ctx = t->ctx;
     TRY(quiesce(ctx));
-    unsigned int n_ctas = tail_group_ctas(t);
-    const unsigned long long want = (half + kTailThreads - 1) / kTailThreads;
-    if (want < n_ctas) n_ctas = (unsigned int)want;
+    const unsigned int cpg = tail_group_ctas(t);
     const size_t groups = (size_t)t->B * t->P;
-    TRY(tail_ensure(ctx, t->B, (size_t)t->B * t->E * 8, groups, groups * n_ctas * kTailMaxDegree * 8));
+    TRY(tail_ensure(ctx, t->B, (size_t)t->B * t->E * 8, groups, groups * kResMaxDegree * cpg));
+    const unsigned int G = sharded ? (unsigned int)ctx->n_ranks : 1u;
+    // rounds: the table before this kernel's first fold has 4 * half * G entries in total = 2^m; m - 1 rounds are left
     unsigned int n_rounds = 0;
-    for (unsigned long long h = half; h >= 1; h >>= 1) n_rounds++;
+    for (unsigned long long h = half * G; h >= 1; h >>= 1) n_rounds++;
+    unsigned int gather_round = kNoGather;
+    unsigned long long gather_local = 0;
+    if (sharded) {
+        // gather when the table (after the fold) is down to `want` entries in total; at least one pair per rank must be left, and
+        // every rank's shard of every table must fit its stage
+        unsigned long long want = ctx->gather_entries;
+        while (want > 2ull * G && (size_t)t->B * t->Dtot * (want / G) > kXchStageElems) want /= 2;
+        unsigned long long total = 2 * half * G;      // after the first round's fold
+        gather_round = 0;
+        while (total > want) { total /= 2; gather_round++; }
+        gather_local = total / G;
+    }
     if (ctx->tail_seq > 0xf0000000u) {                    // stay clear of the reserved sequence numbers
         CK(cudaStreamSynchronize(ctx->stream));
         ctx->tail_seq = 0;
         memset((void*)ctx->tail_mail, 0, ctx->tail_proofs_cap * kMailUnits * 8);
         memset((void*)ctx->tail_res, 0, ctx->tail_units_cap * 8);
-        CK(cudaMemsetAsync(ctx->tail_relay, 0, ctx->tail_groups_cap * kMailUnits * 8, ctx->stream));
-        CK(cudaMemsetAsync(ctx->tail_sums, 0, ctx->tail_sums_cap * 8, ctx->stream));
+        CK(cudaMemsetAsync(ctx->tail_relay, 0, 2 * ctx->tail_proofs_cap * (kMailUnits + 1) * sizeof(unsigned long long), ctx->stream));
         if (ctx->xch_local) CK(cudaMemsetAsync(ctx->xch_local + kXchUnitsOffset(ctx->n_ranks), 0, kXchUnitsBytes(ctx->n_ranks), ctx->stream));
     }
     const unsigned int seq0 = ctx->tail_seq + 1;
     ctx->tail_seq += n_rounds;
     Geo gi = geo_of(t, t->where);
     Geo go = geo_of(t, t->where == 0 ? 1 : t->where);
-    TailArgs a;
+    ResArgs a;
     memset(&a, 0, sizeof(a));
     a.in = gi.base; a.out = go.base;
     a.in_tab_stride = gi.tab_stride; a.in_proof_stride = gi.proof_stride;
     a.out_tab_stride = go.tab_stride; a.out_proof_stride = go.proof_stride;
     a.half = half; a.n_rounds = n_rounds; a.seq0 = seq0;
-    a.n_products = t->P; a.n_evals = t->E;
+    a.n_proofs = t->B; a.n_products = t->P; a.n_evals = t->E; a.n_tables = t->Dtot;
     for (uint32_t p = 0; p < t->P; p++) { a.deg[p] = t->deg[p]; a.koff[p] = t->koff[p]; a.eoff[p] = t->eoff[p]; }
+    a.cpg = cpg;
     a.mail = ctx->tail_mail_dev; a.results = ctx->tail_res_dev;
-    a.relay = ctx->tail_relay; a.sums = ctx->tail_sums;
+    a.relay = ctx->tail_relay; a.relay_tags = ctx->tail_relay + 2 * ctx->tail_proofs_cap * kMailUnits;
+    a.partials = ctx->tail_partials; a.counters = ctx->tail_counters;
     a.n_ranks = 1; a.rank = 0; a.xch_cap = kXchCap;
+    a.gather_round = kNoGather;
     if (sharded) {
         a.n_ranks = ctx->n_ranks; a.rank = ctx->rank;
-        for (int g = 0; g < ctx->n_ranks; g++) a.peer_units[g] = (unsigned long long*)((unsigned char*)ctx->xch_peer[g] + kXchUnitsOffset(ctx->n_ranks));
+        for (int g = 0; g < ctx->n_ranks; g++) {
+            a.peer_units[g] = (unsigned long long*)((unsigned char*)ctx->xch_peer[g] + kXchUnitsOffset(ctx->n_ranks));
+            a.peer_stage[g] = (const Fr*)((unsigned char*)ctx->xch_peer[g] + kXchStageOffset(ctx->n_ranks));
+        }
+        a.gather_round = gather_round; a.gather_local = gather_local;
+        Geo gt = geo_of(t, 2);
+        a.tail = gt.base; a.tail_tab_stride = gt.tab_stride; a.tail_proof_stride = gt.proof_stride;
     }
+    a.relay_cap = (unsigned int)ctx->tail_proofs_cap;
     tail_post(t, seq0);
-    zksc_launch_tail(dim3(n_ctas, t->B, t->P), ctx->stream, a);
+    cudaError_t le = zksc_launch_resident(tail_dsel(t), (unsigned int)(groups * cpg), ctx->stream, a);
+    if (le != cudaSuccess) {
+        // cannot be made resident (another context holds the SMs, MPS limits, ...): ordinary launches from now on
+        cudaGetLastError();
+        t->tail_posted = false;
+        ctx->tail_enabled = false;
+        return kTailExpired;
+    }
     ctx->launches++;
-    CK(cudaGetLastError());
     t->tail_running = true;
     t->tail_left = n_rounds;
+    t->tail_done = 0;
+    t->tail_gather_round = gather_round;
+    t->tail_gather_local = gather_local;
     ctx->active_tail = t;
     return ZKSC_OK;
 }
@@ -1183,12 +1305,12 @@ static int flush_pending(zksc_tables* t) {
     } while (0)
 #endif
 
-__global__ void tail_scatter_kernel(const Fr* gathered, Fr* tail, unsigned int n_tabs_total, unsigned int G) {
-    // gathered: [rank][tab] -> tail: [tab][rank]
+__global__ void tail_scatter_kernel(const Fr* gathered, Fr* tail, unsigned long long tail_stride, unsigned int n_tabs_total, unsigned int G) {
+    // gathered: [rank][tab] -> tail: [tab][rank] (tables tail_stride elements apart)
     unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n_tabs_total * G) {
         unsigned int tab = i / G, g = i % G;
-        st256(tail + i, ld256(gathered + (size_t)g * n_tabs_total + tab));
+        st256(tail + (size_t)tab * tail_stride + g, ld256(gathered + (size_t)g * n_tabs_total + tab));
     }
 }
 __global__ void tail_collect_kernel(const Fr* base, unsigned long long tab_stride, Fr* out, unsigned int n_tabs_total) {
@@ -1210,7 +1332,7 @@ static int gather_tail(zksc_tables* t) {
     ctx->launches++;
     CK(cudaGetLastError());
     NCCLCK(g_nccl.AllGather(ctx->results_send, ctx->results_dev, (size_t)nt * sizeof(Fr), ncclUint8, ctx->comm, ctx->stream));
-    tail_scatter_kernel<<<(nt * ctx->n_ranks + 127) / 128, 128, 0, ctx->stream>>>(ctx->results_dev, t->tail, nt, ctx->n_ranks);
+    tail_scatter_kernel<<<(nt * ctx->n_ranks + 127) / 128, 128, 0, ctx->stream>>>(ctx->results_dev, t->tail, t->tail_stride, nt, ctx->n_ranks);
     ctx->launches++;
     CK(cudaGetLastError());
     t->where = 2;
@@ -1325,18 +1447,24 @@ static int round_evals_impl(zksc_tables* t, uint64_t* out, uint32_t npts_cap) {
     const size_t n_res = (size_t)t->B * t->E;
     if (t->tail_running || (skip1 && tail_eligible(t, half, reduce_ranks))) {
         // latency-bound rounds: the resident kernel runs this round and all later ones of this phase
-        if (!t->tail_running) TRY(tail_start(t, half, reduce_ranks));
-        const auto w0 = std::chrono::steady_clock::now();
-        ctx->prof_launch = std::chrono::duration<double, std::micro>(w0 - prof_t0).count();
-        const int rc = tail_wait(t, t->tail_cur, out);
+        int rc = ZKSC_OK;
+        if (!t->tail_running) rc = tail_start(t, half, reduce_ranks);
         if (rc == ZKSC_OK) {
-            ctx->prof_wait = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - w0).count();
-            tail_round_done(t);
-            finish_round(t, out, true, true, npts_cap);
-            return ZKSC_OK;
+            const auto w0 = std::chrono::steady_clock::now();
+            ctx->prof_launch = std::chrono::duration<double, std::micro>(w0 - prof_t0).count();
+            rc = tail_wait(t, t->tail_cur, out);
+            if (rc == ZKSC_OK) {
+                ctx->prof_wait = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - w0).count();
+                tail_round_done(t);
+                finish_round(t, out, true, true, npts_cap);
+                return ZKSC_OK;
+            }
+            if (rc != kTailExpired) return rc;
+            TRY(tail_expired(t));     // the host took too long between rounds: this round goes through an ordinary launch
+        } else if (rc != kTailExpired) {
+            return rc;
         }
-        if (rc != kTailExpired) return rc;
-        TRY(tail_expired(t));     // the host took too long between rounds: this round goes through an ordinary launch
+        return round_evals_impl(t, out, npts_cap);    // the resident kernel is off for this context now
     }
     const bool peer = reduce_ranks && ctx->p2p && n_res <= kXchCap;   // exchange + sum inside the round kernel
     const bool mapped = (ctx->mapped_results && !reduce_ranks) || peer;
@@ -1464,7 +1592,14 @@ extern "C" int zksc_bind(zksc_tables* t, const uint64_t* challenges) {
     t->vars_left--;
     t->claim_valid = claims;
     t->last_evals_valid = false;
-    if (t->tail_running) tail_post(t, t->tail_cur + 1);     // the resident kernel folds with it and evaluates the next round
+    if (t->tail_running) {
+        // The kernel's CTAs give up waiting for a challenge after kTailTimeoutNs, each by its own clock.  A challenge posted close to
+        // that deadline could reach some and not others, so the host never posts later than half of it after it saw the results:
+        // past that, the kernel is told to leave (nothing of the round has been folded) and ordinary launches carry on.
+        const double waited_ns = std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - t->tail_seen).count();
+        if (waited_ns > 0.5 * (double)kTailTimeoutNs) TRY(tail_stop(t));
+        else tail_post(t, t->tail_cur + 1);     // the resident kernel folds with it and evaluates the next round
+    }
     return ZKSC_OK;
 }
 
