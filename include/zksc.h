@@ -46,6 +46,19 @@ const char* zksc_version(void);
 int zksc_device_count(void);
 /* Create a context on CUDA device `device`.  Fails with ZKSC_ERR_NO_DEVICE when there is none. */
 int zksc_ctx_create(int device, zksc_ctx** out);
+/* One context over several devices of ONE process (the reference's caller, gkr/src/protocol.rs:85, is a single process): `devices` are
+ * n_devices distinct CUDA device ordinals, a power of two up to 8, with peer access to each other (NVLink / NVSwitch).  Every table of
+ * a handle made on such a context is sharded over the devices (device g holds the entries i = g mod n_devices); one host thread -- the
+ * caller's -- runs the one Fiat-Shamir transcript, adds the devices' partial evaluations (read from pinned host memory) and posts
+ * every challenge to all devices; there is no per-round exchange between the devices, and once a table is down to
+ * zksc_ctx_gather_entries() entries every device pulls the other shards over NVLink and the rest runs replicated.
+ * zksc_tables_upload sends every table across PCIe once (staged on the first device, each device picks its shard over NVLink).
+ * Supported on such a context: zksc_tables_upload / _synth / _reset / _free / _vars_left, zksc_poly_sum, zksc_round_evals, zksc_bind,
+ * zksc_residual (once the shards are exhausted), zksc_prove (all protocols but MULTI_FULL), zksc_evaluate, the stand-alone zksc_ml_*
+ * operations (first device); everything else returns ZKSC_ERR_UNSUPPORTED.  n_devices == 1 gives an ordinary context. */
+int zksc_ctx_create_multi(const int* devices, int n_devices, zksc_ctx** out);
+/* Number of devices behind a context (1 unless it came from zksc_ctx_create_multi). */
+int zksc_ctx_devices(const zksc_ctx* ctx);
 int zksc_ctx_destroy(zksc_ctx* ctx);
 /* Last error text of this context (or of the failed zksc_ctx_create when ctx == NULL). */
 const char* zksc_last_error(const zksc_ctx* ctx);

@@ -43,6 +43,8 @@ def lib():
         "zksc_version": (ctypes.c_char_p, []),
         "zksc_device_count": (ctypes.c_int, []),
         "zksc_ctx_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(vp)]),
+        "zksc_ctx_create_multi": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.POINTER(vp)]),
+        "zksc_ctx_devices": (ctypes.c_int, [vp]),
         "zksc_ctx_destroy": (ctypes.c_int, [vp]),
         "zksc_last_error": (ctypes.c_char_p, [vp]),
         "zksc_comm_unique_id": (ctypes.c_int, [_u8p]),
@@ -167,12 +169,21 @@ def from_mont(arr):
 class Context:
     """zksc_ctx: one CUDA device, one stream, optional NCCL communicator (one process per GPU)."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, devices=None):
+        """device: one CUDA device ordinal; devices: a list of them -- ONE context (and one host thread) over several GPUs of this
+        process (zksc_ctx_create_multi): tables are sharded over them, the caller sees a single logical context."""
         self._h = ctypes.c_void_p()
-        rc = lib().zksc_ctx_create(device, ctypes.byref(self._h))
+        if devices is not None:
+            arr = (ctypes.c_int * len(devices))(*[int(d) for d in devices])
+            rc = lib().zksc_ctx_create_multi(arr, len(devices), ctypes.byref(self._h))
+        else:
+            rc = lib().zksc_ctx_create(device, ctypes.byref(self._h))
         if rc != 0:
             raise ZkscError(rc, (lib().zksc_last_error(None) or b"").decode())
         self.rank, self.n_ranks = 0, 1
+
+    def devices(self):
+        return int(lib().zksc_ctx_devices(self._h))
 
     def check(self, rc):
         if rc != 0:
@@ -407,7 +418,8 @@ class Tables:
 
     def free(self):
         if self._h:
-            lib().zksc_tables_free(self._h)
+            if self.ctx._h:          # a handle must not outlive its context: after Context.close() there is nothing left to free into
+                lib().zksc_tables_free(self._h)
             self._h = ctypes.c_void_p()
 
     def __del__(self):

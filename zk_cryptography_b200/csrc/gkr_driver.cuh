@@ -98,6 +98,8 @@ extern "C" int zksc_gkr_prove(zksc_ctx* ctx, uint32_t n_layers, const uint32_t* 
                               const uint32_t* gate_in1, const uint64_t* const* layer_values, const uint64_t* value_len, uint64_t* w0, uint64_t* sums,
                               uint64_t* wb_s, uint64_t* wc_s, uint64_t* round_msgs, uint32_t* round_len, uint64_t* challenges) {
     if (!ctx) return ZKSC_ERR_STATE;
+    if (!ctx->kids.empty()) ctx = ctx->kids[0]->host_reduce ? nullptr : ctx;
+    if (!ctx) return ZKSC_ERR_UNSUPPORTED;      // GKR layer sumchecks are far below the size where sharding pays: use a single-device context
     if (!n_gates || !gate_type || !gate_in0 || !gate_in1 || !layer_values || !value_len || !w0 || !sums || !wb_s || !wc_s || !round_msgs || !round_len ||
         !challenges)
         FAIL(ZKSC_ERR_SHAPE, "NULL argument");

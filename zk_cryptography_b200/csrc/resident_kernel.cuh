@@ -71,6 +71,7 @@ struct ResArgs {
     // cross-GPU exchange (n_ranks > 1): every rank's unit buffer [2][n_ranks][xch_cap][8]
     unsigned long long* peer_units[kMaxRanks];
     unsigned int n_ranks, rank, xch_cap;
+    unsigned int host_reduce;         // n_ranks > 1 inside one process: no exchange, every rank publishes its own sums and the host adds them
     // gather (n_ranks > 1): after round `gather_round` (counted from this kernel's first) the folded local tables -- gather_local
     // entries each -- are copied to this rank's stage; round gather_round + 1 reads all ranks' stages and writes `tail`
     unsigned int gather_round;
@@ -259,7 +260,7 @@ ZKSC_DEV void res_rounds(const ResArgs& args, const volatile ResIds& ids, FoldTa
         const unsigned int seq = args.seq0 + round;
         const bool pull = (args.n_ranks > 1 && round == args.gather_round + 1);          // this round starts from every rank's stage
         if (pull) half = (unsigned int)(args.gather_local * args.n_ranks / 4);           // ... a table of gather_local * n_ranks entries
-        const bool exchange = (args.n_ranks > 1 && (args.gather_round == kNoGather || round <= args.gather_round));
+        const bool exchange = (args.n_ranks > 1 && !args.host_reduce && (args.gather_round == kNoGather || round <= args.gather_round));
         const unsigned int want = (half + kResThreads - 1) / kResThreads;
         const unsigned int n_active = want < args.cpg ? want : args.cpg;
         if (ci >= n_active) {
@@ -430,15 +431,18 @@ ZKSC_DEV void res_rounds(const ResArgs& args, const volatile ResIds& ids, FoldTa
             __syncthreads();
             for (int p = warp; p < NP; p += kResWarps) {
                 const unsigned int elem = elem0 + (p == 0 ? 0 : p + 1);
-                Acc<9> a;
-                acc_zero(a);
-                if (lane < (int)G) {
-                    Fr v;
-                    ok = res_read_elem(args.peer_units[args.rank] + ((size_t)(slot + lane) * args.xch_cap + elem) * 8, seq, v) && ok;
-                    acc_add<9, 8>(a, v.l);
+                Fr v = fr_zero();
+                if (lane < (int)G) ok = res_read_elem(args.peer_units[args.rank] + ((size_t)(slot + lane) * args.xch_cap + elem) * 8, seq, v) && ok;
+                // G <= 8 canonical values: a shuffle tree of modular additions (a Montgomery reduction of the plain sum costs ~1 us of
+                // dependent instructions in a lone warp)
+#pragma unroll
+                for (int d = kMaxRanks / 2; d >= 1; d >>= 1) {
+                    Fr o;
+#pragma unroll
+                    for (int i = 0; i < 8; i++) o.l[i] = __shfl_down_sync(0xffffffffu, v.l[i], d);
+                    v = fr_add(v, o);
                 }
-                acc_warp_reduce(a);
-                if (lane == 0) s_tot[p] = acc9_reduce(a);
+                if (lane == 0) s_tot[p] = v;
             }
             __syncthreads();
         }

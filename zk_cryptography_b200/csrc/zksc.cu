@@ -189,6 +189,15 @@ struct zksc_ctx {
     bool staged_fold = false;     // ... also for the fused fold+evaluate rounds (ZKSC_STAGED_FOLD=1; slower today: DESIGN.md)
     std::string err;
     int rank = 0, n_ranks = 1;
+    // Single-process multi-GPU (zksc_ctx_create_multi): the context the caller holds is a PARENT with one child context per device.
+    // A child is an ordinary sharded context (rank g of G) whose per-round partial evaluations are not exchanged on the device but
+    // published to its own pinned host buffer: the parent's host thread adds the G partials and runs the ONE transcript
+    // (host_reduce).  The children's rounds run concurrently, one pool thread per device.
+    std::vector<zksc_ctx*> kids;
+    zksc_ctx* parent = nullptr;
+    bool host_reduce = false;
+    bool gpu_pool_active = false;
+    HostPool* gpu_pool = nullptr;            // parent: kids.size() - 1 workers, spinning while a call is in progress
     unsigned long long gather_entries = 1;   // sharded contexts: the shards are gathered when a table is down to this many entries IN TOTAL
     // resident rounds kernel (resident_kernel.cuh): mailbox + result units in pinned, device-mapped host memory
     bool fuse_products = true;           // ZKSC_NO_FUSE=1: one launch per product even when the degrees agree
@@ -262,6 +271,21 @@ struct zksc_tables {
     unsigned long long tail_gather_local = 0;     // ... entries per local table at that point
     uint64_t tail_stride = 0;           // elements per table of `tail`
     bool copy_pending = false;          // zksc_tables_reupload_begin without its _end: `orig` is being written by the copy stream
+    // single-process multi-GPU: the parent handle owns one child handle per device and no device memory of its own; a child returns
+    // raw per-shard sums (no claim arithmetic, no point conversion: the parent does that on the totals)
+    std::vector<zksc_tables*> kids;
+    bool last_partial = false;          // the latest round's evaluations cover this rank's shard only (they still have to be added up)
+    bool raw = false;                   // child of a multi-GPU handle
+    bool raw_claim_next = false;        // ... whether the parent holds a claim for the round after the bind being applied
+};
+
+struct GpuPoolSession {     // the per-device worker threads spin while a multi-GPU call is in progress, and only then
+    zksc_ctx* c;
+    bool mine;
+    explicit GpuPoolSession(zksc_ctx* ctx) : c(ctx), mine(false) {
+        if (c && c->gpu_pool && !c->gpu_pool_active) { c->gpu_pool->begin(); c->gpu_pool_active = true; mine = true; }
+    }
+    ~GpuPoolSession() { if (mine) { c->gpu_pool_active = false; c->gpu_pool->end(); } }
 };
 
 #define CK(call)                                                                                          \
@@ -285,6 +309,15 @@ struct zksc_tables {
 
 static int tail_stop(zksc_tables* t);
 static int quiesce(zksc_ctx* ctx);
+static int multi_tables_synth(zksc_ctx* ctx, uint32_t n_vars, uint32_t B, uint32_t P, const uint32_t* degree, uint64_t seed, zksc_tables** out);
+static int multi_tables_upload(zksc_ctx* ctx, uint32_t n_vars, uint32_t B, uint32_t P, const uint32_t* degree, const uint64_t* const* host_tables, zksc_tables** out);
+static int multi_tables_reset(zksc_tables* t);
+static int multi_tables_free(zksc_tables* t);
+static int multi_residual(zksc_tables* t, uint64_t* out);
+#define NOT_MULTI(ctx_, what)                                                                                                  \
+    do {                                                                                                                       \
+        if ((ctx_) && !(ctx_)->kids.empty()) { (ctx_)->err = what ": not available on a multi-GPU context"; return ZKSC_ERR_UNSUPPORTED; } \
+    } while (0)
 
 static inline FrH to_host(const Fr& f) { FrH h; memcpy(h.v, f.l, 32); return h; }
 static inline FrH load_h(const uint64_t* p) { FrH h; memcpy(h.v, p, 32); return h; }
@@ -371,11 +404,21 @@ extern "C" int zksc_ctx_create(int device, zksc_ctx** out) {
 
 extern "C" int zksc_ctx_destroy(zksc_ctx* ctx) {
     if (!ctx) return ZKSC_OK;
-    cudaSetDevice(ctx->device);
-    quiesce(ctx);
-    cudaStreamSynchronize(ctx->stream);
-    for (int g = 0; g < ctx->n_ranks && g < kMaxRanks; g++)
-        if (ctx->xch_peer[g] && g != ctx->rank) cudaIpcCloseMemHandle(ctx->xch_peer[g]);
+    if (ctx->kids.empty()) {
+        cudaSetDevice(ctx->device);
+        quiesce(ctx);
+        cudaStreamSynchronize(ctx->stream);
+    }
+    if (!ctx->kids.empty()) {
+        delete ctx->gpu_pool;
+        for (zksc_ctx* k : ctx->kids) zksc_ctx_destroy(k);
+        delete ctx->pool;
+        delete ctx;
+        return ZKSC_OK;
+    }
+    if (!ctx->host_reduce)       // (a multi-GPU child's peers live in the same process: plain pointers, nothing to close)
+        for (int g = 0; g < ctx->n_ranks && g < kMaxRanks; g++)
+            if (ctx->xch_peer[g] && g != ctx->rank) cudaIpcCloseMemHandle(ctx->xch_peer[g]);
     cudaFree(ctx->xch_local);
 #if ZKSC_HAVE_NCCL_H
     if (ctx->comm) g_nccl.CommDestroy(ctx->comm);
@@ -404,6 +447,10 @@ extern "C" const char* zksc_last_error(const zksc_ctx* ctx) { return ctx ? ctx->
 
 extern "C" int zksc_ctx_synchronize(zksc_ctx* ctx) {
     if (!ctx) return ZKSC_ERR_STATE;
+    if (!ctx->kids.empty()) {
+        for (zksc_ctx* k : ctx->kids) { const int rc = zksc_ctx_synchronize(k); if (rc != ZKSC_OK) { ctx->err = k->err; return rc; } }
+        return ZKSC_OK;
+    }
     CK(cudaSetDevice(ctx->device));
     TRY(quiesce(ctx));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -421,12 +468,18 @@ extern "C" int zksc_ctx_peer_exchange(const zksc_ctx* ctx) { return (ctx && ctx-
 
 extern "C" uint64_t zksc_ctx_gather_entries(const zksc_ctx* ctx) { return ctx ? (uint64_t)ctx->gather_entries : 0; }
 
-extern "C" void* zksc_ctx_stream(zksc_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+extern "C" void* zksc_ctx_stream(zksc_ctx* ctx) { return ctx ? (void*)(ctx->kids.empty() ? ctx->stream : ctx->kids[0]->stream) : nullptr; }
 
-extern "C" unsigned long long zksc_ctx_launch_count(const zksc_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" unsigned long long zksc_ctx_launch_count(const zksc_ctx* ctx) {
+    if (!ctx) return 0;
+    unsigned long long n = ctx->launches;
+    for (const zksc_ctx* k : ctx->kids) n += k->launches;
+    return n;
+}
 
 extern "C" int zksc_ctx_timing(zksc_ctx* ctx, int enable) {
     if (!ctx) return ZKSC_ERR_STATE;
+    NOT_MULTI(ctx, "zksc_ctx_timing");
     CK(cudaSetDevice(ctx->device));
     TRY(quiesce(ctx));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -438,6 +491,7 @@ extern "C" int zksc_ctx_timing(zksc_ctx* ctx, int enable) {
 extern "C" int zksc_ctx_timing_read(zksc_ctx* ctx, uint32_t cap, uint32_t* n_out, float* ms, uint32_t* degree, uint32_t* fold, uint64_t* pairs,
                                     uint64_t* proofs) {
     if (!ctx || !n_out) return ZKSC_ERR_STATE;
+    NOT_MULTI(ctx, "zksc_ctx_timing_read");
     CK(cudaSetDevice(ctx->device));
     TRY(quiesce(ctx));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -483,6 +537,7 @@ __global__ void __launch_bounds__(256) int_peak_kernel(uint32_t* out, int iters,
 }
 extern "C" int zksc_int_peak(zksc_ctx* ctx, double* limb_products_per_second) {
     if (!ctx || !limb_products_per_second) return ZKSC_ERR_STATE;
+    if (!ctx->kids.empty()) ctx = ctx->kids[0];
     CK(cudaSetDevice(ctx->device));
     TRY(quiesce(ctx));
     const int blocks = ctx->sms * 8, iters = 4096;
@@ -603,6 +658,8 @@ static int setup_peer_exchange(zksc_ctx* ctx) {
 
 extern "C" int zksc_comm_init(zksc_ctx* ctx, int n_ranks, int rank, const uint8_t unique_id[128]) {
     if (!ctx) return ZKSC_ERR_STATE;
+    NOT_MULTI(ctx, "zksc_comm_init");
+    if (ctx->host_reduce) FAIL(ZKSC_ERR_STATE, "a child of a multi-GPU context has no communicator");
     if (n_ranks < 1 || (n_ranks & (n_ranks - 1)) || rank < 0 || rank >= n_ranks) FAIL(ZKSC_ERR_SHAPE, "n_ranks must be a power of two and 0 <= rank < n_ranks");
     TRY(quiesce(ctx));
     if (n_ranks == 1) { ctx->rank = 0; ctx->n_ranks = 1; return ZKSC_OK; }
@@ -715,6 +772,7 @@ static int tables_alloc(zksc_ctx* ctx, uint32_t n_vars, uint32_t B, uint32_t P, 
 static int copy_finish(zksc_tables* t);
 extern "C" int zksc_tables_reset(zksc_tables* t) {
     if (!t) return ZKSC_ERR_STATE;
+    if (!t->kids.empty()) return multi_tables_reset(t);
     TRY(copy_finish(t));
     TRY(tail_stop(t));
     t->vars_left = t->n_vars;
@@ -729,6 +787,7 @@ extern "C" int zksc_tables_reset(zksc_tables* t) {
 
 extern "C" int zksc_tables_free(zksc_tables* t) {
     if (!t) return ZKSC_OK;
+    if (!t->kids.empty()) return multi_tables_free(t);
     zksc_ctx* ctx = t->ctx;
     cudaSetDevice(ctx->device);
     copy_finish(t);
@@ -738,7 +797,7 @@ extern "C" int zksc_tables_free(zksc_tables* t) {
     return ZKSC_OK;
 }
 
-extern "C" int zksc_tables_vars_left(const zksc_tables* t, uint32_t* out) {
+extern "C" int zksc_tables_vars_left(const zksc_tables* t, uint32_t* out) {   // (a multi-GPU parent keeps its own count)
     if (!t || !out) return ZKSC_ERR_STATE;
     *out = t->vars_left;
     return ZKSC_OK;
@@ -790,6 +849,13 @@ extern "C" int zksc_tables_upload(zksc_ctx* ctx, uint32_t n_vars, uint32_t n_pro
                                   const uint64_t* const* host_tables, zksc_tables** out) {
     if (!ctx) return ZKSC_ERR_STATE;
     if (!host_tables) FAIL(ZKSC_ERR_SHAPE, "host_tables is NULL");
+    if (!ctx->kids.empty()) {
+        if (!out) return ZKSC_ERR_SHAPE;
+        int lg = 0;
+        while ((1u << lg) < ctx->kids.size()) lg++;
+        if ((int)n_vars < lg || n_vars > 40) FAIL(ZKSC_ERR_SHAPE, "tables have fewer entries than there are devices (or n_vars is too large)");
+        return multi_tables_upload(ctx, n_vars, n_proofs, n_products, degree, host_tables, out);
+    }
     zksc_tables* t = nullptr;
     TRY(tables_alloc(ctx, n_vars, n_proofs, n_products, degree, &t));
     int rc = upload_into(t, host_tables, false);
@@ -801,6 +867,7 @@ extern "C" int zksc_tables_upload(zksc_ctx* ctx, uint32_t n_vars, uint32_t n_pro
 extern "C" int zksc_tables_upload_local(zksc_ctx* ctx, uint32_t n_vars, uint32_t n_proofs, uint32_t n_products, const uint32_t* degree,
                                         const uint64_t* const* host_local_tables, zksc_tables** out) {
     if (!ctx) return ZKSC_ERR_STATE;
+    NOT_MULTI(ctx, "zksc_tables_upload_local");
     if (!host_local_tables) FAIL(ZKSC_ERR_SHAPE, "host_local_tables is NULL");
     zksc_tables* t = nullptr;
     TRY(tables_alloc(ctx, n_vars, n_proofs, n_products, degree, &t));
@@ -813,6 +880,7 @@ extern "C" int zksc_tables_upload_local(zksc_ctx* ctx, uint32_t n_vars, uint32_t
 extern "C" int zksc_tables_reupload(zksc_tables* t, const uint64_t* const* host_tables, int local) {
     if (!t) return ZKSC_ERR_STATE;
     zksc_ctx* ctx = t->ctx;
+    NOT_MULTI(ctx, "zksc_tables_reupload");
     if (!host_tables) FAIL(ZKSC_ERR_SHAPE, "host_tables is NULL");
     zksc_tables_reset(t);
     return upload_into(t, host_tables, local != 0);
@@ -824,6 +892,7 @@ extern "C" int zksc_tables_reupload_begin(zksc_tables* t, const uint64_t* const*
     if (!t) return ZKSC_ERR_STATE;
     zksc_ctx* ctx = t->ctx;
     if (!host_tables) FAIL(ZKSC_ERR_SHAPE, "host_tables is NULL");
+    NOT_MULTI(ctx, "zksc_tables_reupload_begin");
     if (t->copy_pending) FAIL(ZKSC_ERR_STATE, "a refill of this handle is already in flight; call zksc_tables_reupload_end first");
     TRY(zksc_tables_reset(t));      // stops this handle's resident kernel, if any
     TRY(quiesce(ctx));              // single-threaded API: another handle's resident kernel can only be in its exit phase here
@@ -857,6 +926,7 @@ extern "C" int zksc_tables_reupload_end(zksc_tables* t) {
 extern "C" int zksc_tables_read_local(zksc_tables* t, uint64_t* out) {
     if (!t || !out) return ZKSC_ERR_STATE;
     zksc_ctx* ctx = t->ctx;
+    NOT_MULTI(ctx, "zksc_tables_read_local");
     CK(cudaSetDevice(ctx->device));
     TRY(quiesce(ctx));
     const size_t n = (size_t)t->B * t->Dtot * t->n_local0;
@@ -868,6 +938,14 @@ extern "C" int zksc_tables_read_local(zksc_tables* t, uint64_t* out) {
 extern "C" int zksc_tables_synth(zksc_ctx* ctx, uint32_t n_vars, uint32_t n_proofs, uint32_t n_products, const uint32_t* degree, uint64_t seed,
                                  zksc_tables** out) {
     if (!ctx) return ZKSC_ERR_STATE;
+    if (!ctx->kids.empty()) {
+        if (!out) return ZKSC_ERR_SHAPE;
+        int lg = 0;
+        while ((1u << lg) < ctx->kids.size()) lg++;
+        if ((int)n_vars < lg || n_vars > 40) FAIL(ZKSC_ERR_SHAPE, "tables have fewer entries than there are devices (or n_vars is too large)");
+        GpuPoolSession session(ctx);
+        return multi_tables_synth(ctx, n_vars, n_proofs, n_products, degree, seed, out);
+    }
     zksc_tables* t = nullptr;
     TRY(tables_alloc(ctx, n_vars, n_proofs, n_products, degree, &t));
     for (uint32_t b = 0; b < t->B; b++)
@@ -885,12 +963,14 @@ extern "C" int zksc_tables_synth(zksc_ctx* ctx, uint32_t n_vars, uint32_t n_proo
 
 extern "C" int zksc_tables_alloc(zksc_ctx* ctx, uint32_t n_vars, uint32_t n_proofs, uint32_t n_products, const uint32_t* degree, zksc_tables** out) {
     if (!ctx) return ZKSC_ERR_STATE;
+    NOT_MULTI(ctx, "zksc_tables_alloc");
     return tables_alloc(ctx, n_vars, n_proofs, n_products, degree, out);
 }
 
 // common checks of the fill calls: the handle must be unbound (its `orig` tables are being replaced)
 static int fill_prepare(zksc_tables* t, uint32_t table) {
     zksc_ctx* ctx = t->ctx;
+    NOT_MULTI(ctx, "zksc_tables_fill_*");
     CK(cudaSetDevice(ctx->device));
     TRY(quiesce(ctx));
     if (table >= t->B * t->Dtot) FAIL(ZKSC_ERR_SHAPE, "table index out of range");
@@ -1110,6 +1190,7 @@ static int tail_wait(zksc_tables* t, unsigned int seq, uint64_t* out) {
 static void tail_round_done(zksc_tables* t) {
     zksc_ctx* ctx = t->ctx;
     const unsigned int idx = t->tail_done++;
+    t->last_partial = (ctx->n_ranks > 1 && t->where != 2 && (t->tail_gather_round == kNoGather || idx <= t->tail_gather_round));
     if (t->where == 0) t->where = 1;
     t->cur_n /= 2;
     if (t->tail_gather_round != kNoGather && idx == t->tail_gather_round + 1) {
@@ -1241,10 +1322,11 @@ static int tail_start(zksc_tables* t, unsigned long long half, bool sharded) {
     if (sharded) {
         a.n_ranks = ctx->n_ranks; a.rank = ctx->rank;
         for (int g = 0; g < ctx->n_ranks; g++) {
-            a.peer_units[g] = (unsigned long long*)((unsigned char*)ctx->xch_peer[g] + kXchUnitsOffset(ctx->n_ranks));
+            a.peer_units[g] = (unsigned long long*)((unsigned char*)ctx->xch_peer[g] + kXchUnitsOffset(ctx->n_ranks));   // unused with host_reduce
             a.peer_stage[g] = (const Fr*)((unsigned char*)ctx->xch_peer[g] + kXchStageOffset(ctx->n_ranks));
         }
         a.gather_round = gather_round; a.gather_local = gather_local;
+        a.host_reduce = ctx->host_reduce ? 1u : 0u;
         Geo gt = geo_of(t, 2);
         a.tail = gt.base; a.tail_tab_stride = gt.tab_stride; a.tail_proof_stride = gt.proof_stride;
     }
@@ -1271,6 +1353,7 @@ static int tail_start(zksc_tables* t, unsigned long long half, bool sharded) {
 // Apply the pending challenge with the stand-alone fold kernel (no evaluation).
 static int flush_pending(zksc_tables* t) {
     zksc_ctx* ctx = t->ctx;
+    CK(cudaSetDevice(ctx->device));
     TRY(quiesce(ctx));
     if (!t->pending) return ZKSC_OK;
     if (t->cur_n < 2) FAIL(ZKSC_ERR_STATE, "no variable left to bind");
@@ -1390,6 +1473,11 @@ static int launch_round(const zksc_tables* t, const RoundBase& base, int D, int 
 
 // after the device part of a round: fill in point 1 from the claim, remember the evaluations for the next claim
 static void finish_round(zksc_tables* t, uint64_t* out, bool skip1, bool full, uint32_t npts_cap) {
+    if (t->raw) {          // a child of a multi-GPU handle returns its shard's sums as they are; the parent finishes the totals
+        t->claim_valid = false;
+        t->last_evals_valid = full;
+        return;
+    }
     if (skip1) {
         // h_p(1) = claim_p - h_p(0)   (what the verifier checks; exact in the field)
         for (uint32_t b = 0; b < t->B; b++)
@@ -1413,8 +1501,10 @@ static void finish_round(zksc_tables* t, uint64_t* out, bool skip1, bool full, u
 }
 
 // One round: evaluations of every product of every proof at 0..npts_cap-1 (capped by degree+1).
+static int multi_round_evals(zksc_tables* t, uint64_t* out, uint32_t npts_cap);
 static int round_evals_impl(zksc_tables* t, uint64_t* out, uint32_t npts_cap) {
     zksc_ctx* ctx = t->ctx;
+    if (!t->kids.empty()) return multi_round_evals(t, out, npts_cap);
     CK(cudaSetDevice(ctx->device));
     TRY(copy_finish(t));
     if (t->vars_left == 0) FAIL(ZKSC_ERR_STATE, "all variables are bound");
@@ -1428,10 +1518,30 @@ static int round_evals_impl(zksc_tables* t, uint64_t* out, uint32_t npts_cap) {
     const auto prof_t0 = std::chrono::steady_clock::now();
     if (ctx->active_tail && ctx->active_tail != t) TRY(quiesce(ctx));
     if (t->tail_running && (!t->tail_posted || npts_cap <= ZKSC_MAX_DEGREE)) TRY(tail_stop(t));   // not the prover's call pattern
+    // the rounds of a running resident kernel: collect the posted round's evaluations (the kernel knows its own table geometry --
+    // on a sharded context the local tables may be down to one pair while the gathered table it works on next is larger)
+    auto resident_round = [&]() -> int {
+        const auto w0 = std::chrono::steady_clock::now();
+        ctx->prof_launch = std::chrono::duration<double, std::micro>(w0 - prof_t0).count();
+        int rc = tail_wait(t, t->tail_cur, out);
+        if (rc == ZKSC_OK) {
+            ctx->prof_wait = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - w0).count();
+            tail_round_done(t);
+            finish_round(t, out, true, true, npts_cap);
+            return ZKSC_OK;
+        }
+        if (rc != kTailExpired) return rc;
+        TRY(tail_expired(t));                         // the kernel gave up waiting for the host: this round goes through an ordinary launch
+        return round_evals_impl(t, out, npts_cap);    // (the resident kernel is off for this context now)
+    };
+    if (t->tail_running) return resident_round();
     const bool sharded_phase = (ctx->n_ranks > 1 && t->where != 2);
-    if (sharded_phase && !t->tail_running) {
+    if (sharded_phase) {
         uint64_t n_after = t->pending ? t->cur_n / 2 : t->cur_n;
-        if (n_after == 1) TRY(gather_tail(t));
+        if (n_after == 1) {
+            if (ctx->host_reduce) FAIL(ZKSC_ERR_STATE, "multi-GPU child asked to gather (the parent does that)");
+            TRY(gather_tail(t));
+        }
     }
     const bool reduce_ranks = (ctx->n_ranks > 1 && t->where != 2);
     uint64_t n_eval = t->pending ? t->cur_n / 2 : t->cur_n;  // table size of the round being evaluated
@@ -1445,30 +1555,17 @@ static int round_evals_impl(zksc_tables* t, uint64_t* out, uint32_t npts_cap) {
     Geo go = geo_of(t, to);
     const unsigned long long half = n_eval / 2;
     const size_t n_res = (size_t)t->B * t->E;
-    if (t->tail_running || (skip1 && tail_eligible(t, half, reduce_ranks))) {
-        // latency-bound rounds: the resident kernel runs this round and all later ones of this phase
-        int rc = ZKSC_OK;
-        if (!t->tail_running) rc = tail_start(t, half, reduce_ranks);
-        if (rc == ZKSC_OK) {
-            const auto w0 = std::chrono::steady_clock::now();
-            ctx->prof_launch = std::chrono::duration<double, std::micro>(w0 - prof_t0).count();
-            rc = tail_wait(t, t->tail_cur, out);
-            if (rc == ZKSC_OK) {
-                ctx->prof_wait = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - w0).count();
-                tail_round_done(t);
-                finish_round(t, out, true, true, npts_cap);
-                return ZKSC_OK;
-            }
-            if (rc != kTailExpired) return rc;
-            TRY(tail_expired(t));     // the host took too long between rounds: this round goes through an ordinary launch
-        } else if (rc != kTailExpired) {
-            return rc;
-        }
-        return round_evals_impl(t, out, npts_cap);    // the resident kernel is off for this context now
+    if (skip1 && tail_eligible(t, half, reduce_ranks)) {
+        // latency-bound rounds: the resident kernel runs this round and all later ones
+        const int rc = tail_start(t, half, reduce_ranks);
+        if (rc == ZKSC_OK) return resident_round();
+        if (rc != kTailExpired) return rc;
+        return round_evals_impl(t, out, npts_cap);    // could not be made resident: off for this context, ordinary launches from here
     }
-    const bool peer = reduce_ranks && ctx->p2p && n_res <= kXchCap;   // exchange + sum inside the round kernel
-    const bool mapped = (ctx->mapped_results && !reduce_ranks) || peer;
-    Fr* res = reduce_ranks ? ctx->results_send : (mapped ? ctx->results_host_dev : ctx->results_dev);
+    t->last_partial = reduce_ranks;
+    const bool peer = reduce_ranks && ctx->p2p && !ctx->host_reduce && n_res <= kXchCap;   // exchange + sum inside the round kernel
+    const bool mapped = (ctx->mapped_results && !reduce_ranks) || peer || ctx->host_reduce;
+    Fr* res = (reduce_ranks && !ctx->host_reduce) ? ctx->results_send : (mapped ? ctx->results_host_dev : ctx->results_dev);
     const unsigned int seq = ++ctx->flag_seq;
     if (peer) ctx->xch_seq++;
 
@@ -1559,28 +1656,33 @@ static void for_each_proof(zksc_ctx* ctx, uint32_t B, const std::function<void(u
     else for (uint32_t b = 0; b < B; b++) fn(b);
 }
 
+static int multi_bind(zksc_tables* t, const uint64_t* challenges);
 extern "C" int zksc_bind(zksc_tables* t, const uint64_t* challenges) {
     if (!t || !challenges) return ZKSC_ERR_STATE;
     zksc_ctx* ctx = t->ctx;
+    if (!t->kids.empty()) return multi_bind(t, challenges);
     CK(cudaSetDevice(ctx->device));
     if (t->vars_left == 0) FAIL(ZKSC_ERR_STATE, "all variables are bound");
     if (ctx->active_tail && ctx->active_tail != t) TRY(quiesce(ctx));
     if (t->tail_running && (t->tail_posted || !t->last_evals_valid)) TRY(tail_stop(t));   // bind without the round's evaluations
     if (t->pending) {
-        if (ctx->n_ranks > 1 && t->where != 2 && t->cur_n / 2 == 1) TRY(gather_tail(t));
+        if (ctx->n_ranks > 1 && !ctx->host_reduce && t->where != 2 && t->cur_n / 2 == 1) TRY(gather_tail(t));
         else TRY(flush_pending(t));
     }
-    if (ctx->n_ranks > 1 && t->where != 2 && t->cur_n == 1) TRY(gather_tail(t));
+    if (ctx->n_ranks > 1 && t->where != 2 && t->cur_n == 1) {
+        if (ctx->host_reduce) FAIL(ZKSC_ERR_STATE, "multi-GPU child asked to gather (the parent does that)");
+        TRY(gather_tail(t));
+    }
     t->pending_chal.resize(t->B);
     t->pending_tab.resize(t->B);
     // per proof: the fold table of its challenge and, for the next round, the claim = this round's polynomial of every product
     // at the challenge
-    const bool claims = t->last_evals_valid;
-    if (claims) t->claim.resize((size_t)t->B * t->P);
+    const bool claims = t->raw ? t->raw_claim_next : t->last_evals_valid;
+    if (claims && !t->raw) t->claim.resize((size_t)t->B * t->P);
     for_each_proof(ctx, t->B, [&](uint32_t b) {
         memcpy(t->pending_chal[b].l, challenges + 4 * b, 32);
         host::fold_table(load_h(challenges + 4 * b), t->pending_tab[b].w);
-        if (!claims) return;
+        if (!claims || t->raw) return;
         std::vector<FrH> ys;
         for (uint32_t p = 0; p < t->P; p++) {
             ys.clear();
@@ -1606,6 +1708,7 @@ extern "C" int zksc_bind(zksc_tables* t, const uint64_t* challenges) {
 extern "C" int zksc_residual(zksc_tables* t, uint64_t* out) {
     if (!t || !out) return ZKSC_ERR_STATE;
     zksc_ctx* ctx = t->ctx;
+    if (!t->kids.empty()) return multi_residual(t, out);
     CK(cudaSetDevice(ctx->device));
     TRY(quiesce(ctx));
     if (ctx->n_ranks > 1 && t->where != 2) {
@@ -1622,10 +1725,321 @@ extern "C" int zksc_residual(zksc_tables* t, uint64_t* out) {
     return ZKSC_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// single-process multi-GPU: one host thread, G devices (the reference's caller, gkr/src/protocol.rs:85, is one process)
+// ------------------------------------------------------------------------------------------------
+// fn(g) on every child, concurrently (one pool thread per device) inside a GpuPoolSession, one after the other otherwise
+static int for_each_kid(zksc_ctx* ctx, const std::function<int(uint32_t)>& fn) {
+    const uint32_t G = (uint32_t)ctx->kids.size();
+    std::vector<int> rc(G, ZKSC_OK);
+    const std::function<void(uint32_t)> body = [&](uint32_t g) { rc[g] = fn(g); };
+    if (ctx->gpu_pool && ctx->gpu_pool_active) ctx->gpu_pool->parallel_for(G, body);
+    else for (uint32_t g = 0; g < G; g++) body(g);
+    for (uint32_t g = 0; g < G; g++)
+        if (rc[g] != ZKSC_OK) { ctx->err = "device " + std::to_string(ctx->kids[g]->device) + ": " + ctx->kids[g]->err; return rc[g]; }
+    return ZKSC_OK;
+}
+
+extern "C" int zksc_ctx_create_multi(const int* devices, int n_devices, zksc_ctx** out) {
+    if (!out) return ZKSC_ERR_SHAPE;
+    *out = nullptr;
+    if (!devices || n_devices < 1 || n_devices > kMaxRanks || (n_devices & (n_devices - 1))) {
+        g_create_error = "zksc_ctx_create_multi: the device count must be a power of two, at most 8";
+        return ZKSC_ERR_SHAPE;
+    }
+    for (int a = 0; a < n_devices; a++)
+        for (int b = 0; b < a; b++)
+            if (devices[a] == devices[b]) { g_create_error = "zksc_ctx_create_multi: the devices must be distinct"; return ZKSC_ERR_SHAPE; }
+    if (n_devices == 1) return zksc_ctx_create(devices[0], out);
+    zksc_ctx* ctx = new zksc_ctx();
+    auto fail = [&](int rc, const std::string& why) {
+        g_create_error = why;
+        zksc_ctx_destroy(ctx);
+        return rc;
+    };
+    const int G = n_devices;
+    for (int g = 0; g < G; g++) {
+        zksc_ctx* k = nullptr;
+        const int rc = zksc_ctx_create(devices[g], &k);
+        if (rc != ZKSC_OK) {
+            if (ctx->kids.empty()) { delete ctx; return rc; }      // g_create_error is set
+            return fail(rc, g_create_error);
+        }
+        k->parent = ctx; k->rank = g; k->n_ranks = G; k->host_reduce = true;
+        ctx->kids.push_back(k);
+    }
+    ctx->device = devices[0];
+    ctx->sms = ctx->kids[0]->sms;
+    {
+        unsigned long long ge = kGatherDefault;
+        const char* e_ = getenv("ZKSC_GATHER_ENTRIES");
+        if (e_ && atoll(e_) > 0) ge = (unsigned long long)atoll(e_);
+        while (ge & (ge - 1)) ge &= ge - 1;
+        if (ge < 2ull * G) ge = 2ull * G;
+        ctx->gather_entries = ge;
+        for (zksc_ctx* k : ctx->kids) k->gather_entries = ge;
+    }
+    // every device reads every other device's gather stage (and device 0's upload staging) directly: peer access over NVLink
+    const size_t bytes = kXchStageOffset(G) + kXchStageElems * sizeof(Fr);
+    for (int a = 0; a < G; a++) {
+        cudaError_t e = cudaSetDevice(devices[a]);
+        for (int b = 0; b < G && e == cudaSuccess; b++) {
+            if (a == b) continue;
+            int can = 0;
+            e = cudaDeviceCanAccessPeer(&can, devices[a], devices[b]);
+            if (e == cudaSuccess && !can) return fail(ZKSC_ERR_UNSUPPORTED, "zksc_ctx_create_multi: the devices cannot access each other's memory (no NVLink / PCIe peer path)");
+            if (e == cudaSuccess) {
+                e = cudaDeviceEnablePeerAccess(devices[b], 0);
+                if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+            }
+        }
+        if (e == cudaSuccess) e = cudaMalloc(&ctx->kids[a]->xch_local, bytes);
+        if (e == cudaSuccess) e = cudaMemset(ctx->kids[a]->xch_local, 0, bytes);
+        if (e != cudaSuccess) return fail(ZKSC_ERR_CUDA, std::string("zksc_ctx_create_multi: ") + cudaGetErrorString(e));
+    }
+    for (int a = 0; a < G; a++) {
+        for (int b = 0; b < G; b++) ctx->kids[a]->xch_peer[b] = ctx->kids[b]->xch_local;
+        ctx->kids[a]->p2p = true;
+    }
+    ctx->gpu_pool = new HostPool(G - 1);
+    *out = ctx;
+    return ZKSC_OK;
+}
+
+extern "C" int zksc_ctx_devices(const zksc_ctx* ctx) { return ctx ? (ctx->kids.empty() ? 1 : (int)ctx->kids.size()) : 0; }
+
+// the parent handle: shapes and the claim / evaluation bookkeeping of the one transcript; no device memory of its own
+static int multi_tables_new(zksc_ctx* ctx, uint32_t n_vars, uint32_t B, uint32_t P, const uint32_t* degree, zksc_tables** out) {
+    *out = nullptr;
+    if (!degree) return ZKSC_ERR_SHAPE;
+    if (B < 1 || P < 1 || P > ZKSC_MAX_PRODUCTS) FAIL(ZKSC_ERR_SHAPE, "need 1 <= n_products <= ZKSC_MAX_PRODUCTS and n_proofs >= 1");
+    zksc_tables* t = new zksc_tables();
+    t->ctx = ctx; t->n_vars = n_vars; t->B = B; t->P = P; t->Dtot = 0; t->E = 0;
+    for (uint32_t p = 0; p < P; p++) {
+        if (degree[p] < 1 || degree[p] > ZKSC_MAX_DEGREE) { delete t; FAIL(ZKSC_ERR_UNSUPPORTED, "product degree must be in 1..ZKSC_MAX_DEGREE"); }
+        t->deg[p] = degree[p]; t->koff[p] = t->Dtot; t->eoff[p] = t->E;
+        t->Dtot += degree[p]; t->E += degree[p] + 1;
+    }
+    t->n_local0 = 1ull << n_vars;
+    t->vars_left = n_vars; t->cur_n = t->n_local0; t->where = 0; t->pending = false;
+    *out = t;
+    return ZKSC_OK;
+}
+static void multi_adopt(zksc_tables* t, std::vector<zksc_tables*>& kids) {
+    for (zksc_tables* k : kids) k->raw = true;
+    t->kids = kids;
+}
+static int multi_tables_synth(zksc_ctx* ctx, uint32_t n_vars, uint32_t B, uint32_t P, const uint32_t* degree, uint64_t seed, zksc_tables** out) {
+    zksc_tables* t = nullptr;
+    TRY(multi_tables_new(ctx, n_vars, B, P, degree, &t));
+    std::vector<zksc_tables*> kids(ctx->kids.size(), nullptr);
+    const int rc = for_each_kid(ctx, [&](uint32_t g) { return zksc_tables_synth(ctx->kids[g], n_vars, B, P, degree, seed, &kids[g]); });
+    if (rc != ZKSC_OK) { for (zksc_tables* k : kids) zksc_tables_free(k); delete t; return rc; }
+    multi_adopt(t, kids);
+    *out = t;
+    return ZKSC_OK;
+}
+// Every table crosses PCIe ONCE: it is staged chunk by chunk in device 0's memory, and every device picks the entries of its
+// shard (index = rank mod G) out of that staging buffer over NVLink.
+static int multi_tables_upload(zksc_ctx* ctx, uint32_t n_vars, uint32_t B, uint32_t P, const uint32_t* degree, const uint64_t* const* host_tables,
+                               zksc_tables** out) {
+    zksc_tables* t = nullptr;
+    TRY(multi_tables_new(ctx, n_vars, B, P, degree, &t));
+    const uint32_t G = (uint32_t)ctx->kids.size();
+    std::vector<zksc_tables*> kids(G, nullptr);
+    auto bail = [&](int rc, const std::string& why) {
+        for (zksc_tables* k : kids) zksc_tables_free(k);
+        delete t;
+        ctx->err = why;
+        return rc;
+    };
+    for (uint32_t g = 0; g < G; g++) {
+        const int rc = tables_alloc(ctx->kids[g], n_vars, B, P, degree, &kids[g]);
+        if (rc != ZKSC_OK) return bail(rc, ctx->kids[g]->err);
+    }
+    const uint64_t N = 1ull << n_vars, chunk = std::min<uint64_t>(N, 1ull << 22);
+    zksc_ctx* k0 = ctx->kids[0];
+    Fr* stage = nullptr;
+    std::vector<cudaEvent_t> picked(G, nullptr);
+    cudaEvent_t staged = nullptr;
+    cudaError_t e = cudaSetDevice(k0->device);
+    if (e == cudaSuccess) e = cudaMalloc(&stage, chunk * sizeof(Fr));
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&staged, cudaEventDisableTiming);
+    for (uint32_t g = 0; g < G && e == cudaSuccess; g++) {
+        e = cudaSetDevice(ctx->kids[g]->device);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&picked[g], cudaEventDisableTiming);
+    }
+    const size_t n_tabs = (size_t)B * t->Dtot;
+    bool first = true;
+    for (size_t i = 0; i < n_tabs && e == cudaSuccess; i++)
+        for (uint64_t c0 = 0; c0 < N && e == cudaSuccess; c0 += chunk) {
+            e = cudaSetDevice(k0->device);
+            for (uint32_t g = 0; g < G && e == cudaSuccess && !first; g++) e = cudaStreamWaitEvent(k0->stream, picked[g], 0);   // the buffer is free again
+            if (e == cudaSuccess) e = cudaMemcpyAsync(stage, host_tables[i] + 4 * c0, chunk * sizeof(Fr), cudaMemcpyHostToDevice, k0->stream);
+            if (e == cudaSuccess) e = cudaEventRecord(staged, k0->stream);
+            for (uint32_t g = 0; g < G && e == cudaSuccess; g++) {
+                zksc_ctx* k = ctx->kids[g];
+                e = cudaSetDevice(k->device);
+                if (e == cudaSuccess) e = cudaStreamWaitEvent(k->stream, staged, 0);
+                if (e != cudaSuccess) break;
+                const uint64_t n_pick = chunk / G;
+                pick_shard_kernel<<<grid_for(k, n_pick, 256, 8), 256, 0, k->stream>>>(stage, kids[g]->orig + i * kids[g]->n_local0 + c0 / G, n_pick, G, g);
+                k->launches++;
+                e = cudaGetLastError();
+                if (e == cudaSuccess) e = cudaEventRecord(picked[g], k->stream);
+            }
+            first = false;
+        }
+    for (uint32_t g = 0; g < G; g++) {
+        cudaSetDevice(ctx->kids[g]->device);
+        const cudaError_t e2 = cudaStreamSynchronize(ctx->kids[g]->stream);      // the host buffers are only borrowed for the call
+        if (e == cudaSuccess) e = e2;
+        if (picked[g]) cudaEventDestroy(picked[g]);
+    }
+    cudaSetDevice(k0->device);
+    if (staged) cudaEventDestroy(staged);
+    cudaFree(stage);
+    if (e != cudaSuccess) return bail(e == cudaErrorMemoryAllocation ? ZKSC_ERR_OOM : ZKSC_ERR_CUDA, std::string("multi-GPU upload: ") + cudaGetErrorString(e));
+    multi_adopt(t, kids);
+    *out = t;
+    return ZKSC_OK;
+}
+static int multi_tables_reset(zksc_tables* t) {
+    for (zksc_tables* k : t->kids) { const int rc = zksc_tables_reset(k); if (rc != ZKSC_OK) { t->ctx->err = k->ctx->err; return rc; } }
+    t->vars_left = t->n_vars;
+    t->pending = false;
+    t->last_evals_valid = false;
+    t->claim_valid = false;
+    return ZKSC_OK;
+}
+static int multi_tables_free(zksc_tables* t) {
+    for (zksc_tables* k : t->kids) zksc_tables_free(k);
+    delete t;
+    return ZKSC_OK;
+}
+// Without a resident kernel (disabled, or degrees it does not take) the shards shrink to one entry per table and rank; the parent
+// collects those G entries per table through the host and hands every device the whole residual table (replicated from then on).
+static int multi_gather(zksc_tables* t) {
+    zksc_ctx* ctx = t->ctx;
+    const uint32_t G = (uint32_t)ctx->kids.size();
+    const size_t nt = (size_t)t->B * t->Dtot;
+    std::vector<Fr> mine(nt * G), all(nt * G);
+    for (uint32_t g = 0; g < G; g++) {
+        zksc_tables* k = t->kids[g];
+        zksc_ctx* kc = k->ctx;
+        CK(cudaSetDevice(kc->device));
+        { const int rc = flush_pending(k); if (rc != ZKSC_OK) { ctx->err = kc->err; return rc; } }
+        if (k->cur_n != 1) FAIL(ZKSC_ERR_STATE, "multi_gather: local tables not exhausted");
+        Geo ge = geo_of(k, k->where);
+        cudaError_t e = cudaMemcpy2DAsync(mine.data() + (size_t)g * nt, sizeof(Fr), ge.base, ge.tab_stride * sizeof(Fr), sizeof(Fr), nt, cudaMemcpyDeviceToHost, kc->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(kc->stream);
+        if (e != cudaSuccess) FAIL(ZKSC_ERR_CUDA, std::string("multi_gather: ") + cudaGetErrorString(e));
+    }
+    for (size_t tab = 0; tab < nt; tab++)
+        for (uint32_t g = 0; g < G; g++) all[tab * G + g] = mine[(size_t)g * nt + tab];     // entry index of the residual table == rank
+    for (uint32_t g = 0; g < G; g++) {
+        zksc_tables* k = t->kids[g];
+        zksc_ctx* kc = k->ctx;
+        CK(cudaSetDevice(kc->device));
+        cudaError_t e = cudaMemcpy2DAsync(k->tail, k->tail_stride * sizeof(Fr), all.data(), (size_t)G * sizeof(Fr), (size_t)G * sizeof(Fr), nt, cudaMemcpyHostToDevice, kc->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(kc->stream);
+        if (e != cudaSuccess) FAIL(ZKSC_ERR_CUDA, std::string("multi_gather: ") + cudaGetErrorString(e));
+        k->where = 2;
+        k->cur_n = G;
+    }
+    return ZKSC_OK;
+}
+static int multi_gather_if_due(zksc_tables* t) {
+    const zksc_tables* k0 = t->kids[0];
+    if (k0->tail_running || k0->where == 2) return ZKSC_OK;
+    const uint64_t n_after = k0->pending ? k0->cur_n / 2 : k0->cur_n;
+    return n_after == 1 ? multi_gather(t) : ZKSC_OK;
+}
+static int multi_round_evals(zksc_tables* t, uint64_t* out, uint32_t npts_cap) {
+    zksc_ctx* ctx = t->ctx;
+    if (t->vars_left == 0) FAIL(ZKSC_ERR_STATE, "all variables are bound");
+    if (t->r0_valid && t->vars_left == t->n_vars && !t->pending && npts_cap > ZKSC_MAX_DEGREE) {
+        memcpy(out, t->r0_cache.data(), t->r0_cache.size() * sizeof(uint64_t));
+        t->r0_valid = false;
+        t->last_evals = t->r0_cache;
+        t->last_evals_valid = true;
+        return ZKSC_OK;
+    }
+    GpuPoolSession session(ctx);
+    TRY(multi_gather_if_due(t));
+    const uint32_t G = (uint32_t)ctx->kids.size();
+    const size_t n_res = (size_t)t->B * t->E;
+    const bool fold = t->pending, full = npts_cap > ZKSC_MAX_DEGREE;
+    const bool skip1 = fold && full && t->claim_valid;
+    static thread_local std::vector<uint64_t> part_store;
+    part_store.assign((size_t)G * n_res * 4, 0);
+    uint64_t* const part = part_store.data();      // (the worker threads must not name the thread_local itself: they would get their own)
+    TRY(for_each_kid(ctx, [&](uint32_t g) { return round_evals_impl(t->kids[g], part + (size_t)g * n_res * 4, npts_cap); }));
+    // a sharded round: the G partial evaluations add up; a replicated round (after the gather): every device holds the whole value
+    const bool partial = t->kids[0]->last_partial;
+    for (size_t i = 0; i < n_res; i++) {
+        FrH acc = load_h(&part[4 * i]);
+        if (partial) for (uint32_t g = 1; g < G; g++) acc = host::add(acc, load_h(&part[((size_t)g * n_res + i) * 4]));
+        store_h(out + 4 * i, acc);
+    }
+    if (fold) t->pending = false;
+    finish_round(t, out, skip1, full, npts_cap);
+    return ZKSC_OK;
+}
+static int multi_bind(zksc_tables* t, const uint64_t* challenges) {
+    zksc_ctx* ctx = t->ctx;
+    if (t->vars_left == 0) FAIL(ZKSC_ERR_STATE, "all variables are bound");
+    GpuPoolSession session(ctx);
+    const bool claims = t->last_evals_valid;
+    if (claims) {
+        t->claim.resize((size_t)t->B * t->P);
+        for_each_proof(ctx, t->B, [&](uint32_t b) {
+            std::vector<FrH> ys;
+            for (uint32_t p = 0; p < t->P; p++) {
+                ys.clear();
+                for (uint32_t i = 0; i <= t->deg[p]; i++) ys.push_back(load_h(&t->last_evals[((size_t)b * t->E + t->eoff[p] + i) * 4]));
+                t->claim[(size_t)b * t->P + p] = host::SparseUnivariatePolynomial::evaluate_evals_at(ys, load_h(challenges + 4 * b));
+            }
+        });
+    }
+    // a bind on top of an unapplied one flushes the first (stand-alone fold) -- which may be what exhausts the shards
+    if (t->kids[0]->pending && !t->kids[0]->tail_running) {
+        const zksc_tables* k0 = t->kids[0];
+        if (k0->where != 2 && k0->cur_n / 2 == 1) TRY(multi_gather(t));
+    }
+    if (!t->kids[0]->pending && !t->kids[0]->tail_running && t->kids[0]->where != 2 && t->kids[0]->cur_n == 1) TRY(multi_gather(t));
+    TRY(for_each_kid(ctx, [&](uint32_t g) {
+        t->kids[g]->raw_claim_next = claims;
+        return zksc_bind(t->kids[g], challenges);
+    }));
+    t->pending = true;
+    t->vars_left--;
+    t->claim_valid = claims;
+    t->last_evals_valid = false;
+    return ZKSC_OK;
+}
+static int multi_residual(zksc_tables* t, uint64_t* out) {
+    zksc_ctx* ctx = t->ctx;
+    for (zksc_tables* k : t->kids) { const int rc = tail_stop(k); if (rc != ZKSC_OK) { ctx->err = k->ctx->err; return rc; } }
+    TRY(multi_gather_if_due(t));
+    if (t->kids[0]->where != 2) FAIL(ZKSC_ERR_UNSUPPORTED, "sharded residual is only available once each device holds one entry per table");
+    for (zksc_tables* k : t->kids) {
+        CK(cudaSetDevice(k->ctx->device));
+        const int rc = flush_pending(k);
+        if (rc != ZKSC_OK) { ctx->err = k->ctx->err; return rc; }
+    }
+    t->pending = false;
+    const int rc = zksc_residual(t->kids[0], out);
+    if (rc != ZKSC_OK) ctx->err = t->kids[0]->ctx->err;
+    return rc;
+}
+
 extern "C" int zksc_poly_sum(zksc_tables* t, uint64_t* out) {
     if (!t || !out) return ZKSC_ERR_STATE;
     zksc_ctx* ctx = t->ctx;
     if (t->vars_left != t->n_vars || t->pending) FAIL(ZKSC_ERR_STATE, "zksc_poly_sum needs unbound tables");
+    GpuPoolSession gpu_session(t->kids.empty() ? nullptr : ctx);
     std::vector<uint64_t> ev((size_t)t->B * t->E * 4);
     if (t->n_vars == 0) {
         // a single entry per table: the sum is the product itself
@@ -1661,6 +2075,7 @@ extern "C" int zksc_poly_sum(zksc_tables* t, uint64_t* out) {
 extern "C" int zksc_tables_to_bytes(zksc_tables* t, uint32_t proof, uint8_t* out) {
     if (!t || !out) return ZKSC_ERR_STATE;
     zksc_ctx* ctx = t->ctx;
+    NOT_MULTI(ctx, "zksc_tables_to_bytes");
     CK(cudaSetDevice(ctx->device));
     TRY(quiesce(ctx));
     if (ctx->n_ranks != 1) FAIL(ZKSC_ERR_UNSUPPORTED, "zksc_tables_to_bytes: single-rank contexts only");
@@ -1705,6 +2120,7 @@ extern "C" int zksc_prove(zksc_tables* t, int protocol, const uint64_t* sums, ui
     if (t->vars_left != t->n_vars || t->pending) FAIL(ZKSC_ERR_STATE, "tables are partially bound; call zksc_tables_reset first");
     const uint32_t stride = zksc_msg_stride(protocol, t->P, t->deg);
     const uint32_t B = t->B, n = t->n_vars;
+    GpuPoolSession gpu_session(t->kids.empty() ? nullptr : ctx);
     std::vector<host::FiatShamirTranscript> tr(B);
     if (protocol == ZKSC_PROTO_MULTI_FULL) {
         // transcript.commit(&composed_poly_to_bytes(&poly))  multi_composed_sumcheck.rs:52
@@ -1858,6 +2274,7 @@ extern "C" int zksc_verify_rounds(int protocol, uint32_t n_vars, uint32_t msg_st
 
 extern "C" int zksc_evaluate(zksc_tables* t, const uint64_t* points, uint64_t* out) {
     if (!t || !points || !out) return ZKSC_ERR_STATE;
+    GpuPoolSession gpu_session(t->kids.empty() ? nullptr : t->ctx);
     zksc_tables_reset(t);
     std::vector<uint64_t> chal((size_t)t->B * 4);
     for (uint32_t j = 0; j < t->n_vars; j++) {
@@ -1885,6 +2302,7 @@ extern "C" int zksc_evaluate(zksc_tables* t, const uint64_t* points, uint64_t* o
 
 extern "C" int zksc_ml_partial_evaluation(zksc_ctx* ctx, const uint64_t* evals, uint64_t n, const uint64_t* r, uint32_t variable_index, uint64_t* out) {
     if (!ctx) return ZKSC_ERR_STATE;
+    if (!ctx->kids.empty()) ctx = ctx->kids[0];      // stand-alone vector operations run on the first device
     if (!evals || !r || !out) FAIL(ZKSC_ERR_SHAPE, "NULL argument");
     if (n < 2 || (n & (n - 1))) FAIL(ZKSC_ERR_SHAPE, "Number of evaluations must be a power of 2 (and at least 2 to bind a variable)");
     uint32_t n_vars_ml = 0;
@@ -1913,6 +2331,7 @@ extern "C" int zksc_ml_partial_evaluation(zksc_ctx* ctx, const uint64_t* evals, 
 
 extern "C" int zksc_ml_evaluation(zksc_ctx* ctx, const uint64_t* evals, uint64_t n, const uint64_t* points, uint32_t n_points, uint64_t* out) {
     if (!ctx) return ZKSC_ERR_STATE;
+    if (!ctx->kids.empty()) ctx = ctx->kids[0];      // stand-alone vector operations run on the first device
     if (!evals || !out || (n_points && !points)) FAIL(ZKSC_ERR_SHAPE, "NULL argument");
     if (n < 1 || (n & (n - 1))) FAIL(ZKSC_ERR_SHAPE, "Number of evaluations must be a power of 2");
     if ((1ull << n_points) != n) FAIL(ZKSC_ERR_SHAPE, "Number of evaluation points must match the number of variables");
@@ -1940,6 +2359,7 @@ extern "C" int zksc_ml_evaluation(zksc_ctx* ctx, const uint64_t* evals, uint64_t
 
 extern "C" int zksc_ml_outer(zksc_ctx* ctx, int mul, const uint64_t* a, uint64_t na, const uint64_t* b, uint64_t nb, uint64_t* out) {
     if (!ctx) return ZKSC_ERR_STATE;
+    if (!ctx->kids.empty()) ctx = ctx->kids[0];      // stand-alone vector operations run on the first device
     if (!a || !b || !out || !na || !nb) FAIL(ZKSC_ERR_SHAPE, "empty operand");
     unsigned long long n = 0;
     if (__builtin_umulll_overflow(na, nb, &n) || (n & (n - 1))) FAIL(ZKSC_ERR_SHAPE, "Number of evaluations must be a power of 2");
@@ -1961,6 +2381,7 @@ extern "C" int zksc_ml_outer(zksc_ctx* ctx, int mul, const uint64_t* a, uint64_t
 
 extern "C" int zksc_ml_elementwise(zksc_ctx* ctx, int op, const uint64_t* a, const uint64_t* b, uint64_t n, uint64_t* out) {
     if (!ctx) return ZKSC_ERR_STATE;
+    if (!ctx->kids.empty()) ctx = ctx->kids[0];      // stand-alone vector operations run on the first device
     if (!a || !b || !out || !n) FAIL(ZKSC_ERR_SHAPE, "empty operand");
     if (op < 0 || op > 3) FAIL(ZKSC_ERR_SHAPE, "op");
     CK(cudaSetDevice(ctx->device));
