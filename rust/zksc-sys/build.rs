@@ -13,7 +13,7 @@ fn main() {
     println!("cargo:rustc-link-search=native={}", libdir.display());
     println!("cargo:rustc-link-lib=dylib=zksc");
     println!("cargo:rustc-link-arg=-Wl,-rpath,{}", libdir.display());
-    for f in ["zksc.cu", "kernels.cuh", "tail_kernel.cuh", "tail_inst.cu", "round_inst.cu", "fr.cuh", "aux_kernels.cuh", "host_field.hpp"] {
+    for f in ["zksc.cu", "kernels.cuh", "resident_kernel.cuh", "res_inst.cu", "round_inst.cu", "fr.cuh", "aux_kernels.cuh", "host_field.hpp"] {
         println!("cargo:rerun-if-changed={}", csrc.join(f).display());
     }
     println!("cargo:rerun-if-changed={}", root.join("include/zksc.h").display());
