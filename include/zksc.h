@@ -237,6 +237,24 @@ int zksc_ml_outer(zksc_ctx* ctx, int mul, const uint64_t* a, uint64_t na, const 
  * tables (composed_multilinear.rs:105-111): op 0 add, 1 sub, 2 mul, 3 scale by b[0] */
 int zksc_ml_elementwise(zksc_ctx* ctx, int op, const uint64_t* a, const uint64_t* b, uint64_t n, uint64_t* out);
 
+/* ---- multilinear KZG over BLS12-381 G1 (kzg/src/multilinear_kzg.rs) -----------------------------------
+ * A G1 point crosses the boundary in ark-ec 0.4's in-memory form of `G1Projective` (short_weierstrass::Projective: Jacobian X, Y, Z,
+ * each an Fq of 6 x uint64_t little-endian limbs in Montgomery form, R = 2^384; Z = 0 is the identity): 18 x uint64_t per point, so a
+ * `&[G1Projective]` (TrustedSetup::powers_of_tau_in_g1, kzg/src/trusted_setup.rs:10-13) is passed unchanged.  Results come back
+ * normalised (Z = 1 in Montgomery form, or the identity as (1, 1, 0)): equal as group elements to what the reference computes, and
+ * bit-identical to it after `into_affine()`.
+ * zksc_g1_msm: sum_i scalars[i] * points[i] -- MultilinearKZG::commitment (multilinear_kzg.rs:33-48: evaluations zipped with
+ *   powers_of_tau_in_g1, one mul_bigint each, summed).  scalars: n Fr elements (Montgomery); points: n x 18; out: 18.
+ * zksc_kzg_open: MultilinearKZG::open (multilinear_kzg.rs:50-88): per variable the quotient f(1,.) - f(0,.) (get_poly_quotient,
+ *   kzg/src/utils.rs:12-17) blown up to all variables by repetition (add_to_front / duplicate_evaluation,
+ *   evaluation_form.rs:86-96,112-119) is committed, and the polynomial is replaced by its remainder partial_evaluation(point, 0)
+ *   (get_poly_remainder, utils.rs:5-10).  evals: 2^n_vars elements; points: n_vars elements; srs_g1: 2^n_vars x 18;
+ *   out_evaluation: 1 element (= poly.evaluation(points)); out_proofs: n_vars x 18.
+ * The pairing check of MultilinearKZG::verify stays with the caller (ark-ec); it is out of scope here. */
+int zksc_g1_msm(zksc_ctx* ctx, const uint64_t* scalars, const uint64_t* points, uint64_t n, uint64_t* out);
+int zksc_kzg_open(zksc_ctx* ctx, const uint64_t* evals, uint32_t n_vars, const uint64_t* points, const uint64_t* srs_g1, uint64_t* out_evaluation,
+                  uint64_t* out_proofs);
+
 /* ---- host helpers (no device) -------------------------------------------------------------------- */
 /* F::from(u64) in Montgomery form; canonical <-> Montgomery; be32 (sumcheck/src/utils.rs:7-9) */
 void zksc_fr_from_u64(uint64_t x, uint64_t out[4]);

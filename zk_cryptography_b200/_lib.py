@@ -85,6 +85,8 @@ def lib():
         "zksc_evaluate": (ctypes.c_int, [vp, _u64p, _u64p]),
         "zksc_gkr_total_rounds": (ctypes.c_uint64, [ctypes.c_uint32]),
         "zksc_gkr_prove": (ctypes.c_int, [vp, ctypes.c_uint32, _u32p, _u8p, _u32p, _u32p, ctypes.POINTER(_u64p), _u64p, _u64p, _u64p, _u64p, _u64p, _u64p, _u32p, _u64p]),
+        "zksc_g1_msm": (ctypes.c_int, [vp, _u64p, _u64p, ctypes.c_uint64, _u64p]),
+        "zksc_kzg_open": (ctypes.c_int, [vp, _u64p, ctypes.c_uint32, _u64p, _u64p, _u64p, _u64p]),
         "zksc_ml_partial_evaluation": (ctypes.c_int, [vp, _u64p, ctypes.c_uint64, _u64p, ctypes.c_uint32, _u64p]),
         "zksc_ml_evaluation": (ctypes.c_int, [vp, _u64p, ctypes.c_uint64, _u64p, ctypes.c_uint32, _u64p]),
         "zksc_ml_outer": (ctypes.c_int, [vp, ctypes.c_int, _u64p, ctypes.c_uint64, _u64p, ctypes.c_uint64, _u64p]),

@@ -28,6 +28,7 @@
 #include "aux_kernels.cuh"
 #include "kernels.cuh"
 #include "resident_kernel.cuh"
+#include "g1.cuh"
 
 #if __has_include(<nccl.h>)
 #include <nccl.h>
@@ -2399,6 +2400,106 @@ extern "C" int zksc_ml_elementwise(zksc_ctx* ctx, int op, const uint64_t* a, con
     CK(cudaMemcpyAsync(out, dout.p, n * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return ZKSC_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// multilinear KZG over BLS12-381 G1: commitment and opening proofs
+// ------------------------------------------------------------------------------------------------
+// sum_i scalars[i mod period] * points[i] on the device (g1.cuh); scalars and points already in device memory
+static int g1_msm_device(zksc_ctx* ctx, const Fr* d_scalars, unsigned long long period, const g1::Jac* d_points, unsigned long long n, g1::Jac* d_out) {
+    uint8_t* digits = nullptr;
+    g1::Jac *buckets = nullptr, *windows = nullptr;
+    CK(cudaMallocAsync((void**)&digits, (size_t)g1::kWindows * n, ctx->stream));
+    CK(cudaMallocAsync((void**)&buckets, (size_t)g1::kWindows * g1::kBuckets * sizeof(g1::Jac), ctx->stream));
+    CK(cudaMallocAsync((void**)&windows, (size_t)g1::kWindows * sizeof(g1::Jac), ctx->stream));
+    g1::msm_digits_kernel<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(d_scalars, n, period, digits);
+    g1::msm_bucket_kernel<<<g1::kWindows * 256 / 128, 128, 0, ctx->stream>>>(digits, d_points, n, buckets);
+    g1::msm_window_kernel<<<1, g1::kWindows, 0, ctx->stream>>>(buckets, windows);
+    g1::msm_combine_kernel<<<1, 1, 0, ctx->stream>>>(windows, d_out);
+    ctx->launches += 4;
+    CK(cudaGetLastError());
+    cudaFreeAsync(digits, ctx->stream); cudaFreeAsync(buckets, ctx->stream); cudaFreeAsync(windows, ctx->stream);
+    return ZKSC_OK;
+}
+
+extern "C" int zksc_g1_msm(zksc_ctx* ctx, const uint64_t* scalars, const uint64_t* points, uint64_t n, uint64_t* out) {
+    if (!ctx) return ZKSC_ERR_STATE;
+    if (!ctx->kids.empty()) ctx = ctx->kids[0];
+    if (!scalars || !points || !out || n == 0) FAIL(ZKSC_ERR_SHAPE, "empty operand");
+    static_assert(sizeof(g1::Jac) == 144, "ark-ec Projective<g1::Config> is 18 x u64");
+    CK(cudaSetDevice(ctx->device));
+    TRY(quiesce(ctx));
+    Fr* ds = nullptr;
+    g1::Jac *dp = nullptr, *dout = nullptr;
+    CK(cudaMallocAsync((void**)&ds, n * sizeof(Fr), ctx->stream));
+    CK(cudaMallocAsync((void**)&dp, n * sizeof(g1::Jac), ctx->stream));
+    CK(cudaMallocAsync((void**)&dout, sizeof(g1::Jac), ctx->stream));
+    CK(cudaMemcpyAsync(ds, scalars, n * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(dp, points, n * sizeof(g1::Jac), cudaMemcpyHostToDevice, ctx->stream));
+    int rc = g1_msm_device(ctx, ds, 0, dp, n, dout);
+    if (rc == ZKSC_OK) {
+        cudaError_t e = cudaMemcpyAsync(out, dout, sizeof(g1::Jac), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { ctx->err = std::string("zksc_g1_msm: ") + cudaGetErrorString(e); rc = ZKSC_ERR_CUDA; }
+    }
+    cudaFreeAsync(ds, ctx->stream); cudaFreeAsync(dp, ctx->stream); cudaFreeAsync(dout, ctx->stream);
+    return rc;
+}
+
+// q = f(1, .) - f(0, .): second half minus first half (get_poly_quotient, kzg/src/utils.rs:12-17)
+__global__ void __launch_bounds__(256) kzg_quotient_kernel(const Fr* f, Fr* q, unsigned long long half) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < half; i += stride) st256(q + i, fr_sub(ld256(f + half + i), ld256(f + i)));
+}
+
+extern "C" int zksc_kzg_open(zksc_ctx* ctx, const uint64_t* evals, uint32_t n_vars, const uint64_t* points, const uint64_t* srs_g1, uint64_t* out_evaluation,
+                             uint64_t* out_proofs) {
+    if (!ctx) return ZKSC_ERR_STATE;
+    if (!ctx->kids.empty()) ctx = ctx->kids[0];
+    if (!evals || !points || !srs_g1 || !out_evaluation || !out_proofs) FAIL(ZKSC_ERR_SHAPE, "NULL argument");
+    if (n_vars < 1 || n_vars > 30) FAIL(ZKSC_ERR_SHAPE, "zksc_kzg_open: 1 <= n_vars <= 30");
+    CK(cudaSetDevice(ctx->device));
+    TRY(quiesce(ctx));
+    const unsigned long long N = 1ull << n_vars;
+    Fr *poly = nullptr, *quot = nullptr;
+    g1::Jac *srs = nullptr, *proofs = nullptr;
+    CK(cudaMallocAsync((void**)&poly, N * sizeof(Fr), ctx->stream));
+    CK(cudaMallocAsync((void**)&quot, std::max<unsigned long long>(N / 2, 2) * sizeof(Fr), ctx->stream));
+    CK(cudaMallocAsync((void**)&srs, N * sizeof(g1::Jac), ctx->stream));
+    CK(cudaMallocAsync((void**)&proofs, (size_t)n_vars * sizeof(g1::Jac), ctx->stream));
+    CK(cudaMemcpyAsync(poly, evals, N * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(srs, srs_g1, N * sizeof(g1::Jac), cudaMemcpyHostToDevice, ctx->stream));
+    int rc = ZKSC_OK;
+    unsigned long long cur = N;
+    // multilinear_kzg.rs:58-82: per variable, quotient = f(1,.) - f(0,.), blown up to all n variables by repetition
+    // (add_to_front / duplicate_evaluation: a periodic scalar vector, so the MSM just indexes the quotient modulo its length),
+    // committed; then the polynomial is replaced by its remainder = partial_evaluation(point, 0)
+    for (uint32_t v = 0; v < n_vars && rc == ZKSC_OK; v++) {
+        const unsigned long long half = cur / 2;
+        kzg_quotient_kernel<<<grid_for(ctx, half, 256, 8), 256, 0, ctx->stream>>>(poly, quot, half);
+        ctx->launches++;
+        rc = g1_msm_device(ctx, quot, half, srs, N, proofs + v);
+        if (rc != ZKSC_OK) break;
+        FoldArgs a;
+        a.in = poly; a.out = poly;      // variable 0, in place (the remainder; for the last variable: the evaluation itself)
+        a.in_tab_stride = a.in_proof_stride = a.out_tab_stride = a.out_proof_stride = 0;
+        a.n_out = half; a.s = half; a.n_tabs = 1;
+        memcpy(a.chal[0].l, points + 4 * v, 32);
+        fold_kernel<<<dim3(grid_for(ctx, a.n_out, 256, 8), 1), 256, 0, ctx->stream>>>(a);
+        ctx->launches++;
+        cur = half;
+    }
+    if (rc == ZKSC_OK) {
+        cudaError_t e = cudaGetLastError();
+        // evaluation = poly_.evaluation(points) (:56); the chain of remainders ends in the same value (the reference panics otherwise, :84-86)
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out_evaluation, poly, sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out_proofs, proofs, (size_t)n_vars * sizeof(g1::Jac), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { ctx->err = std::string("zksc_kzg_open: ") + cudaGetErrorString(e); rc = ZKSC_ERR_CUDA; }
+    }
+    cudaFreeAsync(poly, ctx->stream); cudaFreeAsync(quot, ctx->stream); cudaFreeAsync(srs, ctx->stream); cudaFreeAsync(proofs, ctx->stream);
+    return rc;
 }
 
 // ------------------------------------------------------------------------------------------------
