@@ -191,7 +191,9 @@ class GKRProtocol:               # gkr/src/protocol.rs:17-195
             r_b, r_c = b, c
             alpha, beta = t.evaluate_challenge_into_field(), t.evaluate_challenge_into_field()
             claimed = (alpha * wb + beta * wc) % R
-        return GKRProof(proofs, wb_s, wc_s, w_0)
+        out = GKRProof(proofs, wb_s, wc_s, w_0)
+        out.last_b, out.last_c = r_b, r_c
+        return out
 
     @staticmethod
     def prove_sparse(circuit, circuit_evaluation, layer_prover=_python_layer_prover, evaluate=None):
@@ -225,7 +227,9 @@ class GKRProtocol:               # gkr/src/protocol.rs:17-195
             r_b, r_c = b, c
             alpha, beta = t.evaluate_challenge_into_field(), t.evaluate_challenge_into_field()
             claimed = (alpha * wb + beta * wc) % R
-        return GKRProof(proofs, wb_s, wc_s, w_0)
+        out = GKRProof(proofs, wb_s, wc_s, w_0)
+        out.last_b, out.last_c = r_b, r_c
+        return out
 
     @staticmethod
     def verify(circuit, inp, proof):          # :115-195
@@ -270,3 +274,67 @@ class GKRProtocol:               # gkr/src/protocol.rs:17-195
             claimed = (alpha * wb + beta * wc) % R
         w_in = pm.Multilinear(list(inp))
         return claimed == (alpha * w_in.evaluation(r_b) + beta * w_in.evaluation(r_c)) % R     # :183-192
+
+
+class SuccintGKRProof:           # gkr/src/succint_protocol.rs:21-29
+    def __init__(self, gkr, proof_wb_opening, proof_wc_opening):
+        self.sumcheck_proofs, self.wb_s, self.wc_s, self.w_0_mle = gkr.sumcheck_proofs, gkr.wb_s, gkr.wc_s, gkr.w_0_mle
+        self.proof_wb_opening, self.proof_wc_opening = proof_wb_opening, proof_wc_opening      # (evaluation, [G1 proofs]) or None
+
+
+class SuccintGKRProtocol:        # gkr/src/succint_protocol.rs:35-266
+    @staticmethod
+    def prove(circuit, circuit_evaluation, tau):   # :37-167; tau: oracle.kzgmodel.TrustedSetup
+        """The transcript and the layer sumchecks are GKRProtocol::prove's (the two functions differ only after the last layer's
+        sumcheck); then the input layer, blown up to the trusted setup's size by add_to_back, is committed and opened at
+        (b, 0, ...) and (c, 0, ...)  (:136-157).  A circuit with a single layer never enters the loop: default commitment / proofs."""
+        from oracle import kzgmodel as k
+        base = GKRProtocol.prove_sparse(circuit, circuit_evaluation)
+        if len(circuit_evaluation) < 3:
+            return None, SuccintGKRProof(base, None, None)
+        w = [int(v) % R for v in circuit_evaluation[-1]]
+        exponent = len(tau.powers_of_tau_in_g1).bit_length() - 1                       # gkr/src/utils.rs:100-111
+        blow = exponent - (len(w).bit_length() - 1)
+        poly = [v for v in w for _ in range(1 << blow)]                                # add_to_back, evaluation_form.rs:98-110
+        b = list(base.last_b) + [0] * (exponent - len(base.last_b))
+        c = list(base.last_c) + [0] * (exponent - len(base.last_c))
+        return k.commitment(poly, tau), SuccintGKRProof(base, k.open_(poly, b, tau), k.open_(poly, c, tau))
+
+    @staticmethod
+    def verify(circuit, commitment, proof, tau):   # :169-266, the two pairing checks restated on the group elements (tau is known here)
+        from oracle import kzgmodel as k
+        if len(proof.sumcheck_proofs) != len(proof.wb_s) or len(proof.sumcheck_proofs) != len(proof.wc_s):
+            return False
+        t = pm.FiatShamirTranscript()
+        t.commit(proof.w_0_mle.to_bytes())
+        n_r = t.evaluate_n_challenge_into_field(proof.w_0_mle.n_vars)
+        claimed = proof.w_0_mle.evaluation(n_r)
+        p0 = proof.sumcheck_proofs[0]
+        if claimed != p0.sum:                                                          # generate_layer_one_verify_sumcheck, utils.rs:59-98
+            return False
+        t.commit(p0.to_bytes())
+        sub = pm.MultiComposedSumcheckVerifier.verify_partial(p0)
+        add1, mul1 = circuit.add_mult_mle(0)
+        rbc = list(n_r) + list(sub.challenges)
+        wb, wc = proof.wb_s[0], proof.wc_s[0]
+        if (add1.evaluation(rbc) * ((wb + wc) % R) + mul1.evaluation(rbc) * (wb * wc % R)) % R != sub.sum:
+            return False
+        alpha, beta = t.evaluate_challenge_into_field(), t.evaluate_challenge_into_field()
+        claimed = (alpha * wb + beta * wc) % R
+        r_b, r_c = [], []
+        for i in range(1, len(proof.sumcheck_proofs)):
+            p = proof.sumcheck_proofs[i]
+            if claimed != p.sum:
+                return False
+            t.commit(p.to_bytes())
+            alpha, beta = t.evaluate_challenge_into_field(), t.evaluate_challenge_into_field()
+            ch = pm.MultiComposedSumcheckVerifier.verify_partial(p).challenges
+            r_b, r_c = ch[:len(ch) // 2], ch[len(ch) // 2:]
+            claimed = (alpha * proof.wb_s[i] + beta * proof.wc_s[i]) % R
+        n_tau = len(tau.tau)
+        rb = list(r_b) + [0] * (n_tau - len(r_b))
+        rc = list(r_c) + [0] * (n_tau - len(r_c))
+        ok_b = proof.proof_wb_opening is not None and k.verify_group(commitment, rb, proof.proof_wb_opening, tau)
+        ok_c = proof.proof_wc_opening is not None and k.verify_group(commitment, rc, proof.proof_wc_opening, tau)
+        eb, ec = (proof.proof_wb_opening[0], proof.proof_wc_opening[0]) if (ok_b and ok_c) else (0, 0)
+        return claimed == (alpha * eb + beta * ec) % R

@@ -132,6 +132,17 @@ def verify_in_exponent(ev, points, srs):
     return (f_tau - v) % R == rhs
 
 
+def verify_group(commit, points, opening, srs):
+    """MultilinearKZG::verify (multilinear_kzg.rs:90-116) on the group elements:  e(C - v G1, G2) == sum_i e(proof_i, (tau_i - z_i) G2)
+    holds iff  C - v G1 == sum_i (tau_i - z_i) proof_i  (bilinearity; tau is known to a test's trusted setup)."""
+    v, proofs = opening
+    lhs = add(commit, mul(R - v % R, G1))
+    rhs = None
+    for pr, t, z in zip(proofs, srs.tau, points):
+        rhs = add(rhs, mul((t - z) % R, pr))
+    return len(proofs) == len(srs.tau) and lhs == rhs
+
+
 # ---- ark-ec memory form: Projective { x, y, z } Jacobian, each Fq 6 x u64 little-endian, Montgomery (R = 2^384) ----
 def to_ark(pt):
     import numpy as np

@@ -84,3 +84,35 @@ def test_random_polynomials(ctx):
             assert zk.from_mont(proof.evaluation) == want_v and [k.from_ark(p) for p in proof.proofs] == want_proofs
     with pytest.raises(zk.ZkscError):
         MultilinearKZG.commitment(zk.Multilinear([1, 2, 3, 4]), _srs(k.TrustedSetup([3])))      # lengths must tally (:36-41)
+
+
+# ---- SuccintGKRProtocol::prove (gkr/src/succint_protocol.rs:37-167) on top of zksc_gkr_prove + the KZG entry points ----
+SUCCINT_1 = ([[("Mul", [0, 1])], [("Add", [0, 1]), ("Mul", [2, 3])]], [2, 3, 4, 5], [54, 90])                                   # :281-306
+SUCCINT_2 = ([[("Add", [0, 1])], [("Mul", [0, 1]), ("Add", [2, 3])],                                                            # :309-351
+              [("Add", [0, 1]), ("Mul", [2, 3]), ("Mul", [4, 5]), ("Mul", [6, 7])]], [4, 3, 7, 6, 6, 1, 4, 2], [54, 90, 76])
+
+
+@pytest.mark.parametrize("layers,inp,points", [SUCCINT_1, SUCCINT_2, (SUCCINT_2[0], SUCCINT_2[1], [54, 90, 76, 11])])
+def test_succint_gkr_prove(ctx, layers, inp, points):
+    """the reference's two succinct-GKR tests (and one with a trusted setup larger than the input layer: the add_to_back blow-up):
+    commitment, both openings and every sumcheck byte equal the oracle's, and the oracle's verifier accepts"""
+    from oracle import gkrmodel as g
+    zc = zk.Circuit([zk.CircuitLayer([zk.Gate(zk.GateType.Add if t == "Add" else zk.GateType.Mul, i) for t, i in layer]) for layer in layers])
+    oc = g.Circuit([g.CircuitLayer([g.Gate(t, i) for t, i in layer]) for layer in layers])
+    ev = zc.evaluation(inp)
+    if layers is SUCCINT_2[0]:
+        assert ev[0][0] == 308                                                            # :337
+    model = k.TrustedSetup(points)
+    commitment, proof = zk.SuccintGKRProtocol.prove(zc, ev, _srs(model))
+    want_c, want = g.SuccintGKRProtocol.prove(oc, ev, model)
+    assert k.from_ark(commitment) == want_c
+    assert b"".join(p.to_bytes() for p in proof.sumcheck_proofs) == b"".join(p.to_bytes() for p in want.sumcheck_proofs)
+    assert proof.wb_s == want.wb_s and proof.wc_s == want.wc_s
+    for got, exp in ((proof.proof_wb_opening, want.proof_wb_opening), (proof.proof_wc_opening, want.proof_wc_opening)):
+        assert zk.from_mont(got.evaluation) == exp[0] and [k.from_ark(p) for p in got.proofs] == exp[1]
+    assert g.SuccintGKRProtocol.verify(oc, want_c, want, model)
+    # the product's proof through the oracle's verifier
+    got = g.SuccintGKRProof(want, (zk.from_mont(proof.proof_wb_opening.evaluation), [k.from_ark(p) for p in proof.proof_wb_opening.proofs]),
+                            (zk.from_mont(proof.proof_wc_opening.evaluation), [k.from_ark(p) for p in proof.proof_wc_opening.proofs]))
+    assert g.SuccintGKRProtocol.verify(oc, k.from_ark(commitment), got, model)
+    assert not g.SuccintGKRProtocol.verify(oc, k.add(want_c, k.G1), want, model)          # a wrong commitment is rejected

@@ -60,3 +60,16 @@ def test_open_on_random_polynomials():
         ev = [rng.randrange(R) for _ in range(1 << n)]
         srs = k.TrustedSetup([rng.randrange(R) for _ in range(n)])
         assert k.verify_in_exponent(ev, [rng.randrange(R) for _ in range(n)], srs)
+
+
+def test_succint_gkr_oracle_roundtrip():
+    """gkr/src/succint_protocol.rs:281-351: the reference's two tests assert verify == true; here the oracle's own prover/verifier pair"""
+    from oracle import gkrmodel as g
+    c1 = g.Circuit([g.CircuitLayer([g.Gate("Mul", [0, 1])]), g.CircuitLayer([g.Gate("Add", [0, 1]), g.Gate("Mul", [2, 3])])])
+    ev = c1.evaluation([2, 3, 4, 5])
+    tau = k.TrustedSetup([54, 90])
+    com, proof = g.SuccintGKRProtocol.prove(c1, ev, tau)
+    assert g.SuccintGKRProtocol.verify(c1, com, proof, tau)
+    assert not g.SuccintGKRProtocol.verify(c1, k.add(com, k.G1), proof, tau)
+    bad = g.SuccintGKRProof(proof, (proof.proof_wb_opening[0] + 1, proof.proof_wb_opening[1]), proof.proof_wc_opening)
+    assert not g.SuccintGKRProtocol.verify(c1, com, bad, tau)

@@ -62,6 +62,10 @@ struct ResArgs {
     unsigned int cpg;          // CTAs per (proof, product) group; group g owns CTAs [g cpg, (g + 1) cpg)
     const unsigned long long* mail;   // [proof][kMailUnits]       host-mapped: fold-table word (FoldTabS order) | seq << 32
     unsigned long long* results;      // [proof][n_evals][8]       host-mapped: limb | seq << 32
+    unsigned long long* status;       // [proof]                   host-mapped: seq | kTailTimeout << 32 ("gave up waiting for round seq's challenge;
+                                      //                           nothing of it was folded") or seq | kTailFailed << 32.  Kept apart from the results: a
+                                      //                           round published BEFORE the time-out must stay readable (synchronous launches, e.g. under
+                                      //                           Nsight Compute, let the host look only after the kernel has ended)
     unsigned long long* relay;        // [2][relay_cap][kMailUnits]  HBM: the fold table of round seq of proof b in slot [seq & 1][b], as units
     unsigned long long* relay_tags;   // [2][relay_cap]              HBM: seq | status << 32 once the table of round seq is complete (status 0) or the
                                       //                             proof's first CTA left instead (1 = told to, 2 = timed out); other seqs are stale
@@ -309,9 +313,8 @@ ZKSC_DEV void res_rounds(const ResArgs& args, const volatile ResIds& ids, FoldTa
         if (s_state != 0) {
             // a timeout is the proof's first CTA's decision alone (the other CTAs only ever hear it through the relay): nothing of
             // this round has been folded anywhere when it is published
-            if (s_state == 2 && poller)
-                for (unsigned int u = threadIdx.x; u < args.n_evals * 8; u += kResThreads) st_unit(args.results + (size_t)proof * args.n_evals * 8 + u, 0u, kTailTimeout);
-            if (s_state == 3 && ci == 0 && threadIdx.x < 8 * (D + 1)) st_unit(args.results + (size_t)elem0 * 8 + threadIdx.x, 0u, kTailFailed);
+            if (s_state == 2 && poller && threadIdx.x == 0) st_unit(args.status + proof, seq, kTailTimeout);
+            if (s_state == 3 && ci == 0 && threadIdx.x == 0) st_unit(args.status + proof, seq, kTailFailed);
             return;
         }
         const unsigned int x0 = ci * kResThreads + threadIdx.x, xs = n_active * kResThreads;
@@ -449,7 +452,7 @@ ZKSC_DEV void res_rounds(const ResArgs& args, const volatile ResIds& ids, FoldTa
         // ---- 6. publish
         unsigned long long* res = args.results + (size_t)elem0 * 8;
         if (__syncthreads_or(!ok)) {
-            if (threadIdx.x < 8 * (D + 1)) st_unit(res + threadIdx.x, 0u, kTailFailed);
+            if (threadIdx.x == 0) st_unit(args.status + proof, seq, kTailFailed);
             return;
         }
         if (threadIdx.x < 8 * NP) {

@@ -213,6 +213,7 @@ struct zksc_ctx {
     Fr* tail_partials = nullptr;               // HBM [tail_part_cap] elements
     unsigned int* tail_counters = nullptr;     // HBM [tail_groups_cap]
     size_t tail_proofs_cap = 0, tail_units_cap = 0, tail_groups_cap = 0, tail_part_cap = 0;
+    size_t tail_status_off = 0;                // the per-proof status units sit behind the result units in tail_res
     unsigned int tail_seq = 0;           // last sequence number handed out
     struct zksc_tables* active_tail = nullptr;   // the handle whose tail kernel is resident on `stream` (at most one)
     // ZKSC_PROFILE=1: host-side wall-clock split of every round of zksc_prove, printed to stderr (ns)
@@ -1075,9 +1076,10 @@ static int tail_ensure(zksc_ctx* ctx, size_t proofs, size_t units, size_t groups
     proofs = std::max(proofs, ctx->tail_proofs_cap); units = std::max(units, ctx->tail_units_cap);
     void *m = nullptr, *r = nullptr, *d = nullptr;
     CK(cudaHostAlloc(&m, proofs * kMailUnits * 8, cudaHostAllocMapped));
-    CK(cudaHostAlloc(&r, units * 8, cudaHostAllocMapped));
+    CK(cudaHostAlloc(&r, (units + proofs) * 8, cudaHostAllocMapped));
     memset(m, 0, proofs * kMailUnits * 8);
-    memset(r, 0, units * 8);
+    memset(r, 0, (units + proofs) * 8);
+    ctx->tail_status_off = units;
     ctx->tail_mail = (volatile uint64_t*)m; ctx->tail_res = (volatile uint64_t*)r;
     CK(cudaHostGetDevicePointer(&d, m, 0)); ctx->tail_mail_dev = (unsigned long long*)d;
     CK(cudaHostGetDevicePointer(&d, r, 0)); ctx->tail_res_dev = (unsigned long long*)d;
@@ -1117,7 +1119,7 @@ static int tail_forget(zksc_tables* t, bool disable) {
     if (disable) ctx->tail_enabled = false;
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     if (ctx->tail_mail) memset((void*)ctx->tail_mail, 0, ctx->tail_proofs_cap * kMailUnits * 8);
-    if (ctx->tail_res) memset((void*)ctx->tail_res, 0, ctx->tail_units_cap * 8);
+    if (ctx->tail_res) memset((void*)ctx->tail_res, 0, (ctx->tail_units_cap + ctx->tail_proofs_cap) * 8);
     ctx->tail_seq = 0;
     if (e == cudaSuccess && ctx->tail_relay) e = cudaMemsetAsync(ctx->tail_relay, 0, 2 * ctx->tail_proofs_cap * (kMailUnits + 1) * sizeof(unsigned long long), ctx->stream);
     if (e == cudaSuccess && ctx->tail_counters) e = cudaMemsetAsync(ctx->tail_counters, 0, ctx->tail_groups_cap * sizeof(unsigned int), ctx->stream);
@@ -1140,6 +1142,7 @@ static int tail_wait(zksc_tables* t, unsigned int seq, uint64_t* out) {
     uint32_t timed_out = 0, done = 0;
     for (uint32_t b = 0; b < t->B; b++) {
         bool proof_timed_out = false;
+        volatile uint64_t* status = ctx->tail_res + ctx->tail_status_off + b;
         for (uint32_t p = 0; p < t->P && !proof_timed_out; p++)
             for (uint32_t pt = 0; pt <= t->deg[p] && !proof_timed_out; pt++) {
                 if (pt == 1) continue;
@@ -1151,8 +1154,10 @@ static int tail_wait(zksc_tables* t, unsigned int seq, uint64_t* out) {
                         const uint64_t v = *u;
                         const uint32_t tag = (uint32_t)(v >> 32);
                         if (tag == seq) { limbs[l] = (uint32_t)v; break; }
-                        if (tag == kTailTimeout) { proof_timed_out = true; break; }   // this proof's CTAs gave up waiting and left; nothing of it was folded
-                        if (tag == kTailFailed) {
+                        // the kernel's notices about THIS round live in the proof's status unit (sequence number | code << 32)
+                        const uint64_t st = *status;
+                        if ((uint32_t)st == seq && (uint32_t)(st >> 32) == kTailTimeout) { proof_timed_out = true; break; }   // gave up waiting; nothing of this round was folded
+                        if ((uint32_t)st == seq && (uint32_t)(st >> 32) == kTailFailed) {
                             tail_forget(t, true);
                             FAIL(ZKSC_ERR_COMM, "resident rounds kernel: a CTA or a peer GPU went missing mid-round; the tables are undefined (reset them)");
                         }
@@ -1167,7 +1172,7 @@ static int tail_wait(zksc_tables* t, unsigned int seq, uint64_t* out) {
                                 ctx->err = msg;
                                 return ZKSC_ERR_CUDA;
                             }
-                            if (q == cudaSuccess && (uint32_t)(*u >> 32) != seq && (uint32_t)(*u >> 32) != kTailTimeout) {
+                            if (q == cudaSuccess && (uint32_t)(*u >> 32) != seq && (uint32_t)*status != seq) {
                                 tail_forget(t, true);
                                 FAIL(ZKSC_ERR_CUDA, "resident kernel ended without publishing its results");
                             }
@@ -1298,7 +1303,7 @@ static int tail_start(zksc_tables* t, unsigned long long half, bool sharded) {
         CK(cudaStreamSynchronize(ctx->stream));
         ctx->tail_seq = 0;
         memset((void*)ctx->tail_mail, 0, ctx->tail_proofs_cap * kMailUnits * 8);
-        memset((void*)ctx->tail_res, 0, ctx->tail_units_cap * 8);
+        memset((void*)ctx->tail_res, 0, (ctx->tail_units_cap + ctx->tail_proofs_cap) * 8);
         CK(cudaMemsetAsync(ctx->tail_relay, 0, 2 * ctx->tail_proofs_cap * (kMailUnits + 1) * sizeof(unsigned long long), ctx->stream));
         if (ctx->xch_local) CK(cudaMemsetAsync(ctx->xch_local + kXchUnitsOffset(ctx->n_ranks), 0, kXchUnitsBytes(ctx->n_ranks), ctx->stream));
     }
@@ -1315,7 +1320,7 @@ static int tail_start(zksc_tables* t, unsigned long long half, bool sharded) {
     a.n_proofs = t->B; a.n_products = t->P; a.n_evals = t->E; a.n_tables = t->Dtot;
     for (uint32_t p = 0; p < t->P; p++) { a.deg[p] = t->deg[p]; a.koff[p] = t->koff[p]; a.eoff[p] = t->eoff[p]; }
     a.cpg = cpg;
-    a.mail = ctx->tail_mail_dev; a.results = ctx->tail_res_dev;
+    a.mail = ctx->tail_mail_dev; a.results = ctx->tail_res_dev; a.status = ctx->tail_res_dev + ctx->tail_status_off;
     a.relay = ctx->tail_relay; a.relay_tags = ctx->tail_relay + 2 * ctx->tail_proofs_cap * kMailUnits;
     a.partials = ctx->tail_partials; a.counters = ctx->tail_counters;
     a.n_ranks = 1; a.rank = 0; a.xch_cap = kXchCap;

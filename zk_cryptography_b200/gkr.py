@@ -293,3 +293,35 @@ class GKRProtocol:               # gkr/src/protocol.rs:17-195
             claimed = (alpha * wb + beta * wc) % R
         w_in = Multilinear([int(v) % R for v in inp])
         return claimed == (alpha * w_in.evaluation(r_b) + beta * w_in.evaluation(r_c)) % R     # :183-192
+
+
+class SuccintGKRProof:           # gkr/src/succint_protocol.rs:21-29
+    def __init__(self, gkr, proof_wb_opening, proof_wc_opening):
+        self.sumcheck_proofs, self.wb_s, self.wc_s, self.w_0_mle = gkr.sumcheck_proofs, gkr.wb_s, gkr.wc_s, gkr.w_0_mle
+        self.proof_wb_opening, self.proof_wc_opening = proof_wb_opening, proof_wc_opening
+
+
+class SuccintGKRProtocol:        # gkr/src/succint_protocol.rs:35-167
+    @staticmethod
+    def prove(circuit, circuit_evaluation, tau, ctx=None):
+        """SuccintGKRProtocol::prove: GKRProtocol::prove's transcript and layer sumchecks (one C call, zksc_gkr_prove), then the input
+        layer -- blown up to the trusted setup's size (add_to_back, evaluation_form.rs:98-110) -- committed and opened at (b, 0, ..)
+        and (c, 0, ..) on the device (zksc_g1_msm, zksc_kzg_open; :136-157).  -> (commitment (18,) uint64 or None, SuccintGKRProof).
+        `verify` (:169-266) needs two pairing checks (MultilinearKZG::verify): the caller's, with ark-ec."""
+        from .kzg import MultilinearKZG
+        ctx = ctx or default_context()
+        base = GKRProtocol.prove(circuit, circuit_evaluation, ctx)
+        if len(circuit_evaluation) < 3:       # the loop of :81 never runs: default commitment and openings
+            return None, SuccintGKRProof(base, None, None)
+        L = len(circuit.layers)
+        ch = base.challenges[-2 * L:]         # the last layer's sumcheck has 2 L rounds: (b, c)
+        w = [int(v) % R for v in circuit_evaluation[-1]]
+        exponent = tau.powers_of_tau_in_g1.shape[0].bit_length() - 1
+        blow = exponent - (len(w).bit_length() - 1)
+        if blow < 0:
+            raise ZkscError(-3, "the trusted setup is smaller than the input layer")
+        poly = Multilinear(np.repeat(to_mont(w).reshape(-1, 4), 1 << blow, axis=0))
+        b = list(ch[:L]) + [0] * (exponent - L)
+        c = list(ch[L:]) + [0] * (exponent - L)
+        commitment = MultilinearKZG.commitment(poly, tau, ctx)
+        return commitment, SuccintGKRProof(base, MultilinearKZG.open(poly, b, tau, ctx), MultilinearKZG.open(poly, c, tau, ctx))
