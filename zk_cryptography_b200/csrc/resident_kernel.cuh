@@ -200,7 +200,10 @@ __device__ unsigned long long g_res_trace[kTraceRounds * kTracePhases];
 // fold + evaluate one pair of every factor; the folded entries go to o[k] + x and o[k] + x + half
 template <int D, class LOAD, class A, int NP>
 ZKSC_DEV void res_pair(A (&acc)[NP], LOAD&& load, Fr* out, unsigned int out_stride, unsigned int x, unsigned int half, const FoldTabS& tab) {
-    constexpr bool kSemi = (D == 2);     // see fr_fold_tab
+#ifndef ZKSC_RES_SEMI3
+#define ZKSC_RES_SEMI3 0
+#endif
+    constexpr bool kSemi = (D == 2) || (ZKSC_RES_SEMI3 && D == 3);     // see fr_fold_tab
     Fr a[D], b[D];
     if constexpr (D == 2) {
         // all eight entries of the pair in flight at once: one exposed memory latency per iteration instead of two
@@ -471,8 +474,11 @@ ZKSC_DEV void res_rounds(const ResArgs& args, const volatile ResIds& ids, FoldTa
 }
 
 // DSEL > 0: every product has degree DSEL (registers are allocated for that degree alone); DSEL == 0: mixed degrees.
+// Degrees 1 and 2 fit 128 registers (4 CTAs per SM); degree 3 spills there (208 bytes of stack, ~45 local loads and stores per pair)
+// and runs 3 % faster on large rounds and 4.5 us faster on small ones with 168 registers and 3 CTAs per SM
+// (profiles/r02_resident_d3_variants.txt); degrees 4, 5 and the mixed form likewise.
 template <int DSEL>
-__global__ void __launch_bounds__(kResThreads, (DSEL == 0 || DSEL >= 4) ? 3 : ZKSC_RES_MINB) resident_kernel(const __grid_constant__ ResArgs args) {
+__global__ void __launch_bounds__(kResThreads, (DSEL == 0 || DSEL >= 3) ? 3 : ZKSC_RES_MINB) resident_kernel(const __grid_constant__ ResArgs args) {
     __shared__ __align__(16) FoldTabS s_tab;
     __shared__ int s_state, s_last;
     __shared__ ResIds s_ids;

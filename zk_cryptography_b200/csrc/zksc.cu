@@ -51,7 +51,11 @@ constexpr size_t kXchTagBytes = 256;               // 2 * kMaxRanks tags, padded
 constexpr unsigned int kXchCap = 2048;             // elements per (slot, rank): rounds with more partials use NCCL
 constexpr size_t kXchStageElems = 1u << 15;        // gather stage of a rank: its folded shard of every table, read by the peers (1 MiB)
 constexpr unsigned long long kGatherDefault = 2048;   // sharded contexts: gather the shards when a table is down to this many entries in total
-constexpr unsigned long long kTailWorkDefault = 1000ull * 1000 * 1000;   // resident kernel from the round with at most this many limb products per rank
+// The resident kernel takes over from the round with at most this many limb products per rank (ZKSC_TAIL_WORK overrides).  One GPU:
+// degree 2 from 2^20 pairs, degree 3 from 2^19 (above that the ordinary launch's constant-bank fold table is worth more than its
+// ~20 us of fixed cost); sharded contexts one round earlier: there an ordinary round also pays the cross-rank exchange in its last block.
+constexpr unsigned long long kTailWorkDefault = 600ull * 1000 * 1000;
+constexpr unsigned long long kTailWorkSharded = 1100ull * 1000 * 1000;
 // exchange buffer of a rank: tags[2][G] | data[2][G][kXchCap] elements (round kernels) | units[2][G][kXchCap][8] (resident kernel) |
 // stage[kXchStageElems] elements (resident kernel, gather)
 static inline size_t kXchUnitsOffset(int G) { return kXchTagBytes + (size_t)2 * G * kXchCap * 32; }
@@ -674,6 +678,7 @@ extern "C" int zksc_comm_init(zksc_ctx* ctx, int n_ranks, int rank, const uint8_
     if (r != ncclSuccess) FAIL(ZKSC_ERR_COMM, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r));
     ctx->rank = rank;
     ctx->n_ranks = n_ranks;
+    if (!getenv("ZKSC_TAIL_WORK")) ctx->tail_work = kTailWorkSharded;
     {
         unsigned long long g = kGatherDefault;
         const char* e_ = getenv("ZKSC_GATHER_ENTRIES");
@@ -1773,6 +1778,7 @@ extern "C" int zksc_ctx_create_multi(const int* devices, int n_devices, zksc_ctx
             return fail(rc, g_create_error);
         }
         k->parent = ctx; k->rank = g; k->n_ranks = G; k->host_reduce = true;
+        if (!getenv("ZKSC_TAIL_WORK")) k->tail_work = kTailWorkSharded;
         ctx->kids.push_back(k);
     }
     ctx->device = devices[0];
