@@ -639,7 +639,10 @@ def run_gkr(args, wl, world, rank, local_rank, dist):
         "e2e": {"value": evals_per_step * args.steps / (wall_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": round(wall_ms / args.steps, 4), "api": "GKRProtocol.prove(circuit, circuit_evaluation): host layer values in, proof out (host wall clock)"},
         "roofline": None, "int_roofline": None, "cpu_baseline": cpu,
-        "note": "latency-bound: 110 sumcheck rounds + 10 layer set-ups per proof, Python layer driver; no single dominant kernel, hence no roofline object",
+        "latency": {"sumcheck_rounds": int(sum(2 * (i + 1) for i in range(depth))), "layers": depth,
+                    "us_per_round_incl_layer_setup": round(ms / args.steps * 1e3 / sum(2 * (i + 1) for i in range(depth)), 2)},
+        "note": "latency-bound: 110 sumcheck rounds (one host round trip each: the transcript stays on the host) + 10 layer set-ups per proof; "
+                "no single dominant kernel, hence a latency object instead of a roofline object",
     }
     print(json.dumps(out))
     sys.stdout.flush()

@@ -54,8 +54,8 @@ int zksc_ctx_create(int device, zksc_ctx** out);
  * zksc_ctx_gather_entries() entries every device pulls the other shards over NVLink and the rest runs replicated.
  * zksc_tables_upload sends every table across PCIe once (staged on the first device, each device picks its shard over NVLink).
  * Supported on such a context: zksc_tables_upload / _synth / _reset / _free / _vars_left, zksc_poly_sum, zksc_round_evals, zksc_bind,
- * zksc_residual (once the shards are exhausted), zksc_prove (all protocols but MULTI_FULL), zksc_evaluate, the stand-alone zksc_ml_*
- * operations (first device); everything else returns ZKSC_ERR_UNSUPPORTED.  n_devices == 1 gives an ordinary context. */
+ * zksc_residual (once the shards are exhausted), zksc_tables_to_bytes, zksc_prove (all four protocols), zksc_evaluate, the stand-alone
+ * zksc_ml_* operations and the KZG entry points (first device); everything else returns ZKSC_ERR_UNSUPPORTED.  n_devices == 1 gives an ordinary context. */
 int zksc_ctx_create_multi(const int* devices, int n_devices, zksc_ctx** out);
 /* Number of devices behind a context (1 unless it came from zksc_ctx_create_multi). */
 int zksc_ctx_devices(const zksc_ctx* ctx);

@@ -73,7 +73,8 @@ inline const uint64_t* raw(const std::vector<Fr>& x) { return reinterpret_cast<c
 inline uint64_t* raw(std::vector<Fr>& x) { return reinterpret_cast<uint64_t*>(x.data()); }
 inline void append(std::vector<uint8_t>& out, const Fr& x) { auto b = x.to_bytes_be(); out.insert(out.end(), b.begin(), b.end()); }
 
-// one process-wide context on the current device (ZKSC_DEVICE selects another one)
+// one process-wide context: on device 0, or the device ZKSC_DEVICE names, or -- ZKSC_DEVICES="0,1,2,3" -- ONE context over several devices
+// of this process (zksc_ctx_create_multi: tables sharded over them, one host thread, one transcript; the reference's caller is one process)
 class Context {
    public:
     static zksc_ctx* get() {
@@ -88,8 +89,19 @@ class Context {
 
    private:
     Context() {
-        const char* d = std::getenv("ZKSC_DEVICE");
-        int rc = zksc_ctx_create(d ? std::atoi(d) : 0, &h_);
+        int rc;
+        if (const char* many = std::getenv("ZKSC_DEVICES")) {
+            std::vector<int> devs;
+            for (const char* p = many; *p;) {
+                devs.push_back(std::atoi(p));
+                while (*p && *p != ',') p++;
+                if (*p == ',') p++;
+            }
+            rc = zksc_ctx_create_multi(devs.data(), (int)devs.size(), &h_);
+        } else {
+            const char* d = std::getenv("ZKSC_DEVICE");
+            rc = zksc_ctx_create(d ? std::atoi(d) : 0, &h_);
+        }
         if (rc != ZKSC_OK) throw Error(rc, std::string("zksc_ctx_create: ") + zksc_last_error(nullptr) + " (there is no CPU fallback)");
     }
     ~Context() { zksc_ctx_destroy(h_); }

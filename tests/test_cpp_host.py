@@ -92,3 +92,22 @@ def test_reference_cases_through_the_cpp_mirror(built):
     assert set(got) == set(want)
     for k in want:
         assert got[k] == want[k], k
+
+
+@pytest.mark.gpu
+def test_reference_cases_on_a_single_process_multi_gpu_context(built):
+    """the same program over ONE context spanning two GPUs (ZKSC_DEVICES -> zksc_ctx_create_multi): every sumcheck case of the
+    reference -- tables of 4 to 32 entries sharded over two devices, `prove` with its full-table absorb included -- must emit the
+    oracle's bytes; the GKR cases need a single-device context and are left out by the program"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    r = subprocess.run([EXE], capture_output=True, text=True, timeout=600, env=dict(os.environ, ZKSC_DEVICES="0,1"))
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l.split(" ", 1) for l in r.stdout.strip().splitlines()]
+    assert lines[-1] == ["ALL", "REFERENCE CASES OK"]
+    got = {k: bytes.fromhex(v) for k, v in lines[:-1]}
+    want = {k: v for k, v in oracle_lines().items() if not k.startswith("gkr_")}
+    assert set(got) == set(want)
+    for k in want:
+        assert got[k] == want[k], k

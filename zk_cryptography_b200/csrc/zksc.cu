@@ -2084,10 +2084,38 @@ extern "C" int zksc_poly_sum(zksc_tables* t, uint64_t* out) {
     return ZKSC_OK;
 }
 
+// multi-GPU handle: every device converts its shard, the host interleaves the 32-byte elements (entry i sits on device i mod G at i / G)
+static int multi_tables_to_bytes(zksc_tables* t, uint32_t proof, uint8_t* out) {
+    zksc_ctx* ctx = t->ctx;
+    if (proof >= t->B) FAIL(ZKSC_ERR_SHAPE, "proof index");
+    const uint32_t G = (uint32_t)t->kids.size();
+    const uint64_t NL = t->kids[0]->n_local0;
+    std::vector<uint8_t> shard((size_t)NL * 32);
+    for (uint32_t g = 0; g < G; g++) {
+        zksc_tables* k = t->kids[g];
+        zksc_ctx* kc = k->ctx;
+        CK(cudaSetDevice(kc->device));
+        { const int rc = quiesce(kc); if (rc != ZKSC_OK) { ctx->err = kc->err; return rc; } }
+        Fr* tmp = nullptr;
+        CK(cudaMallocAsync((void**)&tmp, NL * sizeof(Fr), kc->stream));
+        for (uint32_t tab = 0; tab < t->Dtot; tab++) {
+            to_bytes_kernel<<<grid_for(kc, NL, 256, 8), 256, 0, kc->stream>>>(k->orig + ((size_t)proof * t->Dtot + tab) * NL, tmp, NL);
+            kc->launches++;
+            cudaError_t e = cudaMemcpyAsync(shard.data(), tmp, NL * sizeof(Fr), cudaMemcpyDeviceToHost, kc->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(kc->stream);
+            if (e != cudaSuccess) { cudaFreeAsync(tmp, kc->stream); FAIL(ZKSC_ERR_CUDA, std::string("to_bytes: ") + cudaGetErrorString(e)); }
+            uint8_t* dst = out + (size_t)tab * NL * G * 32;
+            for (uint64_t i = 0; i < NL; i++) memcpy(dst + (i * G + g) * 32, shard.data() + i * 32, 32);
+        }
+        cudaFreeAsync(tmp, kc->stream);
+    }
+    return ZKSC_OK;
+}
+
 extern "C" int zksc_tables_to_bytes(zksc_tables* t, uint32_t proof, uint8_t* out) {
     if (!t || !out) return ZKSC_ERR_STATE;
     zksc_ctx* ctx = t->ctx;
-    NOT_MULTI(ctx, "zksc_tables_to_bytes");
+    if (!t->kids.empty()) return multi_tables_to_bytes(t, proof, out);
     CK(cudaSetDevice(ctx->device));
     TRY(quiesce(ctx));
     if (ctx->n_ranks != 1) FAIL(ZKSC_ERR_UNSUPPORTED, "zksc_tables_to_bytes: single-rank contexts only");
