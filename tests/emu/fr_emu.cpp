@@ -69,3 +69,13 @@ BIN(emu_fr_mul_lazy, fr_mul_lazy)
 extern "C" {
 BIN(emu_fr_sub_lazy, fr_sub_lazy)
 }
+
+// one level of Karatsuba (mul_wide_k) and the product-first Montgomery multiplication built on it (mont_mul_rows_k)
+extern "C" void emu_mul_wide_k(const uint32_t* a, const uint32_t* b, uint32_t* out16) {
+    Fr x, y; memcpy(x.l, a, 32); memcpy(y.l, b, 32);
+    uint32_t T[16]; mul_wide_k(T, x, y); memcpy(out16, T, 64);
+}
+extern "C" void emu_mont_mul_rows_k(const uint32_t* a, const uint32_t* b, uint32_t* out9) {
+    Fr x, y; memcpy(x.l, a, 32); memcpy(y.l, b, 32);
+    uint32_t res[8], top; mont_mul_rows_k(res, top, x, y); memcpy(out9, res, 32); out9[8] = top;
+}

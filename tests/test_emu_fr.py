@@ -184,3 +184,21 @@ def test_lazy_difference(emu):
     for a, b in [(rnd(rng, R), rnd(rng, R)) for _ in range(500)] + [(0, R - 1), (R - 1, 0), (0, 0), (R - 1, R - 1), (1, 2)]:
         emu.emu_fr_sub_lazy(arr(a, 8), arr(b, 8), o8)
         assert val(o8) == a - b + R
+
+
+def test_karatsuba_product_and_product_first_montgomery(emu):
+    """mul_wide_k (one level of Karatsuba: three 4 x 4 limb products, the half sums' carry bits, two subtractions) is the full
+    512-bit product for ANY 256-bit operands, and mont_mul_rows_k (that product first, the eight Montgomery digit rows afterwards)
+    returns exactly what mont_mul_rows returns -- same digits, same limbs"""
+    rng = random.Random(77)
+    o9, p9, o16 = (ctypes.c_uint32 * 9)(), (ctypes.c_uint32 * 9)(), (ctypes.c_uint32 * 16)()
+    halves = [0, 1, 2**128 - 1, 2**127, 2**64, 2**128 - 2**32, (1 << 96) - 1]
+    cases = [(lo + (hi << 128), lo2 + (hi2 << 128)) for lo in halves for hi in halves[:4] for lo2 in halves[:4] for hi2 in halves]   # carries out of both half sums
+    cases += [(rnd(rng, 2**256), rnd(rng, 2**256)) for _ in range(6000)]
+    for a, b in cases:
+        emu.emu_mul_wide_k(arr(a, 8), arr(b, 8), o16)
+        assert val(o16) == a * b, (hex(a), hex(b))
+        emu.emu_mont_mul_rows_k(arr(a, 8), arr(b, 8), o9)
+        emu.emu_mont_mul_rows(arr(a, 8), arr(b, 8), p9)
+        assert list(o9) == list(p9)
+        assert val(o9) % R == a * b * RINV % R

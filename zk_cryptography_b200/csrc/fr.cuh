@@ -321,6 +321,76 @@ ZKSC_DEV void mul_wide(uint32_t (&T)[16], const Fr& a, const Fr& b) {
     T[15] = ptx::addc(E[15], O[15]);
 }
 
+// ---- one level of Karatsuba on the 8 x 8 limb product --------------------------------------------------------------------
+// a = a0 + a1 2^128, b = b0 + b1 2^128:  a b = z0 + (zm - z0 - z2) 2^128 + z2 2^256  with z0 = a0 b0, z2 = a1 b1, zm = (a0 + a1)(b0 + b1):
+// three 4 x 4 limb products = 48 IMAD.WIDE instead of 64, paid for with ~70 more ALU instructions (the half sums, their carry bits,
+// the two subtractions, the recombination).  Worth it only where the multiplier pipe is the limit and the ALU pipe has room (the
+// degree-3 kernels: multiplier pipe 75-80 % busy, ALU pipe 27-32 %; profiles/r02_ncu_c3_round0_and_fold.txt): ZKSC_KARATSUBA.
+// two fused lo/hi pairs on X[pos..pos+3], carry into X[pos+4]
+ZKSC_DEV void chain2(uint32_t* X, int pos, uint32_t v0, uint32_t v2, uint32_t x) {
+    using namespace ptx;
+    X[pos + 0] = mad_lo_cc(x, v0, X[pos + 0]);  X[pos + 1] = madc_hi_cc(x, v0, X[pos + 1]);
+    X[pos + 2] = madc_lo_cc(x, v2, X[pos + 2]); X[pos + 3] = madc_hi_cc(x, v2, X[pos + 3]);
+    X[pos + 4] = addc(X[pos + 4], 0u);
+}
+// 256-bit product of two 128-bit operands (even / odd IMAD.WIDE chains like mul_wide)
+ZKSC_DEV void mul4x4(uint32_t (&T)[8], const uint32_t (&a)[4], const uint32_t (&b)[4]) {
+    uint32_t E[9], O[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) { E[i] = 0; O[i] = 0; }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        uint32_t* A = (i & 1) ? O : E;
+        uint32_t* B = (i & 1) ? E : O;
+        chain2(A, i, a[0], a[2], b[i]);
+        chain2(B, i + 1, a[1], a[3], b[i]);
+    }
+    T[0] = E[0];
+    T[1] = ptx::add_cc(E[1], O[1]);
+#pragma unroll
+    for (int i = 2; i < 7; i++) T[i] = ptx::addc_cc(E[i], O[i]);
+    T[7] = ptx::addc(E[7], O[7]);
+}
+// 512-bit product a*b, any a, b < 2^256 (same contract as mul_wide)
+ZKSC_DEV void mul_wide_k(uint32_t (&T)[16], const Fr& a, const Fr& b) {
+    using namespace ptx;
+    uint32_t a0[4], a1[4], b0[4], b1[4], sa[4], sb[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) { a0[i] = a.l[i]; a1[i] = a.l[4 + i]; b0[i] = b.l[i]; b1[i] = b.l[4 + i]; }
+    sa[0] = add_cc(a0[0], a1[0]); sa[1] = addc_cc(a0[1], a1[1]); sa[2] = addc_cc(a0[2], a1[2]); sa[3] = addc_cc(a0[3], a1[3]);
+    const uint32_t ca = addc(0u, 0u);                   // a0 + a1 = sa + ca 2^128
+    sb[0] = add_cc(b0[0], b1[0]); sb[1] = addc_cc(b0[1], b1[1]); sb[2] = addc_cc(b0[2], b1[2]); sb[3] = addc_cc(b0[3], b1[3]);
+    const uint32_t cb = addc(0u, 0u);
+    uint32_t z0[8], z2[8], zm[8];
+    mul4x4(z0, a0, b0);
+    mul4x4(z2, a1, b1);
+    mul4x4(zm, sa, sb);
+    // middle = zm + (ca sb + cb sa) 2^128 + ca cb 2^256   (< 2^258: ten limbs m[0..9], m[8], m[9] small)
+    const uint32_t ma = 0u - ca, mb = 0u - cb;          // all-ones masks
+    uint32_t m[10];
+#pragma unroll
+    for (int i = 0; i < 4; i++) m[i] = zm[i];
+    m[4] = add_cc(zm[4], sb[0] & ma); m[5] = addc_cc(zm[5], sb[1] & ma); m[6] = addc_cc(zm[6], sb[2] & ma); m[7] = addc_cc(zm[7], sb[3] & ma);
+    m[8] = addc(ca & cb, 0u);
+    m[4] = add_cc(m[4], sa[0] & mb); m[5] = addc_cc(m[5], sa[1] & mb); m[6] = addc_cc(m[6], sa[2] & mb); m[7] = addc_cc(m[7], sa[3] & mb);
+    m[8] = addc(m[8], 0u);
+    // z1 = middle - z0 - z2  (>= 0, < 2^257: nine limbs)
+    m[0] = sub_cc(m[0], z0[0]);
+#pragma unroll
+    for (int i = 1; i < 8; i++) m[i] = subc_cc(m[i], z0[i]);
+    m[8] = subc(m[8], 0u);
+    m[0] = sub_cc(m[0], z2[0]);
+#pragma unroll
+    for (int i = 1; i < 8; i++) m[i] = subc_cc(m[i], z2[i]);
+    m[8] = subc(m[8], 0u);
+    // T = z0 + z1 2^128 + z2 2^256
+#pragma unroll
+    for (int i = 0; i < 4; i++) T[i] = z0[i];
+    T[4] = add_cc(z0[4], m[0]); T[5] = addc_cc(z0[5], m[1]); T[6] = addc_cc(z0[6], m[2]); T[7] = addc_cc(z0[7], m[3]);
+    T[8] = addc_cc(z2[0], m[4]); T[9] = addc_cc(z2[1], m[5]); T[10] = addc_cc(z2[2], m[6]); T[11] = addc_cc(z2[3], m[7]);
+    T[12] = addc_cc(z2[4], m[8]); T[13] = addc_cc(z2[5], 0u); T[14] = addc_cc(z2[6], 0u); T[15] = addc(z2[7], 0u);
+}
+
 // Limb k of C* = sum_{i=0..7} (p - 1 + 2^32) * 2^(32 i): what the "+1" parts of the complement digits add
 // (see mont_mul_rows).  Evaluated at compile time.
 ZKSC_DEV constexpr uint32_t cstar_limb(int k) {
@@ -398,6 +468,48 @@ ZKSC_DEV void mont_mul_rows(uint32_t (&res)[8], uint32_t& top, const Fr& a, cons
     top = addc(E[16], O[16]);
 }
 
+// The same Montgomery product with the multiplication done first (mul_wide_k) and the eight digit rows afterwards: row i of
+// mont_mul_rows reads limb i of the running total, and the product rows j > i only touch limbs >= j, so the digits -- and the
+// result -- are the ones mont_mul_rows finds.  48 + 56 IMAD.WIDE instead of 64 + 56.
+ZKSC_DEV void mont_mul_rows_k(uint32_t (&res)[8], uint32_t& top, const Fr& a, const Fr& b) {
+    using namespace ptx;
+    uint32_t T[16];
+    mul_wide_k(T, a, b);
+    uint32_t E[18], O[18];
+#pragma unroll
+    for (int i = 0; i < 18; i++) O[i] = 0;
+    E[0] = add_cc(T[0], CStar<0>::v); E[1] = addc_cc(T[1], CStar<1>::v); E[2] = addc_cc(T[2], CStar<2>::v); E[3] = addc_cc(T[3], CStar<3>::v);
+    E[4] = addc_cc(T[4], CStar<4>::v); E[5] = addc_cc(T[5], CStar<5>::v); E[6] = addc_cc(T[6], CStar<6>::v); E[7] = addc_cc(T[7], CStar<7>::v);
+    E[8] = addc_cc(T[8], CStar<8>::v); E[9] = addc_cc(T[9], CStar<9>::v); E[10] = addc_cc(T[10], CStar<10>::v); E[11] = addc_cc(T[11], CStar<11>::v);
+    E[12] = addc_cc(T[12], CStar<12>::v); E[13] = addc_cc(T[13], CStar<13>::v); E[14] = addc_cc(T[14], CStar<14>::v); E[15] = addc_cc(T[15], CStar<15>::v);
+    E[16] = addc(0u, CStar<16>::v); E[17] = 0u;
+    const uint32_t p1 = ZKSC_P1, p2 = ZKSC_P2, p3 = ZKSC_P3, p4 = ZKSC_P4, p5 = ZKSC_P5, p6 = ZKSC_P6, p7 = ZKSC_P7;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint32_t* A = (i & 1) ? O : E;
+        uint32_t* B = (i & 1) ? E : O;
+        uint32_t m;
+        if (i == 0) {
+            m = ~E[0];
+            A[0] = add_cc(A[0], m);
+        } else {
+            (void)add_cc(E[i - 1], O[i - 1]);          // limb i-1 is 2^32 - 1 (+ 2^32 k): CF = k
+            m = ~addc(E[i], O[i]);
+            A[i] = addc_cc(A[i], m);                   // k enters here
+        }
+        A[i + 1] = addc_cc(A[i + 1], 0u);
+        A[i + 2] = madc_lo_cc(m, p2, A[i + 2]); A[i + 3] = madc_hi_cc(m, p2, A[i + 3]);
+        A[i + 4] = madc_lo_cc(m, p4, A[i + 4]); A[i + 5] = madc_hi_cc(m, p4, A[i + 5]);
+        A[i + 6] = madc_lo_cc(m, p6, A[i + 6]); A[i + 7] = madc_hi_cc(m, p6, A[i + 7]);
+        A[i + 8] = addc(A[i + 8], 0u);
+        chain4<false>(B, i + 1, p1, p3, p5, p7, m);
+    }
+    (void)add_cc(O[7], E[7]);                          // k_7
+#pragma unroll
+    for (int i = 0; i < 8; i++) res[i] = addc_cc(E[8 + i], O[8 + i]);
+    top = addc(E[16], O[16]);
+}
+
 // Montgomery product, canonical result.  a, b < r.
 ZKSC_DEV Fr fr_mul(const Fr& a, const Fr& b) {
     Fr o;
@@ -418,6 +530,23 @@ ZKSC_DEV Fr fr_mul_lazy(const Fr& a, const Fr& b) {
     Fr o;
     uint32_t top;
     mont_mul_rows(o.l, top, a, b);   // < 2r < 2^256: top == 0
+    (void)top;
+    return o;
+}
+
+// the product-first (Karatsuba) forms of fr_mul / fr_mul_lazy
+ZKSC_DEV Fr fr_mul_k(const Fr& a, const Fr& b) {
+    Fr o;
+    uint32_t top;
+    mont_mul_rows_k(o.l, top, a, b);
+    (void)top;
+    cond_sub_r(o.l);
+    return o;
+}
+ZKSC_DEV Fr fr_mul_lazy_k(const Fr& a, const Fr& b) {
+    Fr o;
+    uint32_t top;
+    mont_mul_rows_k(o.l, top, a, b);
     (void)top;
     return o;
 }

@@ -71,6 +71,12 @@ struct RoundArgsT : RoundBase {
     FoldTab tab[NB];           // FOLD: its shift table (fr.cuh mul_fixed_rows), per proof; read straight from the constant bank
 };
 
+#ifndef ZKSC_KARA_D2
+#define ZKSC_KARA_D2 0
+#endif
+#ifndef ZKSC_KARA_D3
+#define ZKSC_KARA_D3 0
+#endif
 template <int D>
 struct Lazy {
     static constexpr bool wide = (D <= 3);
@@ -116,11 +122,17 @@ ZKSC_DEV void accumulate_product(A& acc, const Fr (&f)[D]) {
     if constexpr (D == 1) {
         acc_add<9, 8>(acc, f[0].l);
     } else if constexpr (Lazy<D>::wide) {
+        // ZKSC_KARA_D2 / ZKSC_KARA_D3: one level of Karatsuba in the 8 x 8 limb products of this degree (fr.cuh mul_wide_k)
+        constexpr bool kKara = (D == 2 && ZKSC_KARA_D2) || (D == 3 && ZKSC_KARA_D3);
         Fr g = f[0];
 #pragma unroll
-        for (int k = 1; k < D - 1; k++) g = (k == D - 2) ? fr_mul_lazy(g, f[k]) : fr_mul(g, f[k]);   // the one that feeds mul_wide may stay < 2r
+        for (int k = 1; k < D - 1; k++) {
+            if constexpr (kKara) g = (k == D - 2) ? fr_mul_lazy_k(g, f[k]) : fr_mul_k(g, f[k]);
+            else g = (k == D - 2) ? fr_mul_lazy(g, f[k]) : fr_mul(g, f[k]);   // the one that feeds mul_wide may stay < 2r
+        }
         uint32_t T[16];
-        mul_wide(T, g, f[D - 1]);      // last multiplication stays unreduced
+        if constexpr (kKara) mul_wide_k(T, g, f[D - 1]);
+        else mul_wide(T, g, f[D - 1]);      // last multiplication stays unreduced
         acc_add<17, 16>(acc, T);
     } else {
         Fr g = f[0];
