@@ -80,6 +80,14 @@ def test_single_process_multi_gpu_context(built, env):
                     c.free()
                 a.free()
                 b.free()
+            # a batch of independent proofs on the multi-GPU context
+            for n, degs, B in ((11, [2], 3), (15, [3], 2)):
+                a, b = zk.Tables.synth(solo, n, degs, 60 + n, n_proofs=B), zk.Tables.synth(multi, n, degs, 60 + n, n_proofs=B)
+                ra, rb = _prove(zk, solo, a, zk.PROTO_MULTI_PARTIAL), _prove(zk, multi, b, zk.PROTO_MULTI_PARTIAL)
+                for x, y in zip(ra, rb):
+                    assert np.array_equal(x, y), "G=%d n=%d batch of %d: multi-GPU context differs from one GPU" % (G, n, B)
+                a.free()
+                b.free()
             # and one case straight against the oracle
             n, degs = 16, [3]
             t = zk.Tables.synth(multi, n, degs, 77)

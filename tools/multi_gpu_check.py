@@ -84,6 +84,23 @@ def main():
             print("case n=%d degs=%s G=%d [%s]: %s (%d proof bytes, sha256 %s)" % (n, degs, world, check, "ok" if good else "MISMATCH", len(got),
                                                                                  hashlib.sha256(got).hexdigest()[:16]), flush=True)
             ok = ok and good
+    # a batch of independent proofs on the sharded context (per-proof mailboxes, exchange slots and gather stage rows)
+    for n, degs, seed, B in ((12, [2], 31, 3), (16, [3, 1], 32, 2)):
+        if n < lg:
+            continue
+        t = zk.Tables.synth(ctx, n, degs, seed, n_proofs=B)
+        s = t.poly_sum()
+        msgs, lens, chal = t.prove(zk.PROTO_MULTI_PARTIAL, s)
+        t.free()
+        if rank == 0:
+            from oracle import cref
+            good = True
+            for b in range(B):
+                tabs = np.concatenate([cref.synth_table(seed + b, k, n) for k in range(sum(degs))])
+                osum = cref.poly_sum(n, degs, tabs)
+                good = good and zk.from_mont(s[b]) == osum and (proof_to_bytes(zk.PROTO_MULTI_PARTIAL, msgs[b], lens[b]), zk.from_mont(chal[b])) == cref.prove(2, n, degs, tabs, osum)
+            print("batch n=%d degs=%s proofs=%d G=%d [bytes]: %s" % (n, degs, B, world, "ok" if good else "MISMATCH"), flush=True)
+            ok = ok and good
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
     dist.barrier()
