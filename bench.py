@@ -48,6 +48,9 @@ WORKLOADS = {
                     "P=2, d=(2,2); layer tables built on the device), replicated on every GPU"),
     "c5": dict(n=22, degs=[2], proto="multi_partial", proofs=64, scaling="strong",
                desc="64 independent prove_partial (degree-2 product, 2^22 entries each), 64/N proofs per GPU, batched launches"),
+    "c5s": dict(n=22, degs=[2], proto="multi_partial", proofs=64, scaling="strong", shard_batch=True,
+                desc="the same 64 proofs, every one SHARDED over the N GPUs (per-round exchange for all 64 at once, late-round gather of "
+                     "the shards inside the resident kernel): BASELINE config 5's gather leg; c5 (replicas) is the faster way to run this batch"),
 }
 
 
@@ -307,7 +310,7 @@ def run_b200(args):
     G = world
     lgG = int(math.log2(G))
     ctx = zk.Context(local_rank)
-    sharded = wl["scaling"] in ("weak", "strong") and wl["proofs"] == 1 and G > 1
+    sharded = wl["scaling"] in ("weak", "strong") and (wl["proofs"] == 1 or wl.get("shard_batch")) and G > 1
     if sharded:
         uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
@@ -316,11 +319,11 @@ def run_b200(args):
         ctx.comm_init(G, rank, bytes(uid.cpu().numpy().tobytes()))
     n = wl["n"] + (lgG if wl["scaling"] == "weak" else 0)
     proofs_total = wl["proofs"]
-    proofs_local = proofs_total // G if (wl["proofs"] > 1) else 1
+    proofs_local = (proofs_total if wl.get("shard_batch") else proofs_total // G) if (wl["proofs"] > 1) else 1
     if wl["proofs"] > 1 and proofs_total % G:
         raise SystemExit("proof count must divide by the GPU count")
     proto = {"multi_partial": zk.PROTO_MULTI_PARTIAL, "sumcheck": zk.PROTO_SUMCHECK}[wl["proto"]]
-    seed = SEED + (rank * proofs_local if wl["proofs"] > 1 else 0)
+    seed = SEED + (rank * proofs_local if (wl["proofs"] > 1 and not wl.get("shard_batch")) else 0)
     tables = zk.Tables.synth(ctx, n, wl["degs"], seed, n_proofs=proofs_local)
     n_tables, n_evals = tables.n_tables, tables.n_evals
 
@@ -655,9 +658,9 @@ def workload_config(workload, G, proof_bytes):
     """The `config` object of a line: a function of the workload and the GPU count only, so that both arms print the same one."""
     wl = WORKLOADS[workload]
     lgG = int(math.log2(G))
-    sharded = wl["scaling"] in ("weak", "strong") and wl["proofs"] == 1 and G > 1
+    sharded = wl["scaling"] in ("weak", "strong") and (wl["proofs"] == 1 or wl.get("shard_batch")) and G > 1
     n = wl["n"] + (lgG if wl["scaling"] == "weak" else 0)
-    proofs_local = wl["proofs"] // G if wl["proofs"] > 1 else 1
+    proofs_local = (wl["proofs"] if wl.get("shard_batch") else wl["proofs"] // G) if wl["proofs"] > 1 else 1
     per_gpu = proofs_local * sum(wl["degs"]) * ((1 << n) // (G if sharded else 1)) * 32
     return {"workload": "%s: %s" % (workload, wl["desc"]), "n_vars": n, "degrees": wl["degs"], "proofs": wl["proofs"], "table_bytes_per_gpu": int(per_gpu),
             "l2_policy": "inputs_exceed_l2" if per_gpu > 126e6 * 2 else "inputs_fit_l2_no_flush",

@@ -1690,9 +1690,27 @@ extern "C" int zksc_bind(zksc_tables* t, const uint64_t* challenges) {
     // at the challenge
     const bool claims = t->raw ? t->raw_claim_next : t->last_evals_valid;
     if (claims && !t->raw) t->claim.resize((size_t)t->B * t->P);
+    bool post = false;
+    if (t->tail_running) {
+        // The kernel's CTAs give up waiting for a challenge after kTailTimeoutNs, each by its own clock.  A challenge posted close to
+        // that deadline could reach some and not others, so the host never posts later than half of it after it saw the results:
+        // past that, the kernel is told to leave (nothing of the round has been folded) and ordinary launches carry on.
+        const double waited_ns = std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - t->tail_seen).count();
+        if (waited_ns > 0.5 * (double)kTailTimeoutNs) TRY(tail_stop(t));
+        else post = true;
+    }
+    const unsigned int post_seq = t->tail_cur + 1;
     for_each_proof(ctx, t->B, [&](uint32_t b) {
         memcpy(t->pending_chal[b].l, challenges + 4 * b, 32);
         host::fold_table(load_h(challenges + 4 * b), t->pending_tab[b].w);
+        if (post) {
+            // the resident kernel folds with it and evaluates the next round: posted as soon as the table exists, before the claims
+            // below (which only the NEXT collection needs) -- this store is on every round's critical path
+            const FoldTab& w = t->pending_tab[b];
+            volatile uint64_t* m = ctx->tail_mail + (size_t)b * kMailUnits;
+            for (int i = 0; i < 8; i++)
+                for (int j = 0; j < 8; j++) m[foldtabs_index(i, j)] = (uint64_t)w.w[i][j] | ((uint64_t)post_seq << 32);
+        }
         if (!claims || t->raw) return;
         std::vector<FrH> ys;
         for (uint32_t p = 0; p < t->P; p++) {
@@ -1705,14 +1723,7 @@ extern "C" int zksc_bind(zksc_tables* t, const uint64_t* challenges) {
     t->vars_left--;
     t->claim_valid = claims;
     t->last_evals_valid = false;
-    if (t->tail_running) {
-        // The kernel's CTAs give up waiting for a challenge after kTailTimeoutNs, each by its own clock.  A challenge posted close to
-        // that deadline could reach some and not others, so the host never posts later than half of it after it saw the results:
-        // past that, the kernel is told to leave (nothing of the round has been folded) and ordinary launches carry on.
-        const double waited_ns = std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - t->tail_seen).count();
-        if (waited_ns > 0.5 * (double)kTailTimeoutNs) TRY(tail_stop(t));
-        else tail_post(t, t->tail_cur + 1);     // the resident kernel folds with it and evaluates the next round
-    }
+    if (post) { t->tail_cur = post_seq; t->tail_posted = true; }
     return ZKSC_OK;
 }
 
