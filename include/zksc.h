@@ -250,7 +250,8 @@ int zksc_ml_elementwise(zksc_ctx* ctx, int op, const uint64_t* a, const uint64_t
  *   evaluation_form.rs:86-96,112-119) is committed, and the polynomial is replaced by its remainder partial_evaluation(point, 0)
  *   (get_poly_remainder, utils.rs:5-10).  evals: 2^n_vars elements; points: n_vars elements; srs_g1: 2^n_vars x 18;
  *   out_evaluation: 1 element (= poly.evaluation(points)); out_proofs: n_vars x 18.
- * The pairing check of MultilinearKZG::verify stays with the caller (ark-ec); it is out of scope here. */
+ * The pairing check of MultilinearKZG::verify is host-side work on n + 1 single points: a Rust caller keeps ark-ec's pairing; the Python
+ * mirror carries its own (zk_cryptography_b200/pairing.py).  No C-ABI entry point: nothing of it runs on the device. */
 int zksc_g1_msm(zksc_ctx* ctx, const uint64_t* scalars, const uint64_t* points, uint64_t n, uint64_t* out);
 int zksc_kzg_open(zksc_ctx* ctx, const uint64_t* evals, uint32_t n_vars, const uint64_t* points, const uint64_t* srs_g1, uint64_t* out_evaluation,
                   uint64_t* out_proofs);

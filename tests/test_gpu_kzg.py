@@ -21,7 +21,8 @@ def _ctx(ctx):
 
 
 def _srs(model):
-    return TrustedSetup(np.stack([k.to_ark(p) for p in model.powers_of_tau_in_g1]))
+    from zk_cryptography_b200 import pairing as pr
+    return TrustedSetup(np.stack([k.to_ark(p) for p in model.powers_of_tau_in_g1]), [pr.g2_mul(t, pr.G2) for t in model.tau])
 
 
 def _msm(ctx, scalars, points):
@@ -67,6 +68,13 @@ def test_reference_kzg_cases(ctx, prover, verifier, ev):
     assert zk.from_mont(proof.evaluation) == want_v
     assert [k.from_ark(p) for p in proof.proofs] == want_proofs
     assert k.verify_in_exponent(ev, verifier, model)       # ... and those are openings the reference's pairing check accepts
+    # MultilinearKZG::verify itself (multilinear_kzg.rs:90-116: the pairing equation, host side) on what the GPU produced -- the
+    # reference's own assertions: true, and false for a setup tampered with (:195-198)
+    commit = MultilinearKZG.commitment(poly, srs)
+    assert MultilinearKZG.verify(commit, verifier, proof, srs) is True
+    bad = list(prover)
+    bad[1] += 10
+    assert MultilinearKZG.verify(commit, verifier, proof, _srs(k.TrustedSetup(bad))) is False
 
 
 def test_random_polynomials(ctx):
@@ -116,3 +124,8 @@ def test_succint_gkr_prove(ctx, layers, inp, points):
                             (zk.from_mont(proof.proof_wc_opening.evaluation), [k.from_ark(p) for p in proof.proof_wc_opening.proofs]))
     assert g.SuccintGKRProtocol.verify(oc, k.from_ark(commitment), got, model)
     assert not g.SuccintGKRProtocol.verify(oc, k.add(want_c, k.G1), want, model)          # a wrong commitment is rejected
+    # SuccintGKRProtocol::verify (succint_protocol.rs:169-266) of the product, pairing checks included: the reference's assertion
+    srs = _srs(model)
+    assert zk.SuccintGKRProtocol.verify(zc, commitment, proof, srs) is True
+    proof.wb_s[-1] = (proof.wb_s[-1] + 1) % R
+    assert zk.SuccintGKRProtocol.verify(zc, commitment, proof, srs) is False

@@ -19,6 +19,6 @@ from .api import (Multilinear, ComposedMultilinear, Sumcheck, SumcheckProof, Com
                   FiatShamirTranscript, SparseUnivariatePolynomial, default_context, set_default_context)
 from .gkr import Gate, GateType, CircuitLayer, Circuit, GKRProof, GKRProtocol, GKRInstance, SuccintGKRProof, SuccintGKRProtocol
 from .kzg import MultilinearKZG, MultilinearKZGProof, TrustedSetup
-from . import utils
+from . import pairing, utils
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -306,8 +306,7 @@ class SuccintGKRProtocol:        # gkr/src/succint_protocol.rs:35-167
     def prove(circuit, circuit_evaluation, tau, ctx=None):
         """SuccintGKRProtocol::prove: GKRProtocol::prove's transcript and layer sumchecks (one C call, zksc_gkr_prove), then the input
         layer -- blown up to the trusted setup's size (add_to_back, evaluation_form.rs:98-110) -- committed and opened at (b, 0, ..)
-        and (c, 0, ..) on the device (zksc_g1_msm, zksc_kzg_open; :136-157).  -> (commitment (18,) uint64 or None, SuccintGKRProof).
-        `verify` (:169-266) needs two pairing checks (MultilinearKZG::verify): the caller's, with ark-ec."""
+        and (c, 0, ..) on the device (zksc_g1_msm, zksc_kzg_open; :136-157).  -> (commitment (18,) uint64 or None, SuccintGKRProof)."""
         from .kzg import MultilinearKZG
         ctx = ctx or default_context()
         base = GKRProtocol.prove(circuit, circuit_evaluation, ctx)
@@ -325,3 +324,55 @@ class SuccintGKRProtocol:        # gkr/src/succint_protocol.rs:35-167
         c = list(ch[L:]) + [0] * (exponent - L)
         commitment = MultilinearKZG.commitment(poly, tau, ctx)
         return commitment, SuccintGKRProof(base, MultilinearKZG.open(poly, b, tau, ctx), MultilinearKZG.open(poly, c, tau, ctx))
+
+    @staticmethod
+    def verify(circuit, commitment, proof, tau):   # gkr/src/succint_protocol.rs:169-266
+        """the sumcheck chain of GKRProtocol::verify, then -- instead of evaluating the input layer -- the two KZG openings are checked
+        (two pairing equations, host side: kzg.py / pairing.py) and their evaluations close the last claim"""
+        from .kzg import MultilinearKZG
+        if len(proof.sumcheck_proofs) != len(proof.wb_s) or len(proof.sumcheck_proofs) != len(proof.wc_s):
+            return False
+        transcript = FiatShamirTranscript()
+        transcript.commit(b"".join(int(e).to_bytes(32, "big") for e in proof.w_0_mle.to_ints()))
+        n_r = transcript.evaluate_n_challenge_into_field(proof.w_0_mle.n_vars)
+        claimed = proof.w_0_mle.evaluation(n_r)
+        p0 = proof.sumcheck_proofs[0]                     # generate_layer_one_verify_sumcheck, gkr/src/utils.rs:59-98
+        if claimed != p0.sum:
+            return False
+        transcript.commit(p0.to_bytes())
+        try:
+            sub = MultiComposedSumcheckVerifier.verify_partial(p0)
+        except ZkscError as e:
+            if e.code == -7:
+                return False
+            raise
+        add1, mul1 = circuit.add_mult_mle(0)
+        rbc = list(n_r) + list(sub.challenges)
+        wb, wc = proof.wb_s[0], proof.wc_s[0]
+        if (add1.evaluation(rbc) * ((wb + wc) % R) + mul1.evaluation(rbc) * (wb * wc % R)) % R != sub.sum:
+            return False
+        alpha, beta = transcript.evaluate_challenge_into_field(), transcript.evaluate_challenge_into_field()
+        claimed = (alpha * wb + beta * wc) % R
+        r_b, r_c = [], []
+        for i in range(1, len(proof.sumcheck_proofs)):    # :207-229 (alpha, beta are drawn before the sub-claim here)
+            p = proof.sumcheck_proofs[i]
+            if claimed != p.sum:
+                return False
+            transcript.commit(p.to_bytes())
+            alpha, beta = transcript.evaluate_challenge_into_field(), transcript.evaluate_challenge_into_field()
+            try:
+                ch = MultiComposedSumcheckVerifier.verify_partial(p).challenges
+            except ZkscError as e:
+                if e.code == -7:
+                    return False
+                raise
+            r_b, r_c = ch[:len(ch) // 2], ch[len(ch) // 2:]
+            claimed = (alpha * proof.wb_s[i] + beta * proof.wc_s[i]) % R
+        if proof.proof_wb_opening is None or proof.proof_wc_opening is None or commitment is None:
+            return False
+        n_tau = len(tau.powers_of_tau_in_g2)
+        rb = list(r_b) + [0] * (n_tau - len(r_b))         # :231-241
+        rc = list(r_c) + [0] * (n_tau - len(r_c))
+        ok = MultilinearKZG.verify(commitment, rb, proof.proof_wb_opening, tau) and MultilinearKZG.verify(commitment, rc, proof.proof_wc_opening, tau)
+        eb, ec = (from_mont(proof.proof_wb_opening.evaluation), from_mont(proof.proof_wc_opening.evaluation)) if ok else (0, 0)      # :248-256
+        return claimed == (alpha * eb + beta * ec) % R

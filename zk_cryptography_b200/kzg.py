@@ -1,19 +1,23 @@
 """Host-side mirror of the reference's multilinear KZG over BLS12-381 (kzg/src/multilinear_kzg.rs, kzg/src/trusted_setup.rs) for
 the part that is table-sized work: `commitment` and `open` run on the GPU through zksc_g1_msm / zksc_kzg_open.  G1 points are held
 in ark-ec's in-memory form (numpy (18,) uint64: Jacobian X, Y, Z in Montgomery form), so a reference-side `Vec<G1Projective>` maps
-onto a (n, 18) array unchanged.  The pairing check of `verify` is the caller's (ark-ec): not part of this path."""
+onto a (n, 18) array unchanged.  `verify` is n + 1 pairings of single points -- host-side, constant-size work like the transcript: it
+runs in `pairing.py` (plain integers), not on the GPU."""
 import numpy as np
 
-from ._lib import ZkscError, lib, p64, to_mont
+from . import pairing
+from ._lib import ZkscError, from_mont, lib, p64, to_mont
 from .api import Multilinear, default_context
 
 
 class TrustedSetup:
-    """TrustedSetup { powers_of_tau_in_g1 } (kzg/src/trusted_setup.rs:10-13): supplied by the caller -- generating it is a
-    one-off the reference does with 2^n scalar multiplications of the generator (:24-35); tests build it with the oracle."""
+    """TrustedSetup { powers_of_tau_in_g1, powers_of_tau_in_g2 } (kzg/src/trusted_setup.rs:10-13): supplied by the caller -- generating
+    it is a one-off the reference does with 2^n scalar multiplications of the generator (:24-35); tests build it with the oracle.
+    powers_of_tau_in_g2 (only the verifier needs it): one affine G2 point per variable, ((x0, x1), (y0, y1)) with Fq2 = x0 + x1 u."""
 
-    def __init__(self, powers_of_tau_in_g1):
+    def __init__(self, powers_of_tau_in_g1, powers_of_tau_in_g2=None):
         self.powers_of_tau_in_g1 = np.ascontiguousarray(powers_of_tau_in_g1, dtype=np.uint64).reshape(-1, 18)
+        self.powers_of_tau_in_g2 = list(powers_of_tau_in_g2) if powers_of_tau_in_g2 is not None else None
 
 
 class MultilinearKZGProof:  # multilinear_kzg.rs:17-21
@@ -43,3 +47,20 @@ class MultilinearKZG:
         proofs = np.zeros((poly.n_vars, 18), dtype=np.uint64)
         ctx.check(lib().zksc_kzg_open(ctx._h, p64(poly.evaluations), poly.n_vars, p64(pts), p64(srs.powers_of_tau_in_g1), p64(ev), p64(proofs)))
         return MultilinearKZGProof(ev, proofs)
+
+    @staticmethod
+    def verify(commit, verifier_points, proof: MultilinearKZGProof, srs: TrustedSetup):  # multilinear_kzg.rs:90-116
+        """e(commit - evaluation g1, g2) == sum_i e(proof_i, tau_i g2 - z_i g2)   (sum_pairing_results, kzg/src/utils.rs:42-61), checked
+        as one product of n + 1 Miller loops and a single final exponentiation."""
+        if srs.powers_of_tau_in_g2 is None:
+            raise ZkscError(-3, "the trusted setup carries no G2 powers: cannot verify")
+        proofs = np.ascontiguousarray(proof.proofs, dtype=np.uint64).reshape(-1, 18)
+        if not (len(verifier_points) == len(srs.powers_of_tau_in_g2) == proofs.shape[0]):      # assert_eq! "Length mismatch", utils.rs:49-50
+            raise ZkscError(-3, "Length mismatch")
+        c = pairing.g1_from_ark(commit) if isinstance(commit, np.ndarray) else commit
+        v = int(from_mont(np.ascontiguousarray(proof.evaluation, dtype=np.uint64))) if isinstance(proof.evaluation, np.ndarray) else int(proof.evaluation)
+        lhs_point = pairing.g1_add(c, pairing.g1_neg(pairing.g1_mul(v, pairing.G1)))
+        pairs = [(lhs_point, pairing.g2_neg(pairing.G2))]
+        for i, z in enumerate(verifier_points):
+            pairs.append((pairing.g1_from_ark(proofs[i]), pairing.g2_add(srs.powers_of_tau_in_g2[i], pairing.g2_neg(pairing.g2_mul(int(z), pairing.G2)))))
+        return pairing.multi_pairing(pairs) == pairing.F12_ONE
