@@ -57,4 +57,5 @@ int zksc_resident_occ_mixed() { return occ<0>(); }
 #if defined(ZKSC_RES_TRACE) && ZKSC_RES_PART == 0
 // debug builds only (not declared in include/zksc.h): copy the timeline out, 64 rounds x 8 phases of %globaltimer ns (degree 2 instantiation)
 extern "C" int zksc_debug_res_trace(unsigned long long* out) { return (int)cudaMemcpyFromSymbol(out, g_res_trace, sizeof(g_res_trace)); }
+extern "C" int zksc_debug_res_cta_trace(unsigned long long* out) { return (int)cudaMemcpyFromSymbol(out, g_res_cta_trace, sizeof(g_res_cta_trace)); }
 #endif

@@ -72,6 +72,8 @@ struct ResArgs {
     unsigned int relay_cap;           // proofs the relay was allocated for (the layout must not depend on the handle in use)
     Fr* partials;                     // [group][kResMaxDegree][cpg]  HBM
     unsigned int* counters;           // [group]                   HBM, zero between rounds
+    unsigned int* work;               // [group]                   HBM, zero between rounds: chunks of 32 pairs handed out beyond every warp's first
+                                      //                           (nullptr: static assignment only)
     // cross-GPU exchange (n_ranks > 1): every rank's unit buffer [2][n_ranks][xch_cap][8]
     unsigned long long* peer_units[kMaxRanks];
     unsigned int n_ranks, rank, xch_cap;
@@ -188,6 +190,18 @@ ZKSC_DEV bool res_read_elem(const unsigned long long* u, unsigned int seq, Fr& o
 #ifdef ZKSC_RES_TRACE
 constexpr int kTraceRounds = 64, kTracePhases = 8;
 __device__ unsigned long long g_res_trace[kTraceRounds * kTracePhases];
+// ... and per CTA, for the kernel's first four rounds: [round][cta] = {start (challenge in shared memory), all warps done with fold + evaluate, %smid}
+constexpr int kTraceCtas = 640, kTraceCtaRounds = 4;
+__device__ unsigned long long g_res_cta_trace[kTraceCtaRounds * kTraceCtas * 3];
+#define ZKSC_TRACE_CTA(which)                                                                                             \
+    do {                                                                                                                 \
+        if (threadIdx.x == 0 && round < (unsigned int)kTraceCtaRounds && blockIdx.x < (unsigned int)kTraceCtas) {        \
+            unsigned int smid_;                                                                                          \
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid_));                                                         \
+            g_res_cta_trace[(round * kTraceCtas + blockIdx.x) * 3 + (which)] = global_timer_ns();                       \
+            g_res_cta_trace[(round * kTraceCtas + blockIdx.x) * 3 + 2] = smid_;                                        \
+        }                                                                                                                \
+    } while (0)
 #define ZKSC_TRACE(cond, phase)                                                                                          \
     do {                                                                                                                 \
         if (threadIdx.x == 0 && (cond) && group == 0 && round < (unsigned int)kTraceRounds)                          \
@@ -195,6 +209,7 @@ __device__ unsigned long long g_res_trace[kTraceRounds * kTracePhases];
     } while (0)
 #else
 #define ZKSC_TRACE(cond, phase) do { } while (0)
+#define ZKSC_TRACE_CTA(which) do { } while (0)
 #endif
 
 // fold + evaluate one pair of every factor; the folded entries go to o[k] + x and o[k] + x + half
@@ -313,6 +328,7 @@ ZKSC_DEV void res_rounds(const ResArgs& args, const volatile ResIds& ids, FoldTa
         }
         __syncthreads();
         ZKSC_TRACE(ci == 0, 0);        // challenge in shared memory
+        ZKSC_TRACE_CTA(0);
         if (s_state != 0) {
             // a timeout is the proof's first CTA's decision alone (the other CTAs only ever hear it through the relay): nothing of
             // this round has been folded anywhere when it is published
@@ -355,9 +371,32 @@ ZKSC_DEV void res_rounds(const ResArgs& args, const volatile ResIds& ids, FoldTa
             const Fr* tin = in;
             const unsigned int tstride = in_stride;
             auto load = [&](int k, unsigned int i) { return ld256_cg(tin + (size_t)k * tstride + i); };
-            for (unsigned int x = x0; x < half; x += xs) {
-                if constexpr (kSmemAcc) res_pair<D>(sacc, load, out, out_stride, x, half, s_tab);
-                else res_pair<D>(acc, load, out, out_stride, x, half, s_tab);
+            // More than one pair per thread: the warps of the group take chunks of 32 pairs from a shared counter instead of a fixed
+            // stride.  The CTAs of an SM do not progress at the same pace (the warp schedulers favour the older ones: with a fixed
+            // split the first CTA of an SM was done after 64 us of an 85 us round, the fourth after 81 us, and the SM ran half empty
+            // in between -- profiles/r02_resident_cta_spread.txt), nor do all SMs; handing the work out keeps every warp busy to
+            // the end.  The next chunk is asked for before the current one is worked on, so the atomic's latency is hidden.  The
+            // rounds that copy entries for other ranks or from them keep the fixed split (a thread must fold what it copied).
+            const bool dynamic = args.work != nullptr && want > args.cpg && !pull && !(args.n_ranks > 1 && round == args.gather_round);
+            if (dynamic) {
+                const unsigned int n_chunks = (half + 31u) >> 5, n_warps = n_active * kResWarps;
+                unsigned int* ctr = args.work + group;
+                unsigned int c = ci * kResWarps + warp;
+                while (c < n_chunks) {
+                    unsigned int nxt = 0;
+                    if (lane == 0) nxt = atomicAdd(ctr, 1u) + n_warps;
+                    const unsigned int x = (c << 5) + lane;
+                    if (x < half) {
+                        if constexpr (kSmemAcc) res_pair<D>(sacc, load, out, out_stride, x, half, s_tab);
+                        else res_pair<D>(acc, load, out, out_stride, x, half, s_tab);
+                    }
+                    c = __shfl_sync(0xffffffffu, nxt, 0);
+                }
+            } else {
+                for (unsigned int x = x0; x < half; x += xs) {
+                    if constexpr (kSmemAcc) res_pair<D>(sacc, load, out, out_stride, x, half, s_tab);
+                    else res_pair<D>(acc, load, out, out_stride, x, half, s_tab);
+                }
             }
         }
         if constexpr (kSmemAcc) {
@@ -367,6 +406,10 @@ ZKSC_DEV void res_rounds(const ResArgs& args, const volatile ResIds& ids, FoldTa
                 for (int i = 0; i < NL; i++) acc[p].l[i] = sacc[p].p[i * kResThreads];
         }
         ZKSC_TRACE(ci == 0, 1);        // fold + evaluate done
+#ifdef ZKSC_RES_TRACE
+        __syncthreads();
+        ZKSC_TRACE_CTA(1);
+#endif
         if (args.n_ranks > 1 && round == args.gather_round) {
             // the folded shard, where the peers can read it (the next round pulls from every rank's stage)
             Fr* stage = const_cast<Fr*>(args.peer_stage[args.rank]) + ((size_t)proof * args.n_tables + koff) * args.gather_local;
@@ -418,7 +461,10 @@ ZKSC_DEV void res_rounds(const ResArgs& args, const volatile ResIds& ids, FoldTa
                 const Fr v = warp_finish_sum(s_red[p]);
                 if (lane == 0) s_tot[p] = v;
             }
-            if (threadIdx.x == 0) args.counters[group] = 0u;     // nobody arrives for the next round before its challenge exists
+            if (threadIdx.x == 0) {
+                args.counters[group] = 0u;     // nobody arrives for the next round before its challenge exists
+                if (args.work) args.work[group] = 0u;
+            }
             __syncthreads();
             ZKSC_TRACE(true, 5);           // partials summed
         }

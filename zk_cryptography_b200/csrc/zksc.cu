@@ -51,10 +51,12 @@ constexpr size_t kXchTagBytes = 256;               // 2 * kMaxRanks tags, padded
 constexpr unsigned int kXchCap = 2048;             // elements per (slot, rank): rounds with more partials use NCCL
 constexpr size_t kXchStageElems = 1u << 15;        // gather stage of a rank: its folded shard of every table, read by the peers (1 MiB)
 constexpr unsigned long long kGatherDefault = 2048;   // sharded contexts: gather the shards when a table is down to this many entries in total
-// The resident kernel takes over from the round with at most this many limb products per rank (ZKSC_TAIL_WORK overrides).  One GPU:
-// degree 2 from 2^20 pairs, degree 3 from 2^19 (above that the ordinary launch's constant-bank fold table is worth more than its
-// ~20 us of fixed cost); sharded contexts one round earlier: there an ordinary round also pays the cross-rank exchange in its last block.
-constexpr unsigned long long kTailWorkDefault = 600ull * 1000 * 1000;
+// The resident kernel takes over from the round with at most this many limb products per rank (ZKSC_TAIL_WORK overrides): degree 2
+// from 2^21 pairs, degree 3 from 2^20 (above that the ordinary launch's constant-bank fold table is worth more than its ~20 us of
+// fixed cost).  Since the resident kernel hands its chunks out dynamically the cross-over sits one round earlier than with a fixed
+// split (profiles/r02_resident_dynamic_ab.txt), at the same place as on sharded contexts, where an ordinary round also pays the
+// cross-rank exchange in its last block.
+constexpr unsigned long long kTailWorkDefault = 1100ull * 1000 * 1000;
 constexpr unsigned long long kTailWorkSharded = 1100ull * 1000 * 1000;
 // exchange buffer of a rank: tags[2][G] | data[2][G][kXchCap] elements (round kernels) | units[2][G][kXchCap][8] (resident kernel) |
 // stage[kXchStageElems] elements (resident kernel, gather)
@@ -207,6 +209,7 @@ struct zksc_ctx {
     // resident rounds kernel (resident_kernel.cuh): mailbox + result units in pinned, device-mapped host memory
     bool fuse_products = true;           // ZKSC_NO_FUSE=1: one launch per product even when the degrees agree
     bool tail_enabled = true;            // ZKSC_NO_TAIL=1: every round is its own launch
+    bool tail_dynamic = true;            // ZKSC_RES_STATIC=1: the resident kernel splits every round by a fixed stride (no work counter)
     unsigned long long tail_work = kTailWorkDefault;   // start threshold of the resident kernel (ZKSC_TAIL_WORK overrides, experiments)
     int res_occ[kResMaxDegree + 1] = {};       // resident CTAs per SM of resident_kernel<dsel>
     volatile uint64_t* tail_mail = nullptr;    // [tail_proofs_cap][kMailUnits]   {word | seq << 32}
@@ -393,6 +396,7 @@ extern "C" int zksc_ctx_create(int device, zksc_ctx** out) {
     { const char* e_ = getenv("ZKSC_NO_MAPPED"); ctx->mapped_results = !(e_ && e_[0] == '1'); }
     { const char* e_ = getenv("ZKSC_PROFILE"); ctx->profile = (e_ && e_[0] == '1'); }
     { const char* e_ = getenv("ZKSC_NO_TAIL"); ctx->tail_enabled = !(e_ && e_[0] == '1'); }
+    { const char* e_ = getenv("ZKSC_RES_STATIC"); ctx->tail_dynamic = !(e_ && e_[0] == '1'); }
     { const char* e_ = getenv("ZKSC_NO_FUSE"); ctx->fuse_products = !(e_ && e_[0] == '1'); }
     { const char* e_ = getenv("ZKSC_TAIL_WORK"); if (e_ && atoll(e_) > 0) ctx->tail_work = (unsigned long long)atoll(e_); }
     { const char* e_ = getenv("ZKSC_NO_STAGED"); ctx->staged = !(e_ && e_[0] == '1'); }
@@ -1091,9 +1095,9 @@ static int tail_ensure(zksc_ctx* ctx, size_t proofs, size_t units, size_t groups
     const size_t relay_words = 2 * proofs * (kMailUnits + 1);
     CK(cudaMalloc(&ctx->tail_relay, relay_words * sizeof(unsigned long long)));
     CK(cudaMalloc(&ctx->tail_partials, partials * sizeof(Fr)));
-    CK(cudaMalloc(&ctx->tail_counters, groups * sizeof(unsigned int)));
+    CK(cudaMalloc(&ctx->tail_counters, 2 * groups * sizeof(unsigned int)));     // arrival counters, then work counters
     CK(cudaMemsetAsync(ctx->tail_relay, 0, relay_words * sizeof(unsigned long long), ctx->stream));
-    CK(cudaMemsetAsync(ctx->tail_counters, 0, groups * sizeof(unsigned int), ctx->stream));
+    CK(cudaMemsetAsync(ctx->tail_counters, 0, 2 * groups * sizeof(unsigned int), ctx->stream));
     ctx->tail_proofs_cap = proofs; ctx->tail_units_cap = units; ctx->tail_groups_cap = groups; ctx->tail_part_cap = partials;
     return ZKSC_OK;
 }
@@ -1127,7 +1131,7 @@ static int tail_forget(zksc_tables* t, bool disable) {
     if (ctx->tail_res) memset((void*)ctx->tail_res, 0, (ctx->tail_units_cap + ctx->tail_proofs_cap) * 8);
     ctx->tail_seq = 0;
     if (e == cudaSuccess && ctx->tail_relay) e = cudaMemsetAsync(ctx->tail_relay, 0, 2 * ctx->tail_proofs_cap * (kMailUnits + 1) * sizeof(unsigned long long), ctx->stream);
-    if (e == cudaSuccess && ctx->tail_counters) e = cudaMemsetAsync(ctx->tail_counters, 0, ctx->tail_groups_cap * sizeof(unsigned int), ctx->stream);
+    if (e == cudaSuccess && ctx->tail_counters) e = cudaMemsetAsync(ctx->tail_counters, 0, 2 * ctx->tail_groups_cap * sizeof(unsigned int), ctx->stream);
     if (e == cudaSuccess && ctx->xch_local) e = cudaMemsetAsync(ctx->xch_local + kXchUnitsOffset(ctx->n_ranks), 0, kXchUnitsBytes(ctx->n_ranks), ctx->stream);
     if (e != cudaSuccess) { ctx->err = std::string("resident kernel clean-up: ") + cudaGetErrorString(e); return ZKSC_ERR_CUDA; }
     return ZKSC_OK;
@@ -1328,6 +1332,7 @@ static int tail_start(zksc_tables* t, unsigned long long half, bool sharded) {
     a.mail = ctx->tail_mail_dev; a.results = ctx->tail_res_dev; a.status = ctx->tail_res_dev + ctx->tail_status_off;
     a.relay = ctx->tail_relay; a.relay_tags = ctx->tail_relay + 2 * ctx->tail_proofs_cap * kMailUnits;
     a.partials = ctx->tail_partials; a.counters = ctx->tail_counters;
+    a.work = ctx->tail_dynamic ? ctx->tail_counters + ctx->tail_groups_cap : nullptr;
     a.n_ranks = 1; a.rank = 0; a.xch_cap = kXchCap;
     a.gather_round = kNoGather;
     if (sharded) {
