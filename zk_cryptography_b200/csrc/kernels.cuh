@@ -24,6 +24,12 @@ namespace zksc {
 constexpr int kThreads = 128;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxBatch = 64;   // proofs per launch (challenges travel as kernel parameters)
+// RoundBase::counters: [group] arrivals | [n_groups] groups done | from kWorkCtrBase on, for launches of at most kDynMaxGroups groups: the
+// work counters, one per (group, warp index in the CTA), each in a cache line of its own -- atomics on ONE address go through at
+// ~0.8 per ns (measured: a degree-1 round of 2^26 pairs took 2.6 ms instead of 1.0 with a single counter per group)
+constexpr unsigned int kDynMaxGroups = 8;
+constexpr unsigned int kWorkCtrBase = kMaxBatch * 8 + 32, kWorkCtrWords = 32;
+constexpr unsigned int kRoundCounterWords = kWorkCtrBase + kDynMaxGroups * 4 * kWorkCtrWords;
 constexpr int kMaxDegree = 8;
 
 constexpr int kMaxRanks = 8;    // GPUs of one NVSwitch box reachable through peer memory
@@ -54,7 +60,12 @@ struct RoundBase {
     unsigned int res_prod_stride;
     unsigned long long half;   // pairs per table in the round being evaluated (N_j / 2)
     Fr* partials;              // [proof][block][npts] scratch
-    unsigned int* counters;    // [proof], zero on entry, zero on exit
+    unsigned int* counters;    // arrivals, groups done, work counters (kWorkCtrBase above); zero on entry, zero on exit
+    unsigned int dynamic;      // 1: warp w of every CTA of a group works on the chunks (32 pairs) c = w mod 4 and takes them from that
+                               // partition's counter (beyond a first, fixed one); 0: fixed stride.  The CTAs that share an SM do not
+                               // progress at the same pace -- the schedulers favour the older warps -- so a fixed split leaves the SM
+                               // half empty while its last CTA finishes (profiles/r02_resident_cta_spread.txt: c3 7.7 % faster); the
+                               // proof does not depend on who folds which pair.  Needs all CTAs of the launch resident at once.
     Fr* result;                // [proof][res_stride]: npts Montgomery elements each
     unsigned int res_stride;
     unsigned int npts;         // evaluation points 0..npts-1 are wanted (<= D+1); SKIP1 kernels leave point 1 untouched
@@ -303,6 +314,8 @@ ZKSC_DEV void reduce_and_publish(Acc<NL> (&acc)[NP], const RoundBase& args, int 
     __syncthreads();
     if (threadIdx.x == 0) {
         args.counters[group] = 0;
+        if (args.dynamic)
+            for (int w = 0; w < kWarps; w++) args.counters[kWorkCtrBase + (group * kWarps + w) * kWorkCtrWords] = 0;
         bool final_block = false;
         if (args.flag) {
             __threadfence_system();
@@ -436,23 +449,20 @@ __global__ void __launch_bounds__(kThreads, ZKSC_ROUND_MINB) round_kernel(const 
         }
     }
 
-    const unsigned long long stride = (unsigned long long)gridDim.x * kThreads;
-    for (unsigned long long x = (unsigned long long)blockIdx.x * kThreads + threadIdx.x; x < half; x += stride) {
+    // chunk c = pairs [32 c, 32 c + 32): a warp's first chunk is its index in the group, the following ones come at a fixed stride
+    // or from the group's counter (asked for before the current chunk is worked on: the atomic's latency is hidden)
+    const unsigned int n_chunks = (unsigned int)((half + 31) >> 5);
+    unsigned int* work_ctr = args.counters + kWorkCtrBase + ((blockIdx.z * gridDim.y + proof) * kWarps + (threadIdx.x >> 5)) * kWorkCtrWords;
+    const bool dynamic = args.dynamic != 0u;
+    for (unsigned int i = blockIdx.x;;) {                    // i-th chunk of this warp's partition
+        const unsigned int c = i * kWarps + (threadIdx.x >> 5);
+        if (c >= n_chunks) break;
+        unsigned int nxt = i + gridDim.x;
+        if (dynamic && (threadIdx.x & 31) == 0) nxt = atomicAdd(work_ctr, 1u) + gridDim.x;
+        const unsigned long long x = ((unsigned long long)c << 5) + (threadIdx.x & 31);
+        i = dynamic ? __shfl_sync(0xffffffffu, nxt, 0) : nxt;
+        if (x >= half) continue;
         Fr a[D], b[D];
-#if ZKSC_PREFETCH
-        // the next iteration's 4 D entries on their way from HBM while this one computes (no registers held: a prefetch has
-        // no destination); 1 = into L2, 2 = into L1
-        if constexpr (FOLD) {
-            const unsigned long long xn = x + stride;
-            if (xn < half) {
-#pragma unroll
-                for (int k = 0; k < D; k++) {
-                    const Fr* t = in + (size_t)k * args.in_tab_stride + xn;
-                    prefetch_line(t); prefetch_line(t + half); prefetch_line(t + 2 * half); prefetch_line(t + 3 * half);
-                }
-            }
-        }
-#endif
         if constexpr (FOLD && D == 2 && ZKSC_FOLD_LOADALL) {
             // all eight entries of the pair in flight at once: one exposed memory latency per iteration instead of two
             const Fr* t0 = in;
@@ -580,6 +590,12 @@ __global__ void __launch_bounds__(kThreads, ZKSC_TMA_MINB(D)) round_tma_kernel(c
     const unsigned int n_tiles = (unsigned int)(half / kTilePairs);
     const unsigned int tile_stride = gridDim.x * kWarps;
     unsigned int tile = blockIdx.x * kWarps + warp;
+    // a warp's first two tiles are fixed (the second is fetched while the first is worked on); the following ones come at a fixed
+    // stride or, with args.dynamic, from the counter of the warp's partition (tiles = warp mod 4) -- asked for one tile ahead of the
+    // fetch (see RoundBase::dynamic)
+    unsigned int next = tile + tile_stride;
+    unsigned int* work_ctr = args.counters + kWorkCtrBase + ((blockIdx.z * gridDim.y + proof) * kWarps + warp) * kWorkCtrWords;
+    const bool dynamic = args.dynamic != 0u;
 
     auto issue = [&](unsigned int t) {               // lane 0 only
         const unsigned long long x0 = (unsigned long long)t * kTilePairs;
@@ -603,8 +619,10 @@ __global__ void __launch_bounds__(kThreads, ZKSC_TMA_MINB(D)) round_tma_kernel(c
     for (int p = 0; p < NP; p++) acc_zero(acc[p]);
 
     uint32_t phase = 0;
-    for (; tile < n_tiles; tile += tile_stride) {
+    while (tile < n_tiles) {
         const unsigned long long x = (unsigned long long)tile * kTilePairs + lane;
+        unsigned int fut = next + tile_stride;
+        if (dynamic && lane == 0) fut = (atomicAdd(work_ctr, 1u) + 2 * gridDim.x) * kWarps + warp;
         mbar_wait(bar, phase);
         phase ^= 1;
         Fr a[D], b[D];
@@ -624,7 +642,7 @@ __global__ void __launch_bounds__(kThreads, ZKSC_TMA_MINB(D)) round_tma_kernel(c
                 const Fr q0 = lds256(tab + kSegBytes), q1 = lds256(tab + 3 * kSegBytes);
                 if (k == D - 1) {
                     __syncwarp();                     // every lane has its last operands: the slot is free
-                    if (lane == 0 && tile + tile_stride < n_tiles) issue(tile + tile_stride);
+                    if (lane == 0 && next < n_tiles) issue(next);
                 }
                 b[k] = fr_fold_tab(q0, q1, args.tab[proof]);
                 st256(o + x + half, b[k]);
@@ -633,11 +651,13 @@ __global__ void __launch_bounds__(kThreads, ZKSC_TMA_MINB(D)) round_tma_kernel(c
                 b[k] = lds256(tab + kSegBytes);
                 if (k == D - 1) {
                     __syncwarp();
-                    if (lane == 0 && tile + tile_stride < n_tiles) issue(tile + tile_stride);
+                    if (lane == 0 && next < n_tiles) issue(next);
                 }
             }
         }
         accumulate_points<D, SKIP1>(acc, a, b, npts);
+        tile = next;
+        next = dynamic ? __shfl_sync(0xffffffffu, fut, 0) : fut;
     }
     reduce_and_publish<NL, NP, SKIP1>(acc, args, npts);
 }

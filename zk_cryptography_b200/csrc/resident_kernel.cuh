@@ -72,8 +72,8 @@ struct ResArgs {
     unsigned int relay_cap;           // proofs the relay was allocated for (the layout must not depend on the handle in use)
     Fr* partials;                     // [group][kResMaxDegree][cpg]  HBM
     unsigned int* counters;           // [group]                   HBM, zero between rounds
-    unsigned int* work;               // [group]                   HBM, zero between rounds: chunks of 32 pairs handed out beyond every warp's first
-                                      //                           (nullptr: static assignment only)
+    unsigned int* work;               // [group][warp in CTA][kWorkCtrWords]  HBM, zero between rounds: chunks of 32 pairs handed out beyond every
+                                      //                           warp's first (nullptr: static assignment only)
     // cross-GPU exchange (n_ranks > 1): every rank's unit buffer [2][n_ranks][xch_cap][8]
     unsigned long long* peer_units[kMaxRanks];
     unsigned int n_ranks, rank, xch_cap;
@@ -377,20 +377,23 @@ ZKSC_DEV void res_rounds(const ResArgs& args, const volatile ResIds& ids, FoldTa
             // in between -- profiles/r02_resident_cta_spread.txt), nor do all SMs; handing the work out keeps every warp busy to
             // the end.  The next chunk is asked for before the current one is worked on, so the atomic's latency is hidden.  The
             // rounds that copy entries for other ranks or from them keep the fixed split (a thread must fold what it copied).
-            const bool dynamic = args.work != nullptr && want > args.cpg && !pull && !(args.n_ranks > 1 && round == args.gather_round);
+            // One counter per warp index in the CTA (warp w works on the chunks c = w mod 4), each in its own cache line: atomics on a
+            // single address go through at ~0.8 per ns.  Degree 1 is bound by HBM alone: nothing to balance.
+            const bool dynamic = D >= 2 && args.work != nullptr && want > args.cpg && !pull && !(args.n_ranks > 1 && round == args.gather_round);
             if (dynamic) {
-                const unsigned int n_chunks = (half + 31u) >> 5, n_warps = n_active * kResWarps;
-                unsigned int* ctr = args.work + group;
-                unsigned int c = ci * kResWarps + warp;
-                while (c < n_chunks) {
+                const unsigned int n_chunks = (half + 31u) >> 5;
+                unsigned int* ctr = args.work + ((size_t)group * kResWarps + warp) * kWorkCtrWords;
+                for (unsigned int i = ci;;) {
+                    const unsigned int c = i * kResWarps + warp;
+                    if (c >= n_chunks) break;
                     unsigned int nxt = 0;
-                    if (lane == 0) nxt = atomicAdd(ctr, 1u) + n_warps;
+                    if (lane == 0) nxt = atomicAdd(ctr, 1u) + n_active;
                     const unsigned int x = (c << 5) + lane;
                     if (x < half) {
                         if constexpr (kSmemAcc) res_pair<D>(sacc, load, out, out_stride, x, half, s_tab);
                         else res_pair<D>(acc, load, out, out_stride, x, half, s_tab);
                     }
-                    c = __shfl_sync(0xffffffffu, nxt, 0);
+                    i = __shfl_sync(0xffffffffu, nxt, 0);
                 }
             } else {
                 for (unsigned int x = x0; x < half; x += xs) {
@@ -463,8 +466,8 @@ ZKSC_DEV void res_rounds(const ResArgs& args, const volatile ResIds& ids, FoldTa
             }
             if (threadIdx.x == 0) {
                 args.counters[group] = 0u;     // nobody arrives for the next round before its challenge exists
-                if (args.work) args.work[group] = 0u;
             }
+            if (args.work && threadIdx.x < kResWarps) args.work[((size_t)group * kResWarps + threadIdx.x) * kWorkCtrWords] = 0u;
             __syncthreads();
             ZKSC_TRACE(true, 5);           // partials summed
         }

@@ -42,6 +42,7 @@ using zksc::host::FrH;
 
 static_assert(kMaxDegree == ZKSC_MAX_DEGREE, "header / kernel limits differ");
 static_assert(kResMaxProducts == ZKSC_MAX_PRODUCTS, "header / resident kernel limits differ");
+static_assert(kWorkCtrBase > kMaxBatch * ZKSC_MAX_PRODUCTS, "work counters overlap the arrival counters");
 cudaError_t zksc_launch_resident(int dsel, unsigned int ctas, cudaStream_t s, const ResArgs& a);   // res_inst.cu
 int zksc_resident_occ(int dsel);
 
@@ -209,6 +210,7 @@ struct zksc_ctx {
     // resident rounds kernel (resident_kernel.cuh): mailbox + result units in pinned, device-mapped host memory
     bool fuse_products = true;           // ZKSC_NO_FUSE=1: one launch per product even when the degrees agree
     bool tail_enabled = true;            // ZKSC_NO_TAIL=1: every round is its own launch
+    bool round_dynamic = true;           // ZKSC_ROUND_STATIC=1: the round kernels split a round by a fixed stride (kernels.cuh RoundBase::dynamic)
     bool tail_dynamic = true;            // ZKSC_RES_STATIC=1: the resident kernel splits every round by a fixed stride (no work counter)
     unsigned long long tail_work = kTailWorkDefault;   // start threshold of the resident kernel (ZKSC_TAIL_WORK overrides, experiments)
     int res_occ[kResMaxDegree + 1] = {};       // resident CTAs per SM of resident_kernel<dsel>
@@ -379,8 +381,8 @@ extern "C" int zksc_ctx_create(int device, zksc_ctx** out) {
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
         cudaGetLastError();
     }
-    if ((e = cudaMalloc(&ctx->counters, (kMaxBatch * ZKSC_MAX_PRODUCTS + 1) * sizeof(unsigned int))) != cudaSuccess) return fail(e, "cudaMalloc");
-    if ((e = cudaMemset(ctx->counters, 0, (kMaxBatch * ZKSC_MAX_PRODUCTS + 1) * sizeof(unsigned int))) != cudaSuccess) return fail(e, "cudaMemset");
+    if ((e = cudaMalloc(&ctx->counters, kRoundCounterWords * sizeof(unsigned int))) != cudaSuccess) return fail(e, "cudaMalloc");
+    if ((e = cudaMemset(ctx->counters, 0, kRoundCounterWords * sizeof(unsigned int))) != cudaSuccess) return fail(e, "cudaMemset");
 #define ZKSC_OCC(D) zksc_prepare_round_##D(); for (int v = 0; v < 6; v++) ctx->occ[D][v] = zksc_occ_round_##D(v);
     ZKSC_OCC(1) ZKSC_OCC(2) ZKSC_OCC(3) ZKSC_OCC(4) ZKSC_OCC(5) ZKSC_OCC(6) ZKSC_OCC(7) ZKSC_OCC(8)
     if ((e = cudaGetLastError()) != cudaSuccess) return fail(e, "occupancy query (is this an sm_100a device?)");
@@ -397,6 +399,7 @@ extern "C" int zksc_ctx_create(int device, zksc_ctx** out) {
     { const char* e_ = getenv("ZKSC_PROFILE"); ctx->profile = (e_ && e_[0] == '1'); }
     { const char* e_ = getenv("ZKSC_NO_TAIL"); ctx->tail_enabled = !(e_ && e_[0] == '1'); }
     { const char* e_ = getenv("ZKSC_RES_STATIC"); ctx->tail_dynamic = !(e_ && e_[0] == '1'); }
+    { const char* e_ = getenv("ZKSC_ROUND_STATIC"); ctx->round_dynamic = !(e_ && e_[0] == '1'); }
     { const char* e_ = getenv("ZKSC_NO_FUSE"); ctx->fuse_products = !(e_ && e_[0] == '1'); }
     { const char* e_ = getenv("ZKSC_TAIL_WORK"); if (e_ && atoll(e_) > 0) ctx->tail_work = (unsigned long long)atoll(e_); }
     { const char* e_ = getenv("ZKSC_NO_STAGED"); ctx->staged = !(e_ && e_[0] == '1'); }
@@ -1076,6 +1079,9 @@ static Geo geo_of(const zksc_tables* t, int where) {
 // ------------------------------------------------------------------------------------------------
 // resident rounds kernel: host side (resident_kernel.cuh has the protocol)
 // ------------------------------------------------------------------------------------------------
+// tail_counters: [groups] arrival counters | (cache-line aligned) [groups][kResWarps][kWorkCtrWords] work counters
+static size_t kTailWorkBase(size_t groups) { return (groups + kWorkCtrWords - 1) / kWorkCtrWords * kWorkCtrWords; }
+static size_t kTailCounterWords(size_t groups) { return kTailWorkBase(groups) + groups * kResWarps * kWorkCtrWords; }
 static int tail_ensure(zksc_ctx* ctx, size_t proofs, size_t units, size_t groups, size_t partials) {
     if (proofs <= ctx->tail_proofs_cap && units <= ctx->tail_units_cap && groups <= ctx->tail_groups_cap && partials <= ctx->tail_part_cap) return ZKSC_OK;
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1095,9 +1101,9 @@ static int tail_ensure(zksc_ctx* ctx, size_t proofs, size_t units, size_t groups
     const size_t relay_words = 2 * proofs * (kMailUnits + 1);
     CK(cudaMalloc(&ctx->tail_relay, relay_words * sizeof(unsigned long long)));
     CK(cudaMalloc(&ctx->tail_partials, partials * sizeof(Fr)));
-    CK(cudaMalloc(&ctx->tail_counters, 2 * groups * sizeof(unsigned int)));     // arrival counters, then work counters
+    CK(cudaMalloc(&ctx->tail_counters, kTailCounterWords(groups) * sizeof(unsigned int)));     // arrival counters, then work counters
     CK(cudaMemsetAsync(ctx->tail_relay, 0, relay_words * sizeof(unsigned long long), ctx->stream));
-    CK(cudaMemsetAsync(ctx->tail_counters, 0, 2 * groups * sizeof(unsigned int), ctx->stream));
+    CK(cudaMemsetAsync(ctx->tail_counters, 0, kTailCounterWords(groups) * sizeof(unsigned int), ctx->stream));
     ctx->tail_proofs_cap = proofs; ctx->tail_units_cap = units; ctx->tail_groups_cap = groups; ctx->tail_part_cap = partials;
     return ZKSC_OK;
 }
@@ -1131,7 +1137,7 @@ static int tail_forget(zksc_tables* t, bool disable) {
     if (ctx->tail_res) memset((void*)ctx->tail_res, 0, (ctx->tail_units_cap + ctx->tail_proofs_cap) * 8);
     ctx->tail_seq = 0;
     if (e == cudaSuccess && ctx->tail_relay) e = cudaMemsetAsync(ctx->tail_relay, 0, 2 * ctx->tail_proofs_cap * (kMailUnits + 1) * sizeof(unsigned long long), ctx->stream);
-    if (e == cudaSuccess && ctx->tail_counters) e = cudaMemsetAsync(ctx->tail_counters, 0, 2 * ctx->tail_groups_cap * sizeof(unsigned int), ctx->stream);
+    if (e == cudaSuccess && ctx->tail_counters) e = cudaMemsetAsync(ctx->tail_counters, 0, kTailCounterWords(ctx->tail_groups_cap) * sizeof(unsigned int), ctx->stream);
     if (e == cudaSuccess && ctx->xch_local) e = cudaMemsetAsync(ctx->xch_local + kXchUnitsOffset(ctx->n_ranks), 0, kXchUnitsBytes(ctx->n_ranks), ctx->stream);
     if (e != cudaSuccess) { ctx->err = std::string("resident kernel clean-up: ") + cudaGetErrorString(e); return ZKSC_ERR_CUDA; }
     return ZKSC_OK;
@@ -1332,7 +1338,7 @@ static int tail_start(zksc_tables* t, unsigned long long half, bool sharded) {
     a.mail = ctx->tail_mail_dev; a.results = ctx->tail_res_dev; a.status = ctx->tail_res_dev + ctx->tail_status_off;
     a.relay = ctx->tail_relay; a.relay_tags = ctx->tail_relay + 2 * ctx->tail_proofs_cap * kMailUnits;
     a.partials = ctx->tail_partials; a.counters = ctx->tail_counters;
-    a.work = ctx->tail_dynamic ? ctx->tail_counters + ctx->tail_groups_cap : nullptr;
+    a.work = ctx->tail_dynamic ? ctx->tail_counters + kTailWorkBase(ctx->tail_groups_cap) : nullptr;
     a.n_ranks = 1; a.rank = 0; a.xch_cap = kXchCap;
     a.gather_round = kNoGather;
     if (sharded) {
@@ -1596,6 +1602,12 @@ static int round_evals_impl(zksc_tables* t, uint64_t* out, uint32_t npts_cap) {
             // the staged kernel works on whole 32-pair warp tiles and pays off once HBM latency matters
             const bool staged = ctx->staged && (variant == 0 || ctx->staged_fold) && ctx->occ[D][3 + variant] > 0 && half % kTilePairs == 0 && half >= 4096;
             int gx = staged ? grid_for(ctx, half / kTilePairs * 32, kThreads, ctx->occ[D][3 + variant]) : grid_for(ctx, half, kThreads, ctx->occ[D][variant]);
+            // Chunks from a counter (kernels.cuh RoundBase::dynamic) need every CTA of a group resident at once -- the first ones to
+            // start would take all of the group's work -- so it is for launches of a few groups, the grid cut to what fits; a batch of
+            // many proofs is balanced by the CTA scheduler itself (37888 short-lived CTAs for 64 proofs), with a fixed split.
+            const unsigned int n_groups = nb * p_step;
+            const bool dynamic = ctx->round_dynamic && n_groups <= kDynMaxGroups && D >= 2;     // degree 1 is bound by HBM alone: nothing to balance
+            if (dynamic) gx = std::max(1, std::min(gx, ctx->sms * ctx->occ[D][staged ? 3 + variant : variant] / (int)n_groups));
             TRY(ensure_partials(ctx, (size_t)nb * gx * (D + 1) * p_step));
             RoundBase base;
             base.in = gi.base + (size_t)b0 * gi.proof_stride + (size_t)t->koff[p] * gi.tab_stride;
@@ -1606,6 +1618,7 @@ static int round_evals_impl(zksc_tables* t, uint64_t* out, uint32_t npts_cap) {
             base.res_prod_stride = (unsigned int)(D + 1);
             base.half = half;
             base.partials = ctx->partials; base.counters = ctx->counters;
+            base.dynamic = dynamic ? 1u : 0u;
             base.result = res + (size_t)b0 * t->E + t->eoff[p];
             base.res_stride = t->E;
             base.npts = (uint32_t)(D + 1) < npts_cap ? (D + 1) : npts_cap;
