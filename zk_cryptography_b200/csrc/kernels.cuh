@@ -27,7 +27,7 @@ constexpr int kMaxBatch = 64;   // proofs per launch (challenges travel as kerne
 // RoundBase::counters: [group] arrivals | [n_groups] groups done | from kWorkCtrBase on, for launches of at most kDynMaxGroups groups: the
 // work counters, one per (group, warp index in the CTA), each in a cache line of its own -- atomics on ONE address go through at
 // ~0.8 per ns (measured: a degree-1 round of 2^26 pairs took 2.6 ms instead of 1.0 with a single counter per group)
-constexpr unsigned int kDynMaxGroups = 8;
+constexpr unsigned int kDynMaxGroups = 64;
 constexpr unsigned int kWorkCtrBase = kMaxBatch * 8 + 32, kWorkCtrWords = 32;
 constexpr unsigned int kRoundCounterWords = kWorkCtrBase + kDynMaxGroups * 4 * kWorkCtrWords;
 constexpr int kMaxDegree = 8;

@@ -210,6 +210,7 @@ struct zksc_ctx {
     // resident rounds kernel (resident_kernel.cuh): mailbox + result units in pinned, device-mapped host memory
     bool fuse_products = true;           // ZKSC_NO_FUSE=1: one launch per product even when the degrees agree
     bool tail_enabled = true;            // ZKSC_NO_TAIL=1: every round is its own launch
+    unsigned int dyn_max_groups = 8;     // ZKSC_DYN_MAX_GROUPS (<= kDynMaxGroups): most groups of a launch that takes its chunks from counters
     bool round_dynamic = true;           // ZKSC_ROUND_STATIC=1: the round kernels split a round by a fixed stride (kernels.cuh RoundBase::dynamic)
     bool tail_dynamic = true;            // ZKSC_RES_STATIC=1: the resident kernel splits every round by a fixed stride (no work counter)
     unsigned long long tail_work = kTailWorkDefault;   // start threshold of the resident kernel (ZKSC_TAIL_WORK overrides, experiments)
@@ -400,6 +401,7 @@ extern "C" int zksc_ctx_create(int device, zksc_ctx** out) {
     { const char* e_ = getenv("ZKSC_NO_TAIL"); ctx->tail_enabled = !(e_ && e_[0] == '1'); }
     { const char* e_ = getenv("ZKSC_RES_STATIC"); ctx->tail_dynamic = !(e_ && e_[0] == '1'); }
     { const char* e_ = getenv("ZKSC_ROUND_STATIC"); ctx->round_dynamic = !(e_ && e_[0] == '1'); }
+    { const char* e_ = getenv("ZKSC_DYN_MAX_GROUPS"); if (e_) ctx->dyn_max_groups = std::min<unsigned int>(kDynMaxGroups, (unsigned int)strtoul(e_, nullptr, 10)); }
     { const char* e_ = getenv("ZKSC_NO_FUSE"); ctx->fuse_products = !(e_ && e_[0] == '1'); }
     { const char* e_ = getenv("ZKSC_TAIL_WORK"); if (e_ && atoll(e_) > 0) ctx->tail_work = (unsigned long long)atoll(e_); }
     { const char* e_ = getenv("ZKSC_NO_STAGED"); ctx->staged = !(e_ && e_[0] == '1'); }
@@ -1606,7 +1608,7 @@ static int round_evals_impl(zksc_tables* t, uint64_t* out, uint32_t npts_cap) {
             // start would take all of the group's work -- so it is for launches of a few groups, the grid cut to what fits; a batch of
             // many proofs is balanced by the CTA scheduler itself (37888 short-lived CTAs for 64 proofs), with a fixed split.
             const unsigned int n_groups = nb * p_step;
-            const bool dynamic = ctx->round_dynamic && n_groups <= kDynMaxGroups && D >= 2;     // degree 1 is bound by HBM alone: nothing to balance
+            const bool dynamic = ctx->round_dynamic && n_groups <= ctx->dyn_max_groups && D >= 2;     // degree 1 is bound by HBM alone: nothing to balance
             if (dynamic) gx = std::max(1, std::min(gx, ctx->sms * ctx->occ[D][staged ? 3 + variant : variant] / (int)n_groups));
             TRY(ensure_partials(ctx, (size_t)nb * gx * (D + 1) * p_step));
             RoundBase base;
