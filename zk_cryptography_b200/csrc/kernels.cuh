@@ -232,31 +232,44 @@ ZKSC_DEV Fr ld256_cg(const Fr* p) {     // L2 only: for data another SM wrote wh
                  : "memory");
     return v;
 }
-// The whole CTA (kThreads threads) sums n canonical elements  base[i * elem_stride],  i < n, into an unreduced 9-limb accumulator
-// per warp: s_red[warp].  Five loads per thread are issued before the first one is consumed -- the last block of a round walks
-// up to 148 x 4 per-block partials per evaluation point, and one load per dependent iteration made that walk ~5 us long.
-ZKSC_DEV void cta_sum_elems(const Fr* base, size_t elem_stride, unsigned int n, Acc<9>* s_red) {
-    constexpr int KB = 5;
-    Acc<9> a;
-    acc_zero(a);
-    for (unsigned int b0 = 0; b0 < n; b0 += KB * kThreads) {
-        Fr v[KB];
+// The whole CTA (kThreads threads) sums, for each of NP evaluation points, n canonical elements  base[p * point_stride + i * elem_stride],
+// i < n, into unreduced 9-limb accumulators  s_red[p][slice].  The points are summed side by side -- warp w takes (point, slice) =
+// (w mod NP, w / NP), a slice being every kSlices-th element -- and ten loads per lane are issued before the first one is consumed:
+// the last block of a round walks up to 148 x 4 per-block partials per point, and one point after the other with one load per
+// dependent iteration made that walk 3-7 us long.
+template <int NP>
+struct SumShape {
+    static constexpr int kSlices = (NP <= kWarps) ? kWarps / NP : 1;     // warps per point
+};
+template <int NP>
+ZKSC_DEV void cta_sum_points(const Fr* base, size_t point_stride, size_t elem_stride, unsigned int n, Acc<9> (*s_red)[kWarps]) {
+    constexpr int KB = 10, SL = SumShape<NP>::kSlices;
+    const int lane = threadIdx.x & 31;
+    for (int task = threadIdx.x >> 5; task < NP * SL; task += kWarps) {
+        const int p = task % NP, j = task / NP;
+        const Fr* src = base + (size_t)p * point_stride;
+        Acc<9> a;
+        acc_zero(a);
+        for (unsigned int b0 = j * 32; b0 < n; b0 += KB * SL * 32) {
+            Fr v[KB];
 #pragma unroll
-        for (int k = 0; k < KB; k++) {
-            const unsigned int c = b0 + k * kThreads + threadIdx.x;
-            v[k] = (c < n) ? ld256_cg(base + (size_t)c * elem_stride) : fr_zero();
+            for (int k = 0; k < KB; k++) {
+                const unsigned int c = b0 + k * SL * 32 + lane;
+                v[k] = (c < n) ? ld256_cg(src + (size_t)c * elem_stride) : fr_zero();
+            }
+#pragma unroll
+            for (int k = 0; k < KB; k++) acc_add<9, 8>(a, v[k].l);
         }
-#pragma unroll
-        for (int k = 0; k < KB; k++) acc_add<9, 8>(a, v[k].l);
+        acc_warp_reduce(a);
+        if (lane == 0) s_red[p][j] = a;
     }
-    acc_warp_reduce(a);
-    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = a;
 }
-// ... and one warp finishes: the canonical total of what cta_sum_elems left in s_red (call after a __syncthreads)
-ZKSC_DEV Fr warp_finish_sum(const Acc<9>* s_red) {
+// ... and one warp finishes a point: the canonical total of what cta_sum_points left in s_red[p] (call after a __syncthreads)
+template <int NP>
+ZKSC_DEV Fr warp_finish_sum(const Acc<9>* s_red_p) {
     const int lane = threadIdx.x & 31;
     Acc<9> a;
-    if (lane < kWarps) a = s_red[lane];
+    if (lane < SumShape<NP>::kSlices) a = s_red_p[lane];
     else acc_zero(a);
     acc_warp_reduce(a);
     return acc9_reduce(a);      // meaningful in lane 0
@@ -303,11 +316,10 @@ ZKSC_DEV void reduce_and_publish(Acc<NL> (&acc)[NP], const RoundBase& args, int 
     // last block of this proof: sum the per-block partials (canonical Montgomery elements)
     const Fr* all = args.partials + (size_t)group * gridDim.x * NP;
     __shared__ Acc<9> s_red[NP][kWarps];
-#pragma unroll 1
-    for (int p = 0; p < NP; p++) cta_sum_elems(all + p, NP, gridDim.x, s_red[p]);
+    cta_sum_points<NP>(all, 1, NP, gridDim.x, s_red);
     __syncthreads();
     for (int p = warp; p < NP; p += kWarps) {
-        const Fr v = warp_finish_sum(s_red[p]);
+        const Fr v = warp_finish_sum<NP>(s_red[p]);
         if (lane == 0 && point_of(p) < npts)
             st256_2x128(args.result + (size_t)proof * args.res_stride + (size_t)blockIdx.z * args.res_prod_stride + point_of(p), v);   // may be host-mapped
     }

@@ -149,21 +149,6 @@ ZKSC_DEV int res_wait_mail(const unsigned long long* mail, unsigned int seq, Fol
         }
     }
 }
-// Warp-level: wait until the relay tag speaks of round `seq`: 0 = its table is there, 1 = abort, 2 = time-out notice; 3 = the relaying CTA
-// went missing.
-ZKSC_DEV int res_wait_relay(const unsigned long long* tag, unsigned int seq) {
-    int st = 0;
-    if ((threadIdx.x & 31) == 0) {
-        const unsigned long long t0 = global_timer_ns();
-        for (unsigned int spins = 1;; spins++) {
-            const unsigned long long v = ld_acquire_gpu(tag);
-            if ((unsigned int)v == seq) { st = (int)(v >> 32); break; }
-            if ((spins & 0x3ff) == 0 && global_timer_ns() - t0 > 8 * kTailTimeoutNs) { st = 3; break; }
-        }
-    }
-    return __shfl_sync(0xffffffffu, st, 0);
-}
-
 // One lane: read an element published as 8 units; spins until all carry `seq`.  false on timeout.
 ZKSC_DEV bool res_read_elem(const unsigned long long* u, unsigned int seq, Fr& out) {
     const unsigned long long t0 = global_timer_ns();
@@ -319,9 +304,10 @@ ZKSC_DEV void res_rounds(const ResArgs& args, const volatile ResIds& ids, FoldTa
                     st = res_wait_mail(args.mail + (size_t)proof * kMailUnits, seq, s_tab, 8 * kTailTimeoutNs, rtag);
                     if (st == 2 && ld_acquire_gpu(rtag) != relay_tag(seq, 2u)) st = 3;     // the first CTA did not time out, yet no challenge came
                 } else {
-                    st = res_wait_relay(rtag, seq);
-                    __syncwarp();
-                    if (st == 0) st = res_wait_mail(runits, seq, s_tab, 8 * kTailTimeoutNs) == 0 ? 0 : 3;
+                    // the relayed units validate themselves, so the listeners poll them directly (one L2 round trip less than waiting
+                    // for the tag first); the tag is looked at now and then, for the first CTA's notice that it left
+                    st = res_wait_mail(runits, seq, s_tab, 8 * kTailTimeoutNs, rtag);
+                    if (st == 2 && ld_acquire_gpu(rtag) != relay_tag(seq, 2u)) st = 3;
                 }
                 if (lane == 0) s_state = st;
             }
@@ -457,11 +443,10 @@ ZKSC_DEV void res_rounds(const ResArgs& args, const volatile ResIds& ids, FoldTa
             ZKSC_TRACE(true, 4);           // last to arrive
             // ---- 4. the last CTA of the group to arrive: sum the partials (all threads, loads issued together)
             fence_acq_rel_gpu();
-#pragma unroll 1
-            for (int p = 0; p < NP; p++) cta_sum_elems(args.partials + ((size_t)group * kResMaxDegree + p) * args.cpg, 1, n_active, s_red[p]);
+            cta_sum_points<NP>(args.partials + (size_t)group * kResMaxDegree * args.cpg, args.cpg, 1, n_active, s_red);
             __syncthreads();
             for (int p = warp; p < NP; p += kResWarps) {
-                const Fr v = warp_finish_sum(s_red[p]);
+                const Fr v = warp_finish_sum<NP>(s_red[p]);
                 if (lane == 0) s_tot[p] = v;
             }
             if (threadIdx.x == 0) {
