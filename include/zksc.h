@@ -225,6 +225,31 @@ int zksc_gkr_prove(zksc_ctx* ctx, uint32_t n_layers, const uint32_t* n_gates, co
                    const uint32_t* gate_in1, const uint64_t* const* layer_values, const uint64_t* value_len, uint64_t* w0, uint64_t* sums,
                    uint64_t* wb_s, uint64_t* wc_s, uint64_t* round_msgs, uint32_t* round_len, uint64_t* challenges);
 
+/* ---- GKR on layered circuits of any widths, linear time (second reading of BASELINE config 4) ---------
+ * The same protocol (gkr/src/protocol.rs:21-113) and the same proof bytes as zksc_gkr_prove, without the dense 2^(2k)-entry layer
+ * tables: the k rounds of a layer sumcheck that bind b run on [W, H1 | H2, 1], the k rounds that bind c on
+ * [A, W(u) + W | W(u) M, W] -- tables of 2^k entries built from the gate lists (csrc/gkr_linear.cuh has the algebra) -- on one
+ * transcript.  The reference's Circuit can only hold the pyramid shape (layer i: 2^i gates, circuit/src/utils.rs:1-34); here layer
+ * i has 2^log_width[i] gates (log_width[0] may be 0: one output, padded to [out, 0] as protocol.rs:31-34 does) whose inputs are wire
+ * indices of layer i + 1; log_width[n_layers] is the input layer.  Gates of all layers concatenated, output layer first, in
+ * gate_type (0 = Add, 1 = Mul), gate_in0, gate_in1.
+ * zksc_circuit_create groups the gates by either input once (host) and keeps the circuit in HBM.
+ * zksc_circuit_evaluate = Circuit::evaluation (circuit/src/circuit.rs:32-55) on the device: inputs 2^log_width[n_layers] Montgomery
+ *   elements (host), outputs (optional) 2^log_width[0]; the layer values stay in HBM.  zksc_circuit_layer_values reads one layer back.
+ * zksc_gkr_prove_linear proves the latest evaluation.  Outputs as zksc_gkr_prove's: w0 (max(2, 2^log_width[0]) elements), per layer
+ *   sums, wb_s, wc_s, and the rounds of all layers concatenated -- layer i has 2 log_width[i + 1] rounds,
+ *   zksc_circuit_total_rounds in all -- as round_msgs (6 elements per round), round_len, challenges.
+ * Unsharded single-device contexts only. */
+typedef struct zksc_circuit zksc_circuit;
+int zksc_circuit_create(zksc_ctx* ctx, uint32_t n_layers, const uint32_t* log_width, const uint8_t* gate_type, const uint32_t* gate_in0,
+                        const uint32_t* gate_in1, zksc_circuit** out);
+int zksc_circuit_free(zksc_circuit* c);
+int zksc_circuit_evaluate(zksc_circuit* c, const uint64_t* inputs, uint64_t* outputs);
+int zksc_circuit_layer_values(zksc_circuit* c, uint32_t layer, uint64_t* out);
+uint64_t zksc_circuit_total_rounds(const zksc_circuit* c);
+int zksc_gkr_prove_linear(zksc_circuit* c, uint64_t* w0, uint64_t* sums, uint64_t* wb_s, uint64_t* wc_s, uint64_t* round_msgs, uint32_t* round_len,
+                          uint64_t* challenges);
+
 /* ---- stand-alone Multilinear operations on caller-owned host vectors (device compute) -----------
  * Each copies its inputs to the device, runs the CUDA kernel and copies the result back. */
 /* Multilinear::partial_evaluation(r, variable_index)  evaluation_form.rs:123-141; n = 2^k entries in, n/2 out */

@@ -276,6 +276,77 @@ class GKRProtocol:               # gkr/src/protocol.rs:17-195
         return claimed == (alpha * w_in.evaluation(r_b) + beta * w_in.evaluation(r_c)) % R     # :183-192
 
 
+# ---- layered circuits of any power-of-two widths (the product's zksc_gkr_prove_linear; BASELINE config 4 as written) ------------
+# The reference's Circuit can only hold the pyramid (layer i: 2^i gates).  The protocol itself does not care: the label widths
+# follow from the layers.  `prove_layered` is GKRProtocol::prove with DENSE width^2 layer tables (the reference's form) on a
+# circuit given as per-layer gate lists; on a pyramid it is prove_sparse, byte for byte (tests/test_oracle_gkr_layered.py).
+class LayeredCircuit:
+    def __init__(self, log_width, layers):
+        """log_width[i] = log2(gates of layer i), [-1] = log2(inputs); layers[i] = list of (type 0/1, in0, in1)"""
+        self.log_width, self.layers = list(log_width), [list(l) for l in layers]
+        for i, l in enumerate(self.layers):
+            assert len(l) == 1 << self.log_width[i]
+            assert all(t in (0, 1) and 0 <= a < (1 << self.log_width[i + 1]) and 0 <= b < (1 << self.log_width[i + 1]) for t, a, b in l)
+
+    @staticmethod
+    def from_circuit(circuit):
+        return LayeredCircuit(list(range(len(circuit.layers) + 1)),
+                              [[(0 if g.gate_type == ADD else 1, g.inputs[0], g.inputs[1]) for g in layer.layer] for layer in circuit.layers])
+
+    def evaluation(self, inp):      # circuit/src/circuit.rs:32-55
+        layers = [[int(v) % R for v in inp]]
+        for l in reversed(self.layers):
+            cur = layers[0]
+            layers.insert(0, [(cur[a] * cur[b]) % R if t else (cur[a] + cur[b]) % R for t, a, b in l])
+        return layers
+
+
+def _layered_wiring(lc, li, points_and_scales):
+    """{(b, c) index: value} of alpha add(r_b, b, c) + beta add(r_c, b, c), and of mul"""
+    bits = lc.log_width[li + 1]
+    wgt = None
+    for r, scale in points_and_scales:
+        e = [x * scale % R for x in eq_vector(r)]
+        wgt = e if wgt is None else [(x + y) % R for x, y in zip(wgt, e)]
+    assert len(wgt) >= len(lc.layers[li])
+    add, mul = {}, {}
+    for gi, (t, a, b) in enumerate(lc.layers[li]):
+        d = (a << bits) | b
+        tgt = mul if t else add
+        tgt[d] = (tgt.get(d, 0) + wgt[gi]) % R
+    return add, mul
+
+
+def prove_layered(lc, evaluation, layer_prover=_python_layer_prover, evaluate=None):
+    """GKRProtocol::prove (gkr/src/protocol.rs:21-113) on a LayeredCircuit, dense layer tables of width^2 entries"""
+    evaluate = evaluate or (lambda w, pts: pm.Multilinear(w).evaluation(pts))
+    t = pm.FiatShamirTranscript()
+    proofs, wb_s, wc_s = [], [], []
+    w0 = [int(v) % R for v in evaluation[0]]
+    w_0 = pm.Multilinear(w0 + [0] if len(w0) == 1 else w0)                          # protocol.rs:31-34
+    t.commit(w_0.to_bytes())
+    r_b = t.evaluate_n_challenge_into_field(w_0.n_vars)
+    claimed = w_0.evaluation(r_b)
+    points = [(r_b, 1)]
+    for li in range(len(lc.layers)):
+        w = [int(v) % R for v in evaluation[li + 1]]
+        n = len(w) * len(w)
+        add, mul = _layered_wiring(lc, li, points)
+        tables = [_dense(add, n), [(x + y) % R for x in w for y in w], _dense(mul, n), [x * y % R for x in w for y in w]]
+        proof, ch = layer_prover(tables, claimed)
+        t.commit(proof.to_bytes())
+        proofs.append(proof)
+        b, c = ch[:len(ch) // 2], ch[len(ch) // 2:]
+        wb, wc = evaluate(w, b), evaluate(w, c)
+        wb_s.append(wb); wc_s.append(wc)
+        alpha, beta = t.evaluate_challenge_into_field(), t.evaluate_challenge_into_field()
+        claimed = (alpha * wb + beta * wc) % R
+        points = [(b, alpha), (c, beta)]
+    out = GKRProof(proofs, wb_s, wc_s, w_0)
+    out.last_b, out.last_c = b, c
+    return out
+
+
 class SuccintGKRProof:           # gkr/src/succint_protocol.rs:21-29
     def __init__(self, gkr, proof_wb_opening, proof_wc_opening):
         self.sumcheck_proofs, self.wb_s, self.wc_s, self.w_0_mle = gkr.sumcheck_proofs, gkr.wb_s, gkr.wc_s, gkr.w_0_mle

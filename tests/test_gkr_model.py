@@ -64,3 +64,31 @@ def test_closed_form_prover_through_the_c_oracle():
     a = g.GKRProtocol.prove_sparse(c, ev)
     b = g.GKRProtocol.prove_sparse(c, ev, layer_prover=g.c_layer_prover, evaluate=g.c_evaluate)
     assert a.to_bytes() == b.to_bytes()
+
+
+# ---- layered circuits of any widths (oracle side of zksc_gkr_prove_linear) -------------------------------------------------------
+def _random_layered(log_width, seed):
+    import random
+    rng = random.Random(seed)
+    return g.LayeredCircuit(log_width, [[(rng.randrange(2), rng.randrange(1 << log_width[i + 1]), rng.randrange(1 << log_width[i + 1]))
+                                         for _ in range(1 << log_width[i])] for i in range(len(log_width) - 1)])
+
+
+def test_layered_prover_is_the_reference_prover_on_pyramids():
+    """prove_layered (label widths taken from the layers) == the literal restatement of GKRProtocol::prove on the reference's own
+    circuits and on Circuit::random -- the anchor for the widths the reference cannot hold"""
+    for c, inp in (circuit_1(), circuit_2(), (g.Circuit.random(4), [(7 * i + 3) % R for i in range(16)])):
+        ev = c.evaluation(inp)
+        lc = g.LayeredCircuit.from_circuit(c)
+        assert lc.evaluation(inp) == ev
+        assert g.prove_layered(lc, ev).to_bytes() == g.GKRProtocol.prove(c, ev).to_bytes()
+
+
+def test_layered_prover_python_and_c_layer_provers_agree():
+    lc = _random_layered([2, 3, 3, 4], 5)
+    inp = [(0x9E3779B97F4A7C15 * (i + 1)) % R for i in range(16)]
+    ev = lc.evaluation(inp)
+    assert [len(l) for l in ev] == [4, 8, 8, 16]
+    a = g.prove_layered(lc, ev)
+    b = g.prove_layered(lc, ev, layer_prover=g.c_layer_prover, evaluate=g.c_evaluate)
+    assert a.to_bytes() == b.to_bytes() and a.wb_s == b.wb_s and a.wc_s == b.wc_s

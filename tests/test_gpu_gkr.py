@@ -120,3 +120,94 @@ def test_gkr_c_driver_shape_errors():
     two_out = zk.Circuit([zk.CircuitLayer([zk.Gate(zk.GateType.Add, [0, 1]), zk.Gate(zk.GateType.Mul, [0, 1])])])
     with pytest.raises(zk.ZkscError):
         zk.GKRProtocol.prove(two_out, [[3, 2], [1, 2]])   # two output gates: w_0 would have 3 entries
+
+
+# ---- layered circuits of any widths, linear-time prover (zksc_gkr_prove_linear; BASELINE config 4 as written) ---------------------
+def _olayered(lc):
+    return g.LayeredCircuit(lc.log_width, [[(int(t), int(a), int(b)) for t, a, b in zip(*layer)] for layer in lc.layers()])
+
+
+@pytest.mark.parametrize("layers,inp", [(CIRCUIT_1, [2, 3, 4, 5]), (CIRCUIT_2, [2, 1, 3, 1, 4, 1, 2, 2, 3, 3, 4, 4, 2, 3, 3, 4])])
+def test_linear_prover_reference_cases(layers, inp):
+    """on the reference's own circuits the linear-time prover gives the bytes of GKRProtocol::prove (oracle, literal restatement) and of
+    the dense device prover, and GKRProtocol::verify accepts them (gkr/src/protocol.rs:209-285)"""
+    zc, oc = both(layers)
+    lc = zk.LayeredCircuit.from_circuit(zc)
+    ev = oc.evaluation(inp)
+    assert lc.evaluate(inp) == ev[0]
+    assert [lc.layer_values(i) for i in range(len(ev))] == ev
+    proof = lc.prove()
+    want = g.GKRProtocol.prove(oc, ev)
+    assert proof.to_bytes() == want.to_bytes()
+    assert proof.wb_s == want.wb_s and proof.wc_s == want.wc_s
+    assert proof.to_bytes() == zk.GKRProtocol.prove(zc, ev).to_bytes()
+    assert zk.GKRProtocol.verify(zc, inp, proof) and lc.verify(inp, proof)
+    proof.wb_s[-1] = (proof.wb_s[-1] + 1) % R
+    assert not lc.verify(inp, proof)
+
+
+@pytest.mark.parametrize("depth", [5, 9])
+def test_linear_prover_random_pyramid_vs_dense_device_prover(depth):
+    """Circuit::random(depth): linear-time prover == dense device prover == oracle (C layer sumchecks), byte for byte"""
+    zc, oc = zk.Circuit.random(depth), g.Circuit.random(depth)
+    inp = [(0x9E3779B97F4A7C15 * (i + 1)) % R for i in range(1 << depth)]
+    lc = zk.LayeredCircuit.from_circuit(zc)
+    lc.evaluate(inp)
+    ev = zc.evaluation(inp)
+    proof = lc.prove()
+    assert proof.to_bytes() == zk.GKRProtocol.prove(zc, ev).to_bytes()
+    if depth <= 8:
+        assert proof.to_bytes() == g.GKRProtocol.prove_sparse(oc, ev, layer_prover=g.c_layer_prover, evaluate=g.c_evaluate).to_bytes()
+    assert zk.GKRProtocol.verify(zc, inp, proof)
+
+
+@pytest.mark.parametrize("log_width,seed", [([3, 3, 3], 1), ([0, 4, 4, 4], 2), ([2, 5, 3, 6], 3), ([6, 6, 6, 6, 6], 4), ([4, 8, 8], 5), ([1, 1, 1], 6)])
+def test_linear_prover_uniform_and_ragged_widths_vs_dense_oracle(log_width, seed):
+    """widths the reference's Circuit cannot hold: against the oracle's DENSE prover (width^2-entry layer tables through the C oracle)"""
+    lc = zk.LayeredCircuit.random(log_width, seed)
+    oc = _olayered(lc)
+    inp = [(0xD1B54A32D192ED03 * (i + 1) + seed) % R for i in range(1 << log_width[-1])]
+    ev = oc.evaluation(inp)
+    assert lc.evaluate(inp) == ev[0]
+    proof = lc.prove()
+    want = g.prove_layered(oc, ev, layer_prover=g.c_layer_prover, evaluate=g.c_evaluate)
+    assert proof.to_bytes() == want.to_bytes()
+    assert proof.wb_s == want.wb_s and proof.wc_s == want.wc_s
+    assert lc.verify(inp, proof)
+    proof.sumcheck_proofs[0].round_polys[0].monomial[0] = ((proof.sumcheck_proofs[0].round_polys[0].monomial[0][0] + 1) % R, proof.sumcheck_proofs[0].round_polys[0].monomial[0][1])
+    assert not lc.verify(inp, proof)
+
+
+def test_linear_prover_special_inputs_and_repeated_proofs():
+    """all-zero and all-one inputs (every round polynomial drops monomials), one circuit proved twice with different inputs"""
+    lc = zk.LayeredCircuit.random([3, 4, 4], 9)
+    oc = _olayered(lc)
+    for inp in ([0] * 16, [1] * 16, list(range(16))):
+        ev = oc.evaluation(inp)
+        lc.evaluate(inp)
+        proof = lc.prove()
+        assert proof.to_bytes() == g.prove_layered(oc, ev, layer_prover=g.c_layer_prover, evaluate=g.c_evaluate).to_bytes()
+        assert lc.verify(inp, proof)
+
+
+def test_linear_prover_width_2_16_verifies():
+    """width 2^16 x 3 layers (the dense form would need 2^32-entry tables): the proof must pass the verifier"""
+    lc = zk.LayeredCircuit.random([16, 16, 16, 16], 11)
+    inp = [(0x9E3779B97F4A7C15 * (i + 1)) % R for i in range(1 << 16)]
+    lc.evaluate(inp)
+    proof = lc.prove()
+    assert lc.verify(inp, proof)
+
+
+def test_linear_prover_shape_errors():
+    with pytest.raises(zk.ZkscError):
+        zk.LayeredCircuit([1, 1], [0, 0], [0, 2], [0, 0])          # input label out of range
+    with pytest.raises(zk.ZkscError):
+        zk.LayeredCircuit([1, 1], [0, 2], [0, 1], [0, 0])          # unknown gate type
+    with pytest.raises(zk.ZkscError):
+        zk.LayeredCircuit([1, 1], [0], [0], [0])                   # 2^1 gates announced, one given
+    lc = zk.LayeredCircuit([1, 1], [0, 1], [0, 1], [1, 0])
+    with pytest.raises(zk.ZkscError):
+        lc.prove()                                                 # nothing evaluated yet
+    with pytest.raises(zk.ZkscError):
+        lc.evaluate([1, 2, 3])                                     # wrong input length

@@ -20,6 +20,7 @@
 #include <cstdlib>
 #include <chrono>
 #include <cstring>
+#include <map>
 #include <string>
 #include <utility>
 #include <vector>
@@ -2181,32 +2182,14 @@ extern "C" uint32_t zksc_msg_stride(int protocol, uint32_t n_products, const uin
     return 2 * (dmax + 1);
 }
 
-extern "C" int zksc_prove(zksc_tables* t, int protocol, const uint64_t* sums, uint64_t* round_msgs, uint32_t* round_len, uint64_t* challenges) {
-    if (!t || !round_msgs || !round_len || !challenges) return ZKSC_ERR_STATE;
+// The round loop of the three provers (multi_composed_sumcheck.rs:75-107, sumcheck.rs:38-57, composed_sumcheck.rs:44-63) over ALL variables of
+// the handle, on transcripts the caller has prepared.  The messages and challenges of round j of the handle go to slot round0 + j of a proof
+// of n rounds in total: a sumcheck whose tables change form half-way (gkr_linear.cuh) is two such runs on one transcript.
+static int prove_run(zksc_tables* t, int protocol, std::vector<host::FiatShamirTranscript>& tr, uint32_t n, uint32_t round0, uint32_t stride,
+                     uint64_t* round_msgs, uint32_t* round_len, uint64_t* challenges) {
     zksc_ctx* ctx = t->ctx;
-    if (protocol < ZKSC_PROTO_SUMCHECK || protocol > ZKSC_PROTO_MULTI_FULL) FAIL(ZKSC_ERR_SHAPE, "unknown protocol");
-    if (protocol == ZKSC_PROTO_SUMCHECK && (t->P != 1 || t->deg[0] != 1)) FAIL(ZKSC_ERR_SHAPE, "Sumcheck::prove takes one multilinear table");
-    if (protocol == ZKSC_PROTO_COMPOSED && t->P != 1) FAIL(ZKSC_ERR_SHAPE, "ComposedSumcheck::prove takes one product");
-    if (protocol != ZKSC_PROTO_COMPOSED && !sums) FAIL(ZKSC_ERR_SHAPE, "sums is NULL");
-    if (t->vars_left != t->n_vars || t->pending) FAIL(ZKSC_ERR_STATE, "tables are partially bound; call zksc_tables_reset first");
-    const uint32_t stride = zksc_msg_stride(protocol, t->P, t->deg);
-    const uint32_t B = t->B, n = t->n_vars;
-    GpuPoolSession gpu_session(t->kids.empty() ? nullptr : ctx);
-    std::vector<host::FiatShamirTranscript> tr(B);
-    if (protocol == ZKSC_PROTO_MULTI_FULL) {
-        // transcript.commit(&composed_poly_to_bytes(&poly))  multi_composed_sumcheck.rs:52
-        if (ctx->n_ranks != 1) FAIL(ZKSC_ERR_UNSUPPORTED, "MULTI_FULL (absorbs every table entry) is single-rank only; use MULTI_PARTIAL");
-        std::vector<uint8_t> bytes((size_t)t->Dtot * t->n_local0 * 32);
-        for (uint32_t b = 0; b < B; b++) {
-            TRY(zksc_tables_to_bytes(t, b, bytes.data()));
-            tr[b].commit(bytes);
-        }
-    }
-    if (protocol != ZKSC_PROTO_COMPOSED)
-        for (uint32_t b = 0; b < B; b++) tr[b].commit_field(load_h(sums + 4 * b));  // :70 / sumcheck.rs:34-35
-
+    const uint32_t B = t->B;
     std::vector<uint64_t> ev((size_t)B * t->E * 4), chal((size_t)B * 4);
-    memset(round_msgs, 0, (size_t)B * n * stride * 32);
     // many independent proofs per round: their transcripts go to a few host threads (they spin only during this call)
     if (B >= kPoolMinProofs && !ctx->pool) {
         const char* e = getenv("ZKSC_HOST_THREADS");
@@ -2218,8 +2201,7 @@ extern "C" int zksc_prove(zksc_tables* t, int protocol, const uint64_t* sums, ui
         explicit PoolSession(zksc_ctx* ctx, bool on) : c(on ? ctx : nullptr) { if (c) { c->pool->begin(); c->pool_active = true; } }
         ~PoolSession() { if (c) { c->pool_active = false; c->pool->end(); } }
     } pool_session(ctx, ctx->pool != nullptr && B >= kPoolMinProofs);
-    ctx->round_us.assign(n, 0.0);
-    for (uint32_t round = 0; round < n; round++) {
+    for (uint32_t round = round0; round < round0 + t->n_vars; round++) {
         const auto p0 = std::chrono::steady_clock::now();
         TRY(round_evals_impl(t, ev.data(), ZKSC_MAX_DEGREE + 1));
         const auto p1 = std::chrono::steady_clock::now();
@@ -2260,7 +2242,7 @@ extern "C" int zksc_prove(zksc_tables* t, int protocol, const uint64_t* sums, ui
         const auto p2 = std::chrono::steady_clock::now();
         TRY(zksc_bind(t, chal.data()));                               // :103-105 (deferred, fused)
         const auto p3 = std::chrono::steady_clock::now();
-        ctx->round_us[round] = std::chrono::duration<double, std::micro>(p3 - p0).count();
+        if (round < ctx->round_us.size()) ctx->round_us[round] = std::chrono::duration<double, std::micro>(p3 - p0).count();
         if (ctx->profile) {
             auto us = [](auto a, auto b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
             fprintf(stderr, "[zksc profile] round %2u: evals %7.1f us (launch %6.1f, wait %7.1f)  transcript %5.1f  bind %5.1f\n", round, us(p0, p1),
@@ -2268,6 +2250,35 @@ extern "C" int zksc_prove(zksc_tables* t, int protocol, const uint64_t* sums, ui
         }
     }
     return ZKSC_OK;
+}
+
+extern "C" int zksc_prove(zksc_tables* t, int protocol, const uint64_t* sums, uint64_t* round_msgs, uint32_t* round_len, uint64_t* challenges) {
+    if (!t || !round_msgs || !round_len || !challenges) return ZKSC_ERR_STATE;
+    zksc_ctx* ctx = t->ctx;
+    if (protocol < ZKSC_PROTO_SUMCHECK || protocol > ZKSC_PROTO_MULTI_FULL) FAIL(ZKSC_ERR_SHAPE, "unknown protocol");
+    if (protocol == ZKSC_PROTO_SUMCHECK && (t->P != 1 || t->deg[0] != 1)) FAIL(ZKSC_ERR_SHAPE, "Sumcheck::prove takes one multilinear table");
+    if (protocol == ZKSC_PROTO_COMPOSED && t->P != 1) FAIL(ZKSC_ERR_SHAPE, "ComposedSumcheck::prove takes one product");
+    if (protocol != ZKSC_PROTO_COMPOSED && !sums) FAIL(ZKSC_ERR_SHAPE, "sums is NULL");
+    if (t->vars_left != t->n_vars || t->pending) FAIL(ZKSC_ERR_STATE, "tables are partially bound; call zksc_tables_reset first");
+    const uint32_t stride = zksc_msg_stride(protocol, t->P, t->deg);
+    const uint32_t B = t->B, n = t->n_vars;
+    GpuPoolSession gpu_session(t->kids.empty() ? nullptr : ctx);
+    std::vector<host::FiatShamirTranscript> tr(B);
+    if (protocol == ZKSC_PROTO_MULTI_FULL) {
+        // transcript.commit(&composed_poly_to_bytes(&poly))  multi_composed_sumcheck.rs:52
+        if (ctx->n_ranks != 1) FAIL(ZKSC_ERR_UNSUPPORTED, "MULTI_FULL (absorbs every table entry) is single-rank only; use MULTI_PARTIAL");
+        std::vector<uint8_t> bytes((size_t)t->Dtot * t->n_local0 * 32);
+        for (uint32_t b = 0; b < B; b++) {
+            TRY(zksc_tables_to_bytes(t, b, bytes.data()));
+            tr[b].commit(bytes);
+        }
+    }
+    if (protocol != ZKSC_PROTO_COMPOSED)
+        for (uint32_t b = 0; b < B; b++) tr[b].commit_field(load_h(sums + 4 * b));  // :70 / sumcheck.rs:34-35
+
+    memset(round_msgs, 0, (size_t)B * n * stride * 32);
+    ctx->round_us.assign(n, 0.0);
+    return prove_run(t, protocol, tr, n, 0, stride, round_msgs, round_len, challenges);
 }
 
 extern "C" int zksc_proof_to_bytes(int protocol, uint32_t n_vars, uint32_t msg_stride, const uint64_t* round_msgs, const uint32_t* round_len,
@@ -2576,6 +2587,7 @@ extern "C" int zksc_kzg_open(zksc_ctx* ctx, const uint64_t* evals, uint32_t n_va
 // GKR layer driver
 // ------------------------------------------------------------------------------------------------
 #include "gkr_driver.cuh"
+#include "gkr_linear.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // host helpers

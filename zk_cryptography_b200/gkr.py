@@ -18,6 +18,8 @@ prover's table handle:
 The Fiat-Shamir transcripts (outer GKR transcript and the per-layer sumcheck transcripts) stay on the host.
 There is no CPU fallback for the table-sized work.
 """
+import ctypes
+
 import numpy as np
 
 from . import _lib
@@ -293,6 +295,179 @@ class GKRProtocol:               # gkr/src/protocol.rs:17-195
             claimed = (alpha * wb + beta * wc) % R
         w_in = Multilinear([int(v) % R for v in inp])
         return claimed == (alpha * w_in.evaluation(r_b) + beta * w_in.evaluation(r_c)) % R     # :183-192
+
+
+class LayeredCircuit:
+    """A layered add/mul circuit whose layers have ANY power-of-two widths, resident on the device, proved in time linear in its gates
+    (zksc_circuit_* / zksc_gkr_prove_linear, csrc/gkr_linear.cuh): BASELINE config 4 read literally ("width 2^20, depth 8").  The
+    reference's `Circuit` holds only the pyramid shape (layer i: 2^i gates); on such circuits this prover gives the bytes of
+    GKRProtocol::prove (gkr/src/protocol.rs:21-113), and its proofs are checked by `verify` below, GKRProtocol::verify (:115-195) with
+    the label widths taken from the layers.
+
+    log_width[i] = log2(gates of layer i), output layer first, log_width[-1] = log2(inputs); gate arrays of all layers concatenated:
+    gtype (0 = Add, 1 = Mul), in0, in1 (wire indices of the layer below)."""
+
+    def __init__(self, log_width, gtype, in0, in1, ctx=None):
+        self.ctx = ctx or default_context()
+        self.log_width = [int(x) for x in log_width]
+        self.n_layers = len(self.log_width) - 1
+        self.gtype = np.ascontiguousarray(gtype, dtype=np.uint8)
+        self.in0 = np.ascontiguousarray(in0, dtype=np.uint32)
+        self.in1 = np.ascontiguousarray(in1, dtype=np.uint32)
+        n_gates = sum(1 << w for w in self.log_width[:-1])
+        if not (len(self.gtype) == len(self.in0) == len(self.in1) == n_gates):
+            raise ZkscError(-3, "gate arrays must hold 2^log_width[i] gates per layer")
+        lw = np.asarray(self.log_width, dtype=np.uint32)
+        h = ctypes.c_void_p()
+        self.ctx.check(_lib.lib().zksc_circuit_create(self.ctx._h, self.n_layers, _lib.p32(lw), _lib.p8(self.gtype), _lib.p32(self.in0), _lib.p32(self.in1),
+                                                      ctypes.byref(h)))
+        self._h = h
+        self.rounds = int(_lib.lib().zksc_circuit_total_rounds(self._h))
+
+    @classmethod
+    def from_circuit(cls, circuit, ctx=None):
+        """the reference's pyramid `Circuit` (layer i: 2^i gates) in this form"""
+        L = len(circuit.layers)
+        gt, a, b = [], [], []
+        for i, layer in enumerate(circuit.layers):
+            if len(layer.layer) != 1 << i:
+                raise ZkscError(-3, "layer %d must have 2^%d gates" % (i, i))
+            for g in layer.layer:
+                gt.append(0 if g.gate_type == GateType.Add else 1); a.append(g.inputs[0]); b.append(g.inputs[1])
+        return cls(list(range(L + 1)), gt, a, b, ctx)
+
+    @classmethod
+    def random(cls, log_width, seed=0, ctx=None):
+        """every gate of layer i: a uniformly random type and two uniformly random wires of layer i + 1"""
+        rng = np.random.default_rng(seed)
+        gt, a, b = [], [], []
+        for i in range(len(log_width) - 1):
+            n, m = 1 << log_width[i], 1 << log_width[i + 1]
+            gt.append(rng.integers(0, 2, n, dtype=np.uint8)); a.append(rng.integers(0, m, n, dtype=np.uint32)); b.append(rng.integers(0, m, n, dtype=np.uint32))
+        return cls(log_width, np.concatenate(gt), np.concatenate(a), np.concatenate(b), ctx)
+
+    def layers(self):
+        """-> per layer (gtype, in0, in1) array views"""
+        out, off = [], 0
+        for w in self.log_width[:-1]:
+            n = 1 << w
+            out.append((self.gtype[off:off + n], self.in0[off:off + n], self.in1[off:off + n]))
+            off += n
+        return out
+
+    def evaluate(self, inputs, mont=False):
+        """Circuit::evaluation (circuit/src/circuit.rs:32-55) on the device; -> the outputs (ints); the layer values stay in HBM"""
+        x = np.ascontiguousarray(inputs, dtype=np.uint64) if mont else to_mont([int(v) % R for v in inputs])
+        if x.shape != (1 << self.log_width[-1], 4):
+            raise ZkscError(-3, "the input layer has 2^%d values" % self.log_width[-1])
+        out = np.zeros((1 << self.log_width[0], 4), dtype=np.uint64)
+        self.ctx.check(_lib.lib().zksc_circuit_evaluate(self._h, _lib.p64(x), _lib.p64(out)))
+        return from_mont(out)
+
+    def layer_values(self, layer):
+        out = np.zeros((1 << self.log_width[layer], 4), dtype=np.uint64)
+        self.ctx.check(_lib.lib().zksc_circuit_layer_values(self._h, layer, _lib.p64(out)))
+        return from_mont(out)
+
+    def prove_raw(self):
+        L, rounds = self.n_layers, self.rounds
+        out = dict(w0=np.zeros((max(2, 1 << self.log_width[0]), 4), dtype=np.uint64), sums=np.zeros((L, 4), dtype=np.uint64),
+                   wb=np.zeros((L, 4), dtype=np.uint64), wc=np.zeros((L, 4), dtype=np.uint64), msgs=np.zeros((rounds, 6, 4), dtype=np.uint64),
+                   lens=np.zeros(rounds, dtype=np.uint32), chal=np.zeros((rounds, 4), dtype=np.uint64))
+        self.ctx.check(_lib.lib().zksc_gkr_prove_linear(self._h, _lib.p64(out["w0"]), _lib.p64(out["sums"]), _lib.p64(out["wb"]), _lib.p64(out["wc"]),
+                                                        _lib.p64(out["msgs"]), _lib.p32(out["lens"]), _lib.p64(out["chal"])))
+        return out
+
+    def prove(self):
+        """GKRProtocol::prove of the latest `evaluate` -> GKRProof (same classes as the dense prover's)"""
+        raw = self.prove_raw()
+        msgs, lens = raw["msgs"], raw["lens"]
+        proofs, off = [], 0
+        sums_i, all_ints = from_mont(raw["sums"]), from_mont(msgs.reshape(-1, 4))
+        for li in range(self.n_layers):
+            n = 2 * self.log_width[li + 1]
+            rps = []
+            for r in range(off, off + n):
+                m = int(lens[r])
+                v = all_ints[r * 6:r * 6 + 2 * m]
+                rps.append(SparseUnivariatePolynomial([(v[2 * i], v[2 * i + 1]) for i in range(m)]))
+            proofs.append(MultiComposedProof(rps, sums_i[li]))
+            off += n
+        proof = GKRProof(proofs, from_mont(raw["wb"]), from_mont(raw["wc"]), Multilinear(raw["w0"]))
+        proof.challenges = from_mont(raw["chal"])
+        return proof
+
+    def wiring_at(self, layer, points_and_scales, b, c):
+        """(add~, mul~)(b, c) = sum over the layer's gates g of [sum_j scale_j eq(r_j, g)] eq(b, in0 g) eq(c, in1 g), on the host
+        (what Multilinear::evaluation of the wiring tables gives, gkr/src/protocol.rs:131-133, 164-171)"""
+        gt, i0, i1 = self.layers()[layer]
+        wgt = None
+        for r, scale in points_and_scales:
+            e = [x * scale % R for x in _eq_vector(r)]
+            wgt = e if wgt is None else [(x + y) % R for x, y in zip(wgt, e)]
+        eb, ec = _eq_vector(b), _eq_vector(c)
+        add = mul = 0
+        for g in range(len(gt)):
+            t = wgt[g] * eb[int(i0[g])] % R * ec[int(i1[g])] % R
+            if gt[g]:
+                mul = (mul + t) % R
+            else:
+                add = (add + t) % R
+        return add, mul
+
+    def verify(self, inputs, proof):
+        """GKRProtocol::verify (gkr/src/protocol.rs:115-195) for this circuit; host side (Python integers: small circuits)"""
+        if len(proof.sumcheck_proofs) != self.n_layers or len(proof.wb_s) != self.n_layers or len(proof.wc_s) != self.n_layers:
+            return False
+        transcript = FiatShamirTranscript()
+        transcript.commit(b"".join(int(e).to_bytes(32, "big") for e in proof.w_0_mle.to_ints()))
+        r_b = transcript.evaluate_n_challenge_into_field(proof.w_0_mle.n_vars)
+        claimed = proof.w_0_mle.evaluation(r_b)
+        points = [(r_b, 1)]
+        alpha = beta = r_c = None
+        for i, p in enumerate(proof.sumcheck_proofs):
+            if claimed != p.sum:
+                return False
+            transcript.commit(p.to_bytes())
+            try:
+                sub = MultiComposedSumcheckVerifier.verify_partial(p)
+            except ZkscError as e:
+                if e.code == -7:
+                    return False
+                raise
+            ch = sub.challenges
+            if len(ch) != 2 * self.log_width[i + 1]:
+                return False
+            b, c = ch[:len(ch) // 2], ch[len(ch) // 2:]
+            wb, wc = proof.wb_s[i], proof.wc_s[i]
+            add, mul = self.wiring_at(i, points, b, c)
+            if (add * ((wb + wc) % R) + mul * (wb * wc % R)) % R != sub.sum:
+                return False
+            alpha, beta = transcript.evaluate_challenge_into_field(), transcript.evaluate_challenge_into_field()
+            claimed = (alpha * wb + beta * wc) % R
+            r_b, r_c = b, c
+            points = [(r_b, alpha), (r_c, beta)]
+        w_in = Multilinear([int(v) % R for v in inputs])
+        return claimed == (alpha * w_in.evaluation(r_b) + beta * w_in.evaluation(r_c)) % R
+
+    def close(self):
+        if getattr(self, "_h", None) and self.ctx._h:
+            _lib.lib().zksc_circuit_free(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _eq_vector(r):
+    """eq(r, a), a's most significant bit paired with r[0] (successive variable-0 folds, evaluation_form.rs:143-159)"""
+    v = [1]
+    for x in r:
+        v = [e * f % R for e in v for f in ((1 - x) % R, x % R)]
+    return v
 
 
 class SuccintGKRProof:           # gkr/src/succint_protocol.rs:21-29
