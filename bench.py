@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- sumcheck prover throughput (hypercube evals/s) on N B200s, or the CPU reference arm.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c1|c4|c5] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c1|c4|c4b|c5] [--impl b200|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 One step = what the reference's `multi_composed_sumcheck_with_prove_partial_benchmark` times
@@ -13,6 +13,7 @@ on synthetic seeded tables.  Workloads (BASELINE.json configs):
     c1            Sumcheck::prove on one 2^20-entry multilinear (replicated on every GPU)
     c5            64 independent degree-2 proofs of 2^22 entries, 64/N per GPU (replicas, batched launches)
     c4            GKRProtocol::prove on Circuit::random(10): 10 layer sumchecks (largest 2^20 entries) with device-built tables
+    c4b           GKRProtocol::prove on a uniform-width layered circuit, width 2^20, depth 8 (linear-time two-phase layer sumchecks)
 `value`   : tables resident in HBM when the clock starts (generated on the device).
 `e2e`     : the same step through the public API with HOST tables: pinned host -> device copy of every
             table and device -> host copy of the proof inside the timed region.
@@ -46,6 +47,10 @@ WORKLOADS = {
     "c4": dict(n=20, degs=[2, 2], proto="gkr", proofs=1, scaling="replicas", depth=10,
                desc="GKRProtocol::prove on Circuit::random(10) (the reference's circuit shape: 2^10 inputs, 10 layer sumchecks of 2^2..2^20 entries, "
                     "P=2, d=(2,2); layer tables built on the device), replicated on every GPU"),
+    "c4b": dict(n=20, degs=[2, 2], proto="gkr_linear", proofs=1, scaling="replicas", depth=8, log_width=20,
+                desc="GKRProtocol::prove on a random layered add/mul circuit of UNIFORM width 2^20, depth 8 (BASELINE config 4 as written; the reference's "
+                     "Circuit cannot hold it and its prover would need 2^40-entry layer tables): linear-time two-phase layer sumchecks on 2^20-entry "
+                     "tables built from the gate lists (zksc_gkr_prove_linear), replicated on every GPU"),
     "c5": dict(n=22, degs=[2], proto="multi_partial", proofs=64, scaling="strong",
                desc="64 independent prove_partial (degree-2 product, 2^22 entries each), 64/N proofs per GPU, batched launches"),
     "c5s": dict(n=22, degs=[2], proto="multi_partial", proofs=64, scaling="strong", shard_batch=True,
@@ -307,6 +312,8 @@ def run_b200(args):
     wl = dict(WORKLOADS[args.workload])
     if wl["proto"] == "gkr":
         return run_gkr(args, wl, world, rank, local_rank, dist)
+    if wl["proto"] == "gkr_linear":
+        return run_gkr_linear(args, wl, world, rank, local_rank, dist)
     G = world
     lgG = int(math.log2(G))
     ctx = zk.Context(local_rank)
@@ -654,6 +661,180 @@ def run_gkr(args, wl, world, rank, local_rank, dist):
         dist.destroy_process_group()
 
 
+def layered_inputs(log_width):
+    R = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+    return [(0xD1B54A32D192ED03 * (i + 1) + SEED) % R for i in range(1 << log_width)]
+
+
+def layered_units(log_width, depth):
+    """hypercube points the linear-time prover evaluates: two phases of 2^k table entries per layer"""
+    return depth * 2 * (1 << log_width)
+
+
+def oracle_layered(lc):
+    from oracle import gkrmodel as g
+    return g.LayeredCircuit(lc.log_width, [[(int(t), int(a), int(b)) for t, a, b in zip(*layer)] for layer in lc.layers()])
+
+
+def run_gkr_linear(args, wl, world, rank, local_rank, dist):
+    """c4b: one step = GKRProtocol::prove of a uniform-width layered circuit (zksc_gkr_prove_linear) on layer values resident in HBM
+    (`value`); `e2e` = Circuit::evaluation from host inputs (zksc_circuit_evaluate: upload + one launch per layer) + the proof,
+    host wall clock.  Parity: the same circuit family at width 2^10 against the oracle's DENSE prover (2^20-entry layer tables
+    through oracle/zkref.c), byte for byte, and GKRProtocol::verify on a width-2^14 instance (`--verify-full`: on the timed one)."""
+    import hashlib
+
+    import numpy as np
+    import torch
+
+    import zk_cryptography_b200 as zk
+    lw, depth = wl["log_width"], wl["depth"]
+    ctx = zk.Context(local_rank)
+    zk.set_default_context(ctx)
+    lc = zk.LayeredCircuit.random([lw] * (depth + 1), SEED, ctx)
+    inp = layered_inputs(lw)
+    inp_m = zk.to_mont(inp)
+    lc.evaluate(inp_m, mont=True)
+    units = layered_units(lw, depth) * world
+    stream = torch.cuda.ExternalStream(ctx.stream_handle(), device=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        raw = lc.prove_raw()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    launches0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.start()
+    e0.record(stream)
+    for _ in range(args.steps):
+        raw = lc.prove_raw()
+    e1.record(stream)
+    barrier()
+    sampler.stop_flag = True
+    ms = e0.elapsed_time(e1)
+    launches = ctx.launch_count() - launches0
+    rounds_us = ctx.round_times(cap=64)
+    # end to end: host inputs -> circuit evaluation on the device -> proof on the host
+    e2e_ms = None
+    if not args.no_e2e:
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            lc.evaluate(inp_m, mont=True)
+            raw2 = lc.prove_raw()
+        barrier()
+        e2e_ms = (time.perf_counter() - t0) * 1e3
+        assert all(np.array_equal(raw[k], raw2[k]) for k in raw), "end-to-end proof differs from the resident one"
+    if dist is not None:
+        tms = torch.tensor([ms, e2e_ms or 0.0], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = float(tms[0].item()), (float(tms[1].item()) if e2e_ms is not None else None)
+    sampler.join(timeout=1.0)
+    proof = lc.prove()
+    proof_bytes = proof.to_bytes()
+    sha = hashlib.sha256(proof_bytes).hexdigest()
+    if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+    # parity and verification, outside the timed regions
+    from oracle import gkrmodel as g
+    t0 = time.perf_counter()
+    small = zk.LayeredCircuit.random([10] * 4, SEED + 1, ctx)
+    sin = layered_inputs(10)
+    small.evaluate(sin)
+    so = oracle_layered(small)
+    want = g.prove_layered(so, so.evaluation(sin), layer_prover=g.c_layer_prover, evaluate=g.c_evaluate)
+    parity = {"ok": small.prove().to_bytes() == want.to_bytes(), "what": "width 2^10 x 3 layers of the same circuit family: proof bytes against the oracle's DENSE "
+              "prover (oracle/gkrmodel.py prove_layered, 2^20-entry layer tables through oracle/zkref.c)", "seconds": None}
+    parity["seconds"] = round(time.perf_counter() - t0, 2)
+    assert parity["ok"], "linear-time GKR proof differs from the oracle's dense prover"
+    t0 = time.perf_counter()
+    if args.verify_full:
+        verified = {"ok": bool(lc.verify(inp, proof)), "what": "GKRProtocol::verify (host, Python integers) of the timed width-2^%d proof" % lw}
+    else:
+        mid = zk.LayeredCircuit.random([14] * 5, SEED + 2, ctx)
+        min_ = layered_inputs(14)
+        mid.evaluate(min_)
+        verified = {"ok": bool(mid.verify(min_, mid.prove())), "what": "GKRProtocol::verify (host, Python integers) of a width-2^14 x 4 layers instance; "
+                    "--verify-full checks the timed proof itself (about a minute)"}
+    verified["seconds"] = round(time.perf_counter() - t0, 2)
+    assert verified["ok"], "GKR proof does not verify"
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        cpu = cpu_gkr_linear_sample(1)
+    n_rounds = depth * 2 * lw
+    value = units * args.steps / (ms * 1e-3)
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (256-bit modular integer, BLS12-381 Fr, Montgomery)",
+        "data": "synthetic (seeded random gates and inputs)",
+        "config": {"workload": "c4b: " + wl["desc"], "log_width": lw, "depth": depth, "gates": depth << lw, "sumcheck_rounds": n_rounds,
+                   "unit_note": "evals = table entries of the two phases of every layer sumcheck (2 x 2^%d x %d per proof); the reference's dense form of "
+                                "the same proof sums over 2^%d entries per layer" % (lw, depth, 2 * lw),
+                   "l2_policy": "inputs_fit_l2_no_flush (four 32 MiB tables per phase)", "sharding": "replicas" if world > 1 else "single GPU",
+                   "proof_bytes": len(proof_bytes)},
+        "clocks": sampler.summary(), "gpu_launches": int(launches), "proof_sha256": sha, "parity": parity, "verified": verified,
+        "e2e": None if e2e_ms is None else {
+            "value": units * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 32 << lw, "d2h_bytes_per_step": int(len(proof_bytes) + (32 << lw)),
+            "ms_per_step": round(e2e_ms / args.steps, 4),
+            "api": "LayeredCircuit.evaluate(host inputs) + LayeredCircuit.prove_raw(): zksc_circuit_evaluate + zksc_gkr_prove_linear (host wall clock)"},
+        "roofline": None, "int_roofline": None, "cpu_baseline": cpu,
+        "latency": {"sumcheck_rounds": n_rounds, "layers": depth, "us_per_round_incl_layer_setup": round(ms / args.steps * 1e3 / n_rounds, 2),
+                    "last_layer_rounds_us": [round(x, 1) for x in rounds_us[:lw]]},
+        "note": "latency-bound: %d sumcheck rounds over tables of at most 2^%d entries (one host round trip each: the transcript stays on the host) "
+                "+ 2 table constructions per layer; no single dominant kernel, hence a latency object instead of a roofline object" % (n_rounds, lw),
+    }
+    print(json.dumps(out))
+    sys.stdout.flush()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_gkr_linear_sample(steps, lw=8, depth=4):
+    """the reference's (dense) algorithm on the same circuit family at a width it can hold: oracle/gkrmodel.py prove_layered"""
+    import random
+
+    from oracle import cref
+    from oracle import gkrmodel as g
+    th = cref.max_threads()
+    cref.set_threads(th)
+    rng = random.Random(SEED)
+    oc = g.LayeredCircuit([lw] * (depth + 1), [[(rng.randrange(2), rng.randrange(1 << lw), rng.randrange(1 << lw)) for _ in range(1 << lw)] for _ in range(depth)])
+    ev = oc.evaluation(layered_inputs(lw))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        g.prove_layered(oc, ev, layer_prover=g.c_layer_prover, evaluate=g.c_evaluate)
+    dt = (time.perf_counter() - t0) / steps
+    cref.set_threads(1)
+    return {"value": layered_units(lw, depth) / dt, "unit": UNIT, "cores": th, "kind": "port",
+            "sample": "oracle/gkrmodel.py prove_layered: the reference's DENSE prover (2^%d-entry layer tables, layer sumchecks in oracle/zkref.c on %d OpenMP "
+                      "threads) on a width-2^%d x %d layers circuit of the same family, %.2f s per proof; it cannot hold width 2^20 (2^40-entry tables); "
+                      "same unit (two phases of 2^k entries per layer)" % (2 * lw, th, lw, depth, dt)}
+
+
+def run_reference_gkr_linear(args):
+    wl = WORKLOADS[args.workload]
+    for _ in range(min(args.warmup, 1)):
+        cpu_gkr_linear_sample(1)
+    t0 = time.perf_counter()
+    cpu = cpu_gkr_linear_sample(args.steps)
+    dt = time.perf_counter() - t0
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64 limbs (256-bit modular integer, BLS12-381 Fr, Montgomery)", "data": "synthetic (same circuit family and inputs)",
+        "config": {"workload": "c4b: " + wl["desc"], "log_width": 8, "depth": 4},
+        "cpu_baseline": cpu, "e2e": {"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
 def workload_config(workload, G, proof_bytes):
     """The `config` object of a line: a function of the workload and the GPU count only, so that both arms print the same one."""
     wl = WORKLOADS[workload]
@@ -716,6 +897,8 @@ def run_reference(args):
         return
     if WORKLOADS[args.workload]["proto"] == "gkr":
         return run_reference_gkr(args)
+    if WORKLOADS[args.workload]["proto"] == "gkr_linear":
+        return run_reference_gkr_linear(args)
     cref, wl, n, tabs, proto = cpu_workload(args.workload, cpu_sample_n(args))
     th = cref.max_threads()
     cref.set_threads(th)
@@ -794,6 +977,7 @@ def main():
     ap.add_argument("--target-n", type=int, default=28, help="n_vars of the target_c3 leg (BASELINE config 3: 28)")
     ap.add_argument("--no-target", action="store_true", help="skip the target_c3 leg (degree 3, 2^28 entries, strong scaling)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--verify-full", action="store_true", help="c4b: run the host verifier on the timed width-2^20 proof (about a minute)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--round-profile", action="store_true", help="add the per-launch-shape average durations to the JSON line")
     args = ap.parse_args()

@@ -23,26 +23,44 @@
 namespace zksc {
 
 constexpr int kEqMaxVars = 30;
+constexpr int kEqHalfMax = 15;         // eq(r, a) = hi[a >> kl] lo[a & (2^kl - 1)]: two tables of at most 2^15 entries, ONE product per label
 struct EqPoint {
     Fr r[kEqMaxVars];          // r[0] pairs with the label's most significant bit (evaluation_form.rs:143-159: successive variable-0 folds)
     unsigned int k;
 };
-ZKSC_DEV Fr eq_at(const EqPoint& p, unsigned long long a) {
-    Fr v = fr_one();
-    for (unsigned int j = 0; j < p.k; j++) {
-        const Fr x = p.r[j];
-        v = fr_mul(v, ((a >> (p.k - 1 - j)) & 1ull) ? x : fr_sub(fr_one(), x));
+// the two half tables of eq(p, .): hi over the first k - kl coordinates (times `scale`), lo over the last kl = k / 2
+__global__ void __launch_bounds__(256) gkr_eq_halves_kernel(const __grid_constant__ EqPoint p, const Fr scale, Fr* hi, Fr* lo) {
+    const unsigned int kl = p.k / 2, kh = p.k - kl;
+    const unsigned int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a < (1u << kh)) {
+        Fr v = scale;
+        for (unsigned int j = 0; j < kh; j++) {
+            const Fr x = p.r[j];
+            v = fr_mul(v, ((a >> (kh - 1 - j)) & 1u) ? x : fr_sub(fr_one(), x));
+        }
+        st256(hi + a, v);
     }
-    return v;
+    if (a < (1u << kl)) {
+        Fr v = fr_one();
+        for (unsigned int j = 0; j < kl; j++) {
+            const Fr x = p.r[kh + j];
+            v = fr_mul(v, ((a >> (kl - 1 - j)) & 1u) ? x : fr_sub(fr_one(), x));
+        }
+        st256(lo + a, v);
+    }
 }
-// out[a] = alpha eq(pb, a) + beta eq(pc, a)   (two == 0: eq(pb, a) alone)
-__global__ void __launch_bounds__(256) gkr_eq_kernel(const __grid_constant__ EqPoint pb, const __grid_constant__ EqPoint pc, const Fr alpha, const Fr beta,
-                                                     int two, Fr* out, unsigned long long n) {
+struct EqHalves {
+    const Fr *hi, *lo;
+    unsigned int kl;
+};
+ZKSC_DEV Fr eq_from_halves(const EqHalves& e, unsigned int a) { return fr_mul(ld256(e.hi + (a >> e.kl)), ld256(e.lo + (a & ((1u << e.kl) - 1u)))); }
+// wgt[g] = alpha eq(r_b, g) + beta eq(r_c, g)  (the scales sit in the hi tables; two == 0: the first term alone)
+__global__ void __launch_bounds__(256) gkr_wgt_kernel(const EqHalves b, const EqHalves c, int two, Fr* out, unsigned long long n) {
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    for (unsigned long long a = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; a < n; a += stride) {
-        Fr v = eq_at(pb, a);
-        if (two) v = fr_add(fr_mul(v, alpha), fr_mul(eq_at(pc, a), beta));
-        st256(out + a, v);
+    for (unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; g < n; g += stride) {
+        Fr v = eq_from_halves(b, (unsigned int)g);
+        if (two) v = fr_add(v, eq_from_halves(c, (unsigned int)g));
+        st256(out + g, v);
     }
 }
 // Circuit::evaluation, one layer: out[g] = in[in0 g] (+ or *) in[in1 g]
@@ -74,13 +92,13 @@ __global__ void __launch_bounds__(256) gkr_phase1_kernel(const unsigned int* row
 }
 // Phase 2 tables: [A, W(u) + W | W(u) M, W].  row[c] .. row[c + 1] index the gates whose second input is wire c.
 __global__ void __launch_bounds__(256) gkr_phase2_kernel(const unsigned int* row, const unsigned int* gate, const unsigned char* type, const unsigned int* in0,
-                                                         const Fr* wgt, const Fr* eq_u, const Fr* w, const Fr wu, Fr* tab, unsigned long long n) {
+                                                         const Fr* wgt, const EqHalves eq_u, const Fr* w, const Fr wu, Fr* tab, unsigned long long n) {
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     for (unsigned long long c = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += stride) {
         Fr a = fr_zero(), m = fr_zero();
         for (unsigned int i = row[c]; i < row[c + 1]; i++) {
             const unsigned int g = gate[i];
-            const Fr t = fr_mul(ld256(wgt + g), ld256(eq_u + in0[g]));
+            const Fr t = fr_mul(ld256(wgt + g), eq_from_halves(eq_u, in0[g]));
             if (type[g]) m = fr_add(m, t);
             else a = fr_add(a, t);
         }
@@ -107,7 +125,9 @@ struct zksc_circuit {
     std::vector<Layer> layers;
     std::vector<Fr*> values;                  // [n_layers + 1] layer values in HBM (zksc_circuit_evaluate)
     bool evaluated = false;
-    Fr *wgt = nullptr, *eq_u = nullptr;       // scratch: widest layer
+    Fr *wgt = nullptr, *eq_half = nullptr;    // scratch: weights of the widest layer; six half tables of eq (2^15 entries each)
+    Fr* bytes = nullptr;                      // scratch: the output layer as big-endian bytes
+    uint8_t* h_stage = nullptr;               // pinned: [bytes | Montgomery values] of the output layer on their way to the host
     std::map<uint32_t, zksc_tables*> handles; // prover table handles by number of variables
 };
 
@@ -119,7 +139,8 @@ extern "C" int zksc_circuit_free(zksc_circuit* c) {
     cudaStreamSynchronize(ctx->stream);
     for (auto& l : c->layers) { cudaFree(l.type); cudaFree(l.in0); cudaFree(l.in1); cudaFree(l.row0); cudaFree(l.gate0); cudaFree(l.row1); cudaFree(l.gate1); }
     for (Fr* v : c->values) cudaFree(v);
-    cudaFree(c->wgt); cudaFree(c->eq_u);
+    cudaFree(c->wgt); cudaFree(c->eq_half); cudaFree(c->bytes);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
     delete c;
     return ZKSC_OK;
 }
@@ -133,6 +154,7 @@ extern "C" int zksc_circuit_create(zksc_ctx* ctx, uint32_t n_layers, const uint3
     if (n_layers < 1 || n_layers > 64) FAIL(ZKSC_ERR_SHAPE, "layered circuit: 1..64 layers");
     for (uint32_t i = 0; i <= n_layers; i++)
         if (log_width[i] > 28 || (i > 0 && log_width[i] < 1)) FAIL(ZKSC_ERR_SHAPE, "layer widths are 2^0..2^28 (2^1 at least below the output layer)");
+    static_assert(2 * zksc::kEqHalfMax >= 28, "eq half tables too small for the widest layer");
     CK(cudaSetDevice(ctx->device));
     TRY(quiesce(ctx));
     zksc_circuit* c = new zksc_circuit();
@@ -172,7 +194,9 @@ extern "C" int zksc_circuit_create(zksc_ctx* ctx, uint32_t n_layers, const uint3
     }
     for (uint32_t i = 0; i <= n_layers; i++) CK(cudaMalloc(&c->values[i], sizeof(Fr) << log_width[i]));
     CK(cudaMalloc(&c->wgt, sizeof(Fr) << std::max(widest, 1u)));
-    CK(cudaMalloc(&c->eq_u, sizeof(Fr) << std::max(widest, 1u)));
+    CK(cudaMalloc(&c->eq_half, 6 * (sizeof(Fr) << zksc::kEqHalfMax)));
+    CK(cudaMalloc(&c->bytes, (sizeof(Fr) << std::max(log_width[0], 1u)) + 2 * sizeof(Fr)));
+    CK(cudaHostAlloc((void**)&c->h_stage, (size_t)2 * (sizeof(Fr) << std::max(log_width[0], 1u)), cudaHostAllocDefault));
     guard.c = nullptr;
     *out = c;
     return ZKSC_OK;
@@ -241,21 +265,43 @@ extern "C" int zksc_gkr_prove_linear(zksc_circuit* c, uint64_t* w0, uint64_t* su
 
     host::FiatShamirTranscript transcript;
     // w_0 = the output layer (one output: [out, 0]); transcript.commit(w_0.to_bytes()); n_r; claimed = w_0(n_r)          protocol.rs:31-38
+    const auto q0 = std::chrono::steady_clock::now();
+    auto us_since = [](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - a).count(); };
+    // (to_bytes on the device, Multilinear::to_bytes evaluation_form.rs:54-62; the SHA-256 of the bytes and the challenges on the host;
+    //  w_0(n_r) by successive folds on the device)
     const uint32_t k0 = std::max(c->lw[0], 1u);
-    std::vector<uint64_t> w0h((size_t)4 << k0, 0);
-    CK(cudaMemcpyAsync(w0h.data(), c->values[0], sizeof(Fr) << c->lw[0], cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    memcpy(w0, w0h.data(), w0h.size() * 8);
-    std::vector<FrH> cur((size_t)1 << k0);
-    for (size_t i = 0; i < cur.size(); i++) { cur[i] = load_h(&w0h[4 * i]); transcript.commit_field(cur[i]); }
-    std::vector<FrH> r_b = transcript.evaluate_n_challenge_into_field(k0), r_c;
-    for (uint32_t j = 0; j < k0; j++) {        // Multilinear::evaluation: successive variable-0 folds (evaluation_form.rs:162-175)
-        const size_t half = cur.size() / 2;
-        std::vector<FrH> nx(half);
-        for (size_t i = 0; i < half; i++) nx[i] = host::add(cur[i], host::mul(r_b[j], host::sub(cur[i + half], cur[i])));
-        cur.swap(nx);
+    const size_t n0 = (size_t)1 << k0;
+    Fr* d_w0 = c->bytes + n0;          // scratch behind the bytes: [out, 0] when the layer has one gate
+    std::vector<FrH> r_b, r_c;
+    FrH claimed;
+    {
+        const Fr* w0_src = c->values[0];
+        if (c->lw[0] == 0) {
+            CK(cudaMemsetAsync(d_w0, 0, 2 * sizeof(Fr), ctx->stream));
+            CK(cudaMemcpyAsync(d_w0, c->values[0], sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
+            w0_src = d_w0;
+        }
+        to_bytes_kernel<<<grid_for(ctx, n0, 256, 8), 256, 0, ctx->stream>>>(w0_src, c->bytes, n0);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        // through pinned memory (a pageable destination makes these two copies 20 ms instead of 1.2 for a layer of 2^20 values)
+        CK(cudaMemcpyAsync(c->h_stage, c->bytes, n0 * 32, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(c->h_stage + n0 * 32, w0_src, n0 * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        const double t_copy = us_since(q0);
+        transcript.commit(c->h_stage, n0 * 32);
+        r_b = transcript.evaluate_n_challenge_into_field(k0);
+        memcpy(w0, c->h_stage + n0 * 32, n0 * sizeof(Fr));
+        if (ctx->profile) fprintf(stderr, "[zksc profile] gkr linear: output layer to_bytes + copies %8.1f us, sha-256 + challenges %8.1f us\n", t_copy, us_since(q0) - t_copy);
+        std::vector<uint64_t> pts((size_t)4 * k0);
+        for (uint32_t j = 0; j < k0; j++) store_h(&pts[4 * j], r_b[j]);
+        uint64_t ev0[4];
+        DevBuf res(ctx);
+        CK(dev_alloc(ctx, (void**)&res.p, sizeof(Fr)));
+        TRY(gkr_eval_device(ctx, w0_src, k0, pts.data(), 1, res.p, ev0));
+        claimed = load_h(ev0);
+        if (ctx->profile) fprintf(stderr, "[zksc profile] gkr linear: output layer in all %8.1f us\n", us_since(q0));
     }
-    FrH claimed = cur[0];
     FrH alpha = host::kOne, beta = host::kZero;
 
     const uint32_t degs[2] = {2, 2};
@@ -270,14 +316,23 @@ extern "C" int zksc_gkr_prove_linear(zksc_circuit* c, uint64_t* w0, uint64_t* su
         const unsigned long long ng = 1ull << c->lw[li], nw = 1ull << k;
         const zksc_circuit::Layer& l = c->layers[li];
         if (r_b.size() != ka) FAIL(ZKSC_ERR_STATE, "challenge vector does not match the layer's gate-label bits");
+        const auto p0 = std::chrono::steady_clock::now();
         zksc_tables*& t = c->handles[k];
         if (!t) TRY(tables_alloc(ctx, k, 1, 2, degs, &t));
         // wgt(g) = alpha eq(r_b, g) + beta eq(r_c, g); the output layer: eq(n_r, g) (utils.rs:23-24, protocol.rs:86-88)
+        const size_t hsz = (size_t)1 << zksc::kEqHalfMax;
+        auto halves = [&](const std::vector<FrH>& r, const FrH& scale, int slot) {
+            const zksc::EqPoint p = gkr_eq_point(r);
+            Fr sc;
+            store_h((uint64_t*)sc.l, scale);
+            const unsigned int kl = p.k / 2, kh = p.k - kl;
+            zksc::gkr_eq_halves_kernel<<<((1u << kh) + 255) / 256, 256, 0, ctx->stream>>>(p, sc, c->eq_half + (2 * slot) * hsz, c->eq_half + (2 * slot + 1) * hsz);
+            ctx->launches++;
+            return zksc::EqHalves{c->eq_half + (2 * slot) * hsz, c->eq_half + (2 * slot + 1) * hsz, kl};
+        };
         {
-            const zksc::EqPoint pb = gkr_eq_point(r_b), pc = gkr_eq_point(li > 0 ? r_c : r_b);
-            Fr a_m, b_m;
-            store_h((uint64_t*)a_m.l, alpha); store_h((uint64_t*)b_m.l, beta);
-            zksc::gkr_eq_kernel<<<grid_for(ctx, ng, 256, 8), 256, 0, ctx->stream>>>(pb, pc, a_m, b_m, li > 0 ? 1 : 0, c->wgt, ng);
+            const zksc::EqHalves hb = halves(r_b, alpha, 0), hc = li > 0 ? halves(r_c, beta, 1) : hb;
+            zksc::gkr_wgt_kernel<<<grid_for(ctx, ng, 256, 8), 256, 0, ctx->stream>>>(hb, hc, li > 0 ? 1 : 0, c->wgt, ng);
         }
         // ---- phase 1: the k rounds that bind b
         TRY(zksc_tables_reset(t));
@@ -294,26 +349,28 @@ extern "C" int zksc_gkr_prove_linear(zksc_circuit* c, uint64_t* w0, uint64_t* su
         // prove_run indexes its outputs by (proof * n + round) with the handle's own round count: this proof has n = 2k rounds, so the two runs
         // are given the layer's slots directly
         TRY(prove_run(t, ZKSC_PROTO_MULTI_PARTIAL, tr, k, 0, stride, msgs, lens, chal));
+        const double t_ph1 = us_since(p0);
         uint64_t resid[16];
         TRY(zksc_residual(t, resid));                                         // W(u), H1(u), H2(u), 1
+        const double t_res1 = us_since(p0);
         const FrH wu = load_h(resid);
         std::vector<FrH> u(k), v(k);
         for (uint32_t j = 0; j < k; j++) u[j] = load_h(chal + 4 * j);
         // ---- phase 2: the k rounds that bind c
         {
-            const zksc::EqPoint pu = gkr_eq_point(u);
-            Fr one_m, wu_m;
-            store_h((uint64_t*)one_m.l, host::kOne); store_h((uint64_t*)wu_m.l, wu);
-            zksc::gkr_eq_kernel<<<grid_for(ctx, nw, 256, 8), 256, 0, ctx->stream>>>(pu, pu, one_m, one_m, 0, c->eq_u, nw);
+            Fr wu_m;
+            store_h((uint64_t*)wu_m.l, wu);
+            const zksc::EqHalves hu = halves(u, host::kOne, 2);
             TRY(zksc_tables_reset(t));
-            zksc::gkr_phase2_kernel<<<grid_for(ctx, nw, 256, 8), 256, 0, ctx->stream>>>(l.row1, l.gate1, l.type, l.in0, c->wgt, c->eq_u, c->values[li + 1], wu_m,
-                                                                                         t->orig, nw);
-            ctx->launches += 2;
+            zksc::gkr_phase2_kernel<<<grid_for(ctx, nw, 256, 8), 256, 0, ctx->stream>>>(l.row1, l.gate1, l.type, l.in0, c->wgt, hu, c->values[li + 1], wu_m, t->orig, nw);
+            ctx->launches++;
             CK(cudaGetLastError());
             t->r0_valid = false;
         }
         TRY(prove_run(t, ZKSC_PROTO_MULTI_PARTIAL, tr, k, 0, stride, msgs + (size_t)k * stride * 4, lens + k, chal + (size_t)k * 4));
+        const double t_ph2 = us_since(p0);
         TRY(zksc_residual(t, resid));                                         // A(v), W(u) + W(v), W(u) M(v), W(v)
+        const double t_res2 = us_since(p0);
         const FrH wv = load_h(resid + 12);
         for (uint32_t j = 0; j < k; j++) v[j] = load_h(chal + 4 * (k + j));
         // transcript.commit(&proof.to_bytes()); W(b*), W(c*); alpha, beta                                    protocol.rs:93-113
@@ -329,6 +386,9 @@ extern "C" int zksc_gkr_prove_linear(zksc_circuit* c, uint64_t* w0, uint64_t* su
         beta = transcript.evaluate_challenge_into_field();
         claimed = host::add(host::mul(alpha, wu), host::mul(beta, wv));
         round_off += n;
+        if (ctx->profile)
+            fprintf(stderr, "[zksc profile] gkr linear layer %2u: tables + phase 1 %8.1f us, residual %7.1f, tables + phase 2 %8.1f, residual %7.1f, absorb %7.1f\n", li, t_ph1,
+                    t_res1 - t_ph1, t_ph2 - t_res1, t_res2 - t_ph2, us_since(p0) - t_res2);
     }
     return ZKSC_OK;
 }

@@ -356,13 +356,14 @@ class LayeredCircuit:
         return out
 
     def evaluate(self, inputs, mont=False):
-        """Circuit::evaluation (circuit/src/circuit.rs:32-55) on the device; -> the outputs (ints); the layer values stay in HBM"""
+        """Circuit::evaluation (circuit/src/circuit.rs:32-55) on the device; -> the outputs (ints; with mont=True inputs and outputs are
+        Montgomery limb arrays, as a Rust caller holds its Vec<Fr>); the layer values stay in HBM"""
         x = np.ascontiguousarray(inputs, dtype=np.uint64) if mont else to_mont([int(v) % R for v in inputs])
         if x.shape != (1 << self.log_width[-1], 4):
             raise ZkscError(-3, "the input layer has 2^%d values" % self.log_width[-1])
         out = np.zeros((1 << self.log_width[0], 4), dtype=np.uint64)
         self.ctx.check(_lib.lib().zksc_circuit_evaluate(self._h, _lib.p64(x), _lib.p64(out)))
-        return from_mont(out)
+        return out if mont else from_mont(out)
 
     def layer_values(self, layer):
         out = np.zeros((1 << self.log_width[layer], 4), dtype=np.uint64)
