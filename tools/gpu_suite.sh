@@ -6,12 +6,12 @@ grep -v "site-packages" gpurun_out/suite_pytest.log | tail -25
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 timeout 900 python bench.py --steps 20 --warmup 5 --round-profile > gpurun_out/suite_bench_c2.json 2> gpurun_out/suite_bench_c2.err; echo "bench rc=$?"; tail -c 600 gpurun_out/suite_bench_c2.err
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/suite_bench_ref.json 2>/dev/null; echo "ref rc=$?"
-for wl in c1 c3 c4 c5; do
+for wl in c1 c3 c4 c4b c5; do
     timeout 600 python bench.py --workload $wl --steps 10 --warmup 3 > gpurun_out/suite_bench_$wl.json 2>gpurun_out/suite_bench_$wl.err; echo "$wl rc=$?"
 done
 python - <<'PY'
 import json
-for wl in ('c2','c1','c3','c4','c5'):
+for wl in ('c2','c1','c3','c4','c4b','c5'):
     try:
         d=json.loads([l for l in open('gpurun_out/suite_bench_%s.json'%wl) if l.startswith('{')][-1])
         e=d.get('e2e') or {}
