@@ -71,11 +71,13 @@ def test_c5_shape_batch_byte_parity(ctx):
 
 
 @pytest.mark.parametrize("env", [{"ZKSC_STAGED_FOLD": "1"}, {"ZKSC_NO_TAIL": "1"}, {"ZKSC_NO_STAGED": "1"}, {"ZKSC_TAIL_WORK": "1"},
-                                 {"ZKSC_TAIL_WORK": "1000000000000"}])
+                                 {"ZKSC_TAIL_WORK": "1000000000000"}, {"ZKSC_ROUND_STATIC": "1"}, {"ZKSC_RES_STATIC": "1"},
+                                 {"ZKSC_ROUND_STATIC": "1", "ZKSC_RES_STATIC": "1", "ZKSC_NO_STAGED": "1"}, {"ZKSC_STAGED_FOLD": "1", "ZKSC_NO_TAIL": "1"}])
 @pytest.mark.parametrize("n,degs", [(22, [2]), (22, [3])])
 def test_kernel_variants_byte_parity(built, env, n, degs):
     """the alternative data paths (TMA-staged fold rounds, no resident kernel, no staged kernels, resident kernel only for the
-    last rounds / from round 1 on) must give the oracle's bytes too; a fresh context reads the switches"""
+    last rounds / from round 1 on, fixed split instead of chunks handed out from counters) must give the oracle's bytes too; a fresh
+    context reads the switches"""
     s, (want_bytes, want_chal) = _oracle(2, n, degs, 7700 + n)
     old = {k: os.environ.get(k) for k in env}
     os.environ.update(env)
@@ -92,6 +94,29 @@ def test_kernel_variants_byte_parity(built, env, n, degs):
             else:
                 os.environ[k] = v
     assert got == (s, want_bytes, want_chal), "variant %r differs from the oracle" % (env,)
+
+
+@pytest.mark.parametrize("env", [{"ZKSC_DYN_MAX_GROUPS": "64"}, {"ZKSC_DYN_MAX_GROUPS": "0"}])
+def test_batch_with_and_without_work_hand_out(built, env):
+    """a batch of 6 proofs of two products each (12 groups per launch): chunks from counters in every launch, or in none"""
+    n, degs, B, seed = 18, [2, 2], 6, 8300
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        c = zk.Context(0)
+        try:
+            got = _gpu(c, zk.PROTO_MULTI_PARTIAL, n, degs, seed, n_proofs=B)
+        finally:
+            c.close()
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    for b in range(B):
+        s, (want_bytes, want_chal) = _oracle(2, n, degs, seed + b)
+        assert got[b] == (s, want_bytes, want_chal), "proof %d of the batch differs from the oracle (%r)" % (b, env)
 
 
 def oracle_verifies(n, degs, seed, s, proof_bytes, chal):
