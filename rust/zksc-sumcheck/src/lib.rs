@@ -454,3 +454,69 @@ pub fn gkr_prove(gates: &[Vec<(bool, usize, usize)>], circuit_evaluation: &Vec<V
     }
     (proofs, wb.chunks(4).map(fr).collect(), wc.chunks(4).map(fr).collect(), w0.chunks(4).map(fr).collect())
 }
+
+/// A layered add/mul circuit of ANY power-of-two layer widths, resident on the device, proved in time linear in its gates
+/// (`zksc_circuit_*`, `zksc_gkr_prove_linear`; BASELINE config 4 as written: "width 2^20, depth 8").  `circuit::Circuit` holds only
+/// the pyramid shape (layer i: 2^i gates, circuit/src/utils.rs:1-34); on such circuits `prove` returns what `gkr_prove` returns,
+/// i.e. the fields of `GKRProtocol::prove`'s `GKRProof` (gkr/src/protocol.rs:10-15, :21-113), byte for byte.
+pub struct LayeredCircuit {
+    h: *mut zksc_circuit,
+    log_width: Vec<u32>,
+}
+impl LayeredCircuit {
+    /// `log_width[i]` = log2(gates of layer i), output layer first, last entry = log2(inputs);
+    /// `gates`: per layer the gates as (is_mul, in0, in1), inputs being wire indices of the layer below.
+    pub fn new(log_width: &[u32], gates: &[Vec<(bool, usize, usize)>]) -> Self {
+        assert_eq!(log_width.len(), gates.len() + 1, "one width per layer plus the input layer");
+        let gate_type: Vec<u8> = gates.iter().flatten().map(|g| g.0 as u8).collect();
+        let in0: Vec<u32> = gates.iter().flatten().map(|g| g.1 as u32).collect();
+        let in1: Vec<u32> = gates.iter().flatten().map(|g| g.2 as u32).collect();
+        for (i, g) in gates.iter().enumerate() {
+            assert_eq!(g.len(), 1usize << log_width[i], "layer {} must have 2^{} gates", i, log_width[i]);
+        }
+        let ctx = context();
+        let mut h = ptr::null_mut();
+        let rc = unsafe { zksc_circuit_create(ctx, gates.len() as u32, log_width.as_ptr(), gate_type.as_ptr(), in0.as_ptr(), in1.as_ptr(), &mut h) };
+        check(ctx, rc);
+        LayeredCircuit { h, log_width: log_width.to_vec() }
+    }
+    /// `Circuit::evaluation` (circuit/src/circuit.rs:32-55) on the device; returns the output layer, keeps every layer in HBM.
+    pub fn evaluate(&mut self, inputs: &[Fr]) -> Vec<Fr> {
+        assert_eq!(inputs.len(), 1usize << self.log_width[self.log_width.len() - 1], "the input layer has 2^log_width values");
+        let mut out = vec![0u64; 4 << self.log_width[0]];
+        let rc = unsafe { zksc_circuit_evaluate(self.h, limbs(inputs), out.as_mut_ptr()) };
+        check(context(), rc);
+        out.chunks(4).map(fr).collect()
+    }
+    /// `GKRProtocol::prove` of the latest `evaluate`: (sumcheck_proofs, wb_s, wc_s, w_0).
+    pub fn prove(&mut self) -> (Vec<ComposedSumcheckProof>, Vec<Fr>, Vec<Fr>, Vec<Fr>) {
+        let l = self.log_width.len() - 1;
+        let rounds = unsafe { zksc_circuit_total_rounds(self.h) } as usize;
+        let n0 = std::cmp::max(2usize, 1usize << self.log_width[0]);
+        let (mut w0, mut sums, mut wb, mut wc) = (vec![0u64; 4 * n0], vec![0u64; 4 * l], vec![0u64; 4 * l], vec![0u64; 4 * l]);
+        let (mut msgs, mut lens, mut chal) = (vec![0u64; rounds * 6 * 4], vec![0u32; rounds], vec![0u64; rounds * 4]);
+        let rc = unsafe {
+            zksc_gkr_prove_linear(self.h, w0.as_mut_ptr(), sums.as_mut_ptr(), wb.as_mut_ptr(), wc.as_mut_ptr(), msgs.as_mut_ptr(), lens.as_mut_ptr(), chal.as_mut_ptr())
+        };
+        check(context(), rc);
+        let mut proofs = Vec::with_capacity(l);
+        let mut off = 0usize;
+        for li in 0..l {
+            let n = 2 * self.log_width[li + 1] as usize;
+            let round_polys = (off..off + n).map(|r| SparseUnivariatePolynomial {
+                monomial: (0..lens[r] as usize).map(|m| {
+                    let o = (r * 6 + 2 * m) * 4;
+                    UnivariateMonomial { coeff: fr(&msgs[o..o + 4]), pow: fr(&msgs[o + 4..o + 8]) }
+                }).collect(),
+            }).collect();
+            proofs.push(ComposedSumcheckProof { round_polys, sum: fr(&sums[4 * li..4 * li + 4]) });
+            off += n;
+        }
+        (proofs, wb.chunks(4).map(fr).collect(), wc.chunks(4).map(fr).collect(), w0.chunks(4).map(fr).collect())
+    }
+}
+impl Drop for LayeredCircuit {
+    fn drop(&mut self) {
+        unsafe { zksc_circuit_free(self.h) };
+    }
+}

@@ -65,3 +65,21 @@ fn test_multi_composed_sum_check_proof_2_on_gkr_example() {
     bad.sum += Fr::from(1u64);
     assert_eq!(MultiComposedSumcheckVerifier::verify_partial(&bad).unwrap_err(), "Verification failed");
 }
+
+/// gkr/src/protocol.rs:209-233 (test_gkr_protocol_1): the linear-time prover on the reference's circuit gives the dense prover's proof
+#[test]
+fn test_gkr_linear_prover_matches_the_dense_prover_on_the_reference_circuit() {
+    use zksc_sumcheck::{gkr_prove, LayeredCircuit};
+    let gates = vec![vec![(true, 0usize, 1usize)], vec![(false, 0, 1), (true, 2, 3)]];
+    let input: Vec<Fr> = [2u64, 3, 4, 5].iter().map(|&x| Fr::from(x)).collect();
+    let mut lc = LayeredCircuit::new(&[0, 1, 2], &gates);
+    assert_eq!(lc.evaluate(&input), vec![Fr::from(100u64)]);
+    let evaluation = vec![vec![Fr::from(100u64)], vec![Fr::from(5u64), Fr::from(20u64)], input.clone()];
+    let (proofs, wb, wc, w0) = lc.prove();
+    let (dproofs, dwb, dwc, dw0) = gkr_prove(&gates, &evaluation);
+    assert_eq!(proofs.len(), dproofs.len());
+    for (a, b) in proofs.iter().zip(dproofs.iter()) {
+        assert_eq!(a.to_bytes(), b.to_bytes());
+    }
+    assert_eq!((wb, wc, w0), (dwb, dwc, dw0));
+}
