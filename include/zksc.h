@@ -247,6 +247,11 @@ int zksc_circuit_free(zksc_circuit* c);
 int zksc_circuit_evaluate(zksc_circuit* c, const uint64_t* inputs, uint64_t* outputs);
 int zksc_circuit_layer_values(zksc_circuit* c, uint32_t layer, uint64_t* out);
 uint64_t zksc_circuit_total_rounds(const zksc_circuit* c);
+/* Verifier side of one layer (GKRProtocol::verify, gkr/src/protocol.rs:131-133, :164-171): out[0] = alpha add(r_b, b, c) + beta add(r_c, b, c),
+ * out[1] = the same for mul, from the gate lists on the device (the reference evaluates dense wiring tables).  r_b, r_c: max(1, log_width[layer])
+ * coordinates each (r_c / beta NULL: one point, the output layer's n_r); b, c: log_width[layer + 1] coordinates each. */
+int zksc_circuit_wiring_eval(zksc_circuit* c, uint32_t layer, const uint64_t* r_b, const uint64_t* alpha, const uint64_t* r_c, const uint64_t* beta,
+                             const uint64_t* b, const uint64_t* cpt, uint64_t* out);
 int zksc_gkr_prove_linear(zksc_circuit* c, uint64_t* w0, uint64_t* sums, uint64_t* wb_s, uint64_t* wc_s, uint64_t* round_msgs, uint32_t* round_len,
                           uint64_t* challenges);
 

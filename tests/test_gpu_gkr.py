@@ -173,7 +173,12 @@ def test_linear_prover_uniform_and_ragged_widths_vs_dense_oracle(log_width, seed
     want = g.prove_layered(oc, ev, layer_prover=g.c_layer_prover, evaluate=g.c_evaluate)
     assert proof.to_bytes() == want.to_bytes()
     assert proof.wb_s == want.wb_s and proof.wc_s == want.wc_s
-    assert lc.verify(inp, proof)
+    assert lc.verify(inp, proof) and lc.verify(inp, proof, device=False)       # wiring polynomials on the device / in Python integers
+    ch = proof.challenges[:2 * log_width[1]]
+    pts = [(ch[:log_width[1]][:max(log_width[0], 1)] if False else [5] * max(log_width[0], 1), 3), ([7] * max(log_width[0], 1), 11)]
+    b, c = ch[:log_width[1]], ch[log_width[1]:]
+    assert lc.wiring_at_device(0, pts, b, c) == lc.wiring_at(0, pts, b, c)
+    assert lc.wiring_at_device(0, pts[:1], b, c) == lc.wiring_at(0, pts[:1], b, c)
     proof.sumcheck_proofs[0].round_polys[0].monomial[0] = ((proof.sumcheck_proofs[0].round_polys[0].monomial[0][0] + 1) % R, proof.sumcheck_proofs[0].round_polys[0].monomial[0][1])
     assert not lc.verify(inp, proof)
 
@@ -196,7 +201,9 @@ def test_linear_prover_width_2_16_verifies():
     inp = [(0x9E3779B97F4A7C15 * (i + 1)) % R for i in range(1 << 16)]
     lc.evaluate(inp)
     proof = lc.prove()
-    assert lc.verify(inp, proof)
+    assert lc.verify(inp, proof) and lc.verify(inp, proof, device=False)
+    proof.wc_s[1] = (proof.wc_s[1] + 1) % R
+    assert not lc.verify(inp, proof)
 
 
 def test_linear_prover_shape_errors():

@@ -93,6 +93,7 @@ def lib():
         "zksc_circuit_layer_values": (ctypes.c_int, [vp, ctypes.c_uint32, _u64p]),
         "zksc_circuit_total_rounds": (ctypes.c_uint64, [vp]),
         "zksc_gkr_prove_linear": (ctypes.c_int, [vp, _u64p, _u64p, _u64p, _u64p, _u64p, _u32p, _u64p]),
+        "zksc_circuit_wiring_eval": (ctypes.c_int, [vp, ctypes.c_uint32, _u64p, _u64p, _u64p, _u64p, _u64p, _u64p, _u64p]),
         "zksc_ml_partial_evaluation": (ctypes.c_int, [vp, _u64p, ctypes.c_uint64, _u64p, ctypes.c_uint32, _u64p]),
         "zksc_ml_evaluation": (ctypes.c_int, [vp, _u64p, ctypes.c_uint64, _u64p, ctypes.c_uint32, _u64p]),
         "zksc_ml_outer": (ctypes.c_int, [vp, ctypes.c_int, _u64p, ctypes.c_uint64, _u64p, ctypes.c_uint64, _u64p]),

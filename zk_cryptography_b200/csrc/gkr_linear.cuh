@@ -110,6 +110,35 @@ __global__ void __launch_bounds__(256) gkr_phase2_kernel(const unsigned int* row
     }
 }
 
+// Verifier side: per-block partial sums of  wgt(g) eq(b, in0 g) eq(c, in1 g)  over the add gates (out[2 blk]) and the mul gates (out[2 blk + 1])
+// of a layer = add~(r, b, c), mul~(r, b, c) of gkr/src/protocol.rs:131-133, 164-171 without the dense wiring tables
+__global__ void __launch_bounds__(256) gkr_wiring_eval_kernel(const unsigned char* type, const unsigned int* in0, const unsigned int* in1, const EqHalves wb,
+                                                              const EqHalves wc, int two, const EqHalves eb, const EqHalves ec, Fr* out, unsigned long long n_gates) {
+    __shared__ Fr s_a[256], s_m[256];
+    Fr a = fr_zero(), m = fr_zero();
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; g < n_gates; g += stride) {
+        Fr w = eq_from_halves(wb, (unsigned int)g);
+        if (two) w = fr_add(w, eq_from_halves(wc, (unsigned int)g));
+        const Fr t = fr_mul(w, fr_mul(eq_from_halves(eb, in0[g]), eq_from_halves(ec, in1[g])));
+        if (type[g]) m = fr_add(m, t);
+        else a = fr_add(a, t);
+    }
+    s_a[threadIdx.x] = a;
+    s_m[threadIdx.x] = m;
+    for (unsigned int d = 128; d >= 1; d >>= 1) {
+        __syncthreads();
+        if (threadIdx.x < d) {
+            s_a[threadIdx.x] = fr_add(s_a[threadIdx.x], s_a[threadIdx.x + d]);
+            s_m[threadIdx.x] = fr_add(s_m[threadIdx.x], s_m[threadIdx.x + d]);
+        }
+    }
+    if (threadIdx.x == 0) {
+        st256(out + 2 * blockIdx.x, s_a[0]);
+        st256(out + 2 * blockIdx.x + 1, s_m[0]);
+    }
+}
+
 }  // namespace zksc
 
 struct zksc_circuit {
@@ -390,5 +419,50 @@ extern "C" int zksc_gkr_prove_linear(zksc_circuit* c, uint64_t* w0, uint64_t* su
             fprintf(stderr, "[zksc profile] gkr linear layer %2u: tables + phase 1 %8.1f us, residual %7.1f, tables + phase 2 %8.1f, residual %7.1f, absorb %7.1f\n", li, t_ph1,
                     t_res1 - t_ph1, t_ph2 - t_res1, t_res2 - t_ph2, us_since(p0) - t_res2);
     }
+    return ZKSC_OK;
+}
+
+// Verifier side of a layer (GKRProtocol::verify, gkr/src/protocol.rs:131-133 and :164-171):  out[0] = alpha add(r_b, b, c) + beta add(r_c, b, c),
+// out[1] = the same for mul, evaluated from the gate lists on the device.  r_b, r_c: log2(width of `layer`) coordinates each (at least one; beta and
+// r_c may be NULL: one point, as for the output layer); b, c: log2(width of layer + 1) coordinates each.  Montgomery elements.
+extern "C" int zksc_circuit_wiring_eval(zksc_circuit* c, uint32_t layer, const uint64_t* r_b, const uint64_t* alpha, const uint64_t* r_c, const uint64_t* beta,
+                                        const uint64_t* b, const uint64_t* cpt, uint64_t* out) {
+    if (!c) return ZKSC_ERR_STATE;
+    zksc_ctx* ctx = c->ctx;
+    if (!r_b || !alpha || !b || !cpt || !out || (r_c && !beta)) FAIL(ZKSC_ERR_SHAPE, "NULL argument");
+    if (layer >= c->n_layers) FAIL(ZKSC_ERR_SHAPE, "no such layer");
+    CK(cudaSetDevice(ctx->device));
+    TRY(quiesce(ctx));
+    const uint32_t ka = std::max(c->lw[layer], 1u), k = c->lw[layer + 1];
+    const unsigned long long ng = 1ull << c->lw[layer];
+    const zksc_circuit::Layer& l = c->layers[layer];
+    const size_t hsz = (size_t)1 << zksc::kEqHalfMax;
+    DevBuf tabs(ctx);
+    const int blocks = grid_for(ctx, ng, 256, 4);
+    CK(dev_alloc(ctx, (void**)&tabs.p, (8 * hsz + 2 * (size_t)blocks) * sizeof(Fr)));     // own half tables: a proof's may be in use by nobody, but keep them apart
+    auto halves = [&](const uint64_t* pt, uint32_t kk, const FrH& scale, int slot) {
+        std::vector<FrH> r(kk);
+        for (uint32_t j = 0; j < kk; j++) r[j] = load_h(pt + 4 * j);
+        const zksc::EqPoint p = gkr_eq_point(r);
+        Fr sc;
+        store_h((uint64_t*)sc.l, scale);
+        const unsigned int kl = p.k / 2, kh = p.k - kl;
+        zksc::gkr_eq_halves_kernel<<<((1u << kh) + 255) / 256, 256, 0, ctx->stream>>>(p, sc, tabs.p + (2 * slot) * hsz, tabs.p + (2 * slot + 1) * hsz);
+        ctx->launches++;
+        return zksc::EqHalves{tabs.p + (2 * slot) * hsz, tabs.p + (2 * slot + 1) * hsz, kl};
+    };
+    const zksc::EqHalves hb = halves(r_b, ka, load_h(alpha), 0), hc = r_c ? halves(r_c, ka, load_h(beta), 1) : hb;
+    const zksc::EqHalves eb = halves(b, k, host::kOne, 2), ec = halves(cpt, k, host::kOne, 3);
+    Fr* part = tabs.p + 8 * hsz;
+    zksc::gkr_wiring_eval_kernel<<<blocks, 256, 0, ctx->stream>>>(l.type, l.in0, l.in1, hb, hc, r_c ? 1 : 0, eb, ec, part, ng);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    std::vector<uint64_t> h((size_t)blocks * 8);
+    CK(cudaMemcpyAsync(h.data(), part, (size_t)blocks * 2 * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    FrH a = host::kZero, m = host::kZero;
+    for (int i = 0; i < blocks; i++) { a = host::add(a, load_h(&h[8 * (size_t)i])); m = host::add(m, load_h(&h[8 * (size_t)i + 4])); }
+    store_h(out, a);
+    store_h(out + 4, m);
     return ZKSC_OK;
 }

@@ -398,6 +398,20 @@ class LayeredCircuit:
         proof.challenges = from_mont(raw["chal"])
         return proof
 
+    def wiring_at_device(self, layer, points_and_scales, b, c):
+        """the same two values from the gate lists on the device (zksc_circuit_wiring_eval): what makes `verify` cheap at width 2^20"""
+        (r_b, alpha) = points_and_scales[0]
+        two = len(points_and_scales) > 1
+        out = np.zeros((2, 4), dtype=np.uint64)
+        null = ctypes.POINTER(ctypes.c_uint64)()
+        rc_arr = to_mont([int(x) for x in points_and_scales[1][0]]) if two else None
+        beta_arr = to_mont([int(points_and_scales[1][1])]) if two else None
+        self.ctx.check(_lib.lib().zksc_circuit_wiring_eval(self._h, layer, _lib.p64(to_mont([int(x) for x in r_b])), _lib.p64(to_mont([int(alpha)])),
+                                                           _lib.p64(rc_arr) if two else null, _lib.p64(beta_arr) if two else null,
+                                                           _lib.p64(to_mont([int(x) for x in b])), _lib.p64(to_mont([int(x) for x in c])), _lib.p64(out)))
+        v = from_mont(out)
+        return v[0], v[1]
+
     def wiring_at(self, layer, points_and_scales, b, c):
         """(add~, mul~)(b, c) = sum over the layer's gates g of [sum_j scale_j eq(r_j, g)] eq(b, in0 g) eq(c, in1 g), on the host
         (what Multilinear::evaluation of the wiring tables gives, gkr/src/protocol.rs:131-133, 164-171)"""
@@ -416,8 +430,10 @@ class LayeredCircuit:
                 add = (add + t) % R
         return add, mul
 
-    def verify(self, inputs, proof):
-        """GKRProtocol::verify (gkr/src/protocol.rs:115-195) for this circuit; host side (Python integers: small circuits)"""
+    def verify(self, inputs, proof, device=True):
+        """GKRProtocol::verify (gkr/src/protocol.rs:115-195) for this circuit: transcript, round checks and claims on the host; the wiring
+        polynomials add~, mul~ at (r, b*, c*) and the input layer at (b*, c*) on the device (device=False: everything in Python integers,
+        the independent cross-check of the tests, small circuits only)"""
         if len(proof.sumcheck_proofs) != self.n_layers or len(proof.wb_s) != self.n_layers or len(proof.wc_s) != self.n_layers:
             return False
         transcript = FiatShamirTranscript()
@@ -441,14 +457,14 @@ class LayeredCircuit:
                 return False
             b, c = ch[:len(ch) // 2], ch[len(ch) // 2:]
             wb, wc = proof.wb_s[i], proof.wc_s[i]
-            add, mul = self.wiring_at(i, points, b, c)
+            add, mul = (self.wiring_at_device if device else self.wiring_at)(i, points, b, c)
             if (add * ((wb + wc) % R) + mul * (wb * wc % R)) % R != sub.sum:
                 return False
             alpha, beta = transcript.evaluate_challenge_into_field(), transcript.evaluate_challenge_into_field()
             claimed = (alpha * wb + beta * wc) % R
             r_b, r_c = b, c
             points = [(r_b, alpha), (r_c, beta)]
-        w_in = Multilinear([int(v) % R for v in inputs])
+        w_in = Multilinear(inputs) if isinstance(inputs, np.ndarray) else Multilinear([int(v) % R for v in inputs])   # (an array: Montgomery limbs)
         return claimed == (alpha * w_in.evaluation(r_b) + beta * w_in.evaluation(r_c)) % R
 
     def close(self):
