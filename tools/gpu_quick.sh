@@ -1,0 +1,7 @@
+#!/bin/bash
+# parity tests + the short bench lines (no CPU leg, no target leg)
+cd "$GRAFT_REPO_ROOT"
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_parity_large.py tests/test_gpu_gkr.py -m gpu -x -q 2>&1 | tail -3
+ZKSC_AB_WORKLOADS="c2 c1 c5" bash tools/gpu_ab_env.sh "quick:ZKSC_X=0"
+for wl in c4 c4b; do timeout 300 python bench.py --workload $wl --steps 10 --warmup 3 --no-cpu > gpurun_out/quick_$wl.json 2>gpurun_out/quick_$wl.err; python -c "
+import json; d=json.loads([l for l in open('gpurun_out/quick_$wl.json') if l.startswith('{')][-1]); print('$wl ms/step %.4f' % d['ms_per_step'], d['latency'])"; done

@@ -403,6 +403,22 @@ struct SparseUnivariatePolynomial {
     // ~10 us each -- too slow for a per-round host step).
     static std::vector<FrH> dense_interpolate_evals(const std::vector<FrH>& ys) {
         const size_t n = ys.size();
+        // Degrees 1-3 in closed form (Newton's forward differences over x = 0, 1, 2, 3): the per-round host step of every prover here.
+        // The interpolant is unique, so these are the field values of the general routine below (tests/test_host_logic.py compares them).
+        if (n == 2) return {ys[0], sub(ys[1], ys[0])};
+        if (n == 3 || n == 4) {
+            static const FrH inv2 = inverse(from_u64(2)), inv6 = inverse(from_u64(6));
+            const FrH d1 = sub(ys[1], ys[0]);
+            const FrH d2 = add(sub(ys[2], add(ys[1], ys[1])), ys[0]);                 // y2 - 2 y1 + y0
+            const FrH h2 = mul(d2, inv2);                                             // coefficient of x (x - 1)
+            if (n == 3) return {ys[0], sub(d1, h2), h2};
+            // y3 - 3 y2 + 3 y1 - y0
+            const FrH t21 = sub(ys[1], ys[2]);
+            const FrH d3 = add(sub(ys[3], ys[0]), add(t21, add(t21, t21)));
+            const FrH c3 = mul(d3, inv6);                                             // coefficient of x (x - 1) (x - 2) = x^3 - 3 x^2 + 2 x
+            const FrH c3_2 = add(c3, c3);
+            return {ys[0], add(sub(d1, h2), c3_2), sub(h2, add(c3_2, c3)), c3};
+        }
         if (n >= 64) {
             std::vector<FrH> xs;
             for (size_t i = 0; i < n; i++) xs.push_back(from_u64(i));

@@ -2221,18 +2221,36 @@ static int prove_run(zksc_tables* t, int protocol, std::vector<host::FiatShamirT
                     bytes.insert(bytes.end(), be, be + 32);
                 }
             } else {
-                host::SparseUnivariatePolynomial round_poly = host::SparseUnivariatePolynomial::zero();  // :77
+                // round_poly = sum over the products of interpolate(evaluations)  (:77, :91-94).  SparseUnivariatePolynomial's interpolation
+                // drops the monomials whose coefficient is zero, its Add merges by power and KEEPS a sum that happens to be zero
+                // (sparse_univariate.rs:52-60, :159-203): a power is present iff some product has a nonzero coefficient there, and carries
+                // the sum of all products' coefficients -- formed here on the dense coefficients, without building the sparse objects.
+                FrH coeff[ZKSC_MAX_DEGREE + 1];
+                bool present[ZKSC_MAX_DEGREE + 1] = {};
+                static thread_local std::vector<FrH> ys;
                 for (uint32_t p = 0; p < t->P; p++) {
-                    std::vector<FrH> ys;
+                    ys.clear();
                     for (uint32_t i = 0; i <= t->deg[p]; i++) ys.push_back(load_h(e + 4 * (t->eoff[p] + i)));
-                    round_poly = round_poly + host::SparseUnivariatePolynomial::interpolate_evals(ys);  // :91-94
+                    const std::vector<FrH> dense = host::SparseUnivariatePolynomial::dense_interpolate_evals(ys);
+                    for (size_t k = 0; k < dense.size(); k++) {
+                        if (dense[k] == host::kZero) continue;
+                        coeff[k] = present[k] ? host::add(coeff[k], dense[k]) : dense[k];
+                        present[k] = true;
+                    }
                 }
-                *len = (uint32_t)round_poly.monomial.size();
-                for (size_t m = 0; m < round_poly.monomial.size(); m++) {
-                    store_h(msg + 8 * m, round_poly.monomial[m].coeff);
-                    store_h(msg + 8 * m + 4, round_poly.monomial[m].pow);
+                uint32_t nm = 0;
+                for (uint32_t k = 0; k <= ZKSC_MAX_DEGREE; k++) {
+                    if (!present[k]) continue;
+                    const FrH& pw = host::SparseUnivariatePolynomial::small_mont(k);
+                    store_h(msg + 8 * nm, coeff[k]);
+                    store_h(msg + 8 * nm + 4, pw);
+                    uint8_t b64[64];                                   // SparseUnivariatePolynomial::to_bytes (:27-34)
+                    host::to_be_bytes(coeff[k], b64);
+                    host::to_be_bytes(pw, b64 + 32);
+                    bytes.insert(bytes.end(), b64, b64 + 64);
+                    nm++;
                 }
-                round_poly.to_bytes(bytes);
+                *len = nm;
             }
             tr[b].commit(bytes);                                      // :97
             FrH r = tr[b].evaluate_challenge_into_field();            // :99
