@@ -330,6 +330,27 @@ def test_resident_tail_kernel_call_patterns(ctx):
     other.free()
 
 
+@pytest.mark.parametrize("n,degs,B", [(12, [2], 1), (9, [3, 1], 3), (14, [2, 2], 1)])
+def test_proof_after_a_proof_left_half_way(ctx, n, degs, B):
+    """A proof abandoned in the middle of the resident kernel's rounds (reset), then a whole proof whose round 0 runs inside the prover: the
+    resident kernel is queued behind that round's launch before any challenge is posted, so it must not read the "leave" mark the
+    abandoned session put into the mailbox (found by tools/stress.py)."""
+    rng = random.Random(5)
+    t = zk.Tables.synth(ctx, n, degs, 4242, n_proofs=B)
+    s = t.poly_sum()
+    first = t.prove(zk.PROTO_MULTI_PARTIAL, s)
+    for stop_after in (2, n - 1, 1):
+        t.reset()
+        for _ in range(stop_after):
+            t.round_evals()
+            t.bind(zk.to_mont([rng.randrange(R) for _ in range(B)]))
+        t.reset()
+        again = t.prove(zk.PROTO_MULTI_PARTIAL, s)          # no cached round 0 this time: it is launched inside the prover
+        for x, y in zip(first, again):
+            assert np.array_equal(x, y)
+    t.free()
+
+
 def test_tail_kernel_off_gives_identical_proofs():
     """ZKSC_NO_TAIL=1 (every round its own launch) and the default (resident tail kernel) must agree byte for byte."""
     import os

@@ -213,6 +213,7 @@ struct zksc_ctx {
     bool tail_enabled = true;            // ZKSC_NO_TAIL=1: every round is its own launch
     unsigned int dyn_max_groups = 8;     // ZKSC_DYN_MAX_GROUPS (<= kDynMaxGroups): most groups of a launch that takes its chunks from counters
     bool round_dynamic = true;           // ZKSC_ROUND_STATIC=1: the round kernels split a round by a fixed stride (kernels.cuh RoundBase::dynamic)
+    bool tail_prelaunch = true;          // ZKSC_NO_PRELAUNCH=1: the resident kernel is launched in its first round, not behind the launch of the round before
     bool tail_dynamic = true;            // ZKSC_RES_STATIC=1: the resident kernel splits every round by a fixed stride (no work counter)
     unsigned long long tail_work = kTailWorkDefault;   // start threshold of the resident kernel (ZKSC_TAIL_WORK overrides, experiments)
     int res_occ[kResMaxDegree + 1] = {};       // resident CTAs per SM of resident_kernel<dsel>
@@ -265,6 +266,7 @@ struct zksc_tables {
     // round-0 evaluations computed by zksc_poly_sum, handed to the next round-0 zksc_round_evals once
     // (calculate_poly_sum followed by prove is the reference's calling pattern; the input is immutable)
     std::vector<uint64_t> r0_cache;
+    bool in_prove = false;              // inside a prover's round loop: the next call is this handle's bind (what a queued-ahead resident kernel relies on)
     bool r0_valid = false;
     // The evaluations returned by the latest zksc_round_evals (valid until the next bind) and, after a
     // bind that followed them, the per-product claims h_p(r) = h_p,next(0) + h_p,next(1): with a claim the
@@ -401,6 +403,7 @@ extern "C" int zksc_ctx_create(int device, zksc_ctx** out) {
     { const char* e_ = getenv("ZKSC_PROFILE"); ctx->profile = (e_ && e_[0] == '1'); }
     { const char* e_ = getenv("ZKSC_NO_TAIL"); ctx->tail_enabled = !(e_ && e_[0] == '1'); }
     { const char* e_ = getenv("ZKSC_RES_STATIC"); ctx->tail_dynamic = !(e_ && e_[0] == '1'); }
+    { const char* e_ = getenv("ZKSC_NO_PRELAUNCH"); ctx->tail_prelaunch = !(e_ && e_[0] == '1'); }
     { const char* e_ = getenv("ZKSC_ROUND_STATIC"); ctx->round_dynamic = !(e_ && e_[0] == '1'); }
     { const char* e_ = getenv("ZKSC_DYN_MAX_GROUPS"); if (e_) ctx->dyn_max_groups = std::min<unsigned int>(kDynMaxGroups, (unsigned int)strtoul(e_, nullptr, 10)); }
     { const char* e_ = getenv("ZKSC_NO_FUSE"); ctx->fuse_products = !(e_ && e_[0] == '1'); }
@@ -1252,6 +1255,8 @@ static int tail_stop(zksc_tables* t) {
     }
     if (ctx->active_tail == t) ctx->active_tail = nullptr;
     CK(cudaStreamSynchronize(ctx->stream));
+    for (uint32_t b = 0; b < t->B && b < ctx->tail_proofs_cap; b++)       // the kernel is gone: no "leave" mark stays behind
+        if ((uint32_t)(ctx->tail_mail[(size_t)b * kMailUnits] >> 32) == kTailAbort) ctx->tail_mail[(size_t)b * kMailUnits] = 0;
     return ZKSC_OK;
 }
 static int quiesce(zksc_ctx* ctx) { return ctx && ctx->active_tail ? tail_stop(ctx->active_tail) : ZKSC_OK; }
@@ -1295,7 +1300,10 @@ static bool tail_eligible(const zksc_tables* t, unsigned long long half, bool sh
 }
 
 // Launch the resident kernel for all remaining rounds; the pending challenge is its first mailbox message.
-static int tail_start(zksc_tables* t, unsigned long long half, bool sharded) {
+// prelaunch: the kernel is queued BEHIND the ordinary launch of the round before its first one, while that round still runs -- the
+// cooperative launch (~12 us of API time and start-up, against ~5 for an ordinary one) disappears behind it; the first challenge does not
+// exist yet, the kernel waits for it in the mailbox like for every later one (zksc_bind posts it).
+static int tail_start(zksc_tables* t, unsigned long long half, bool sharded, bool prelaunch = false) {
     zksc_ctx* ctx = t->ctx;
     TRY(quiesce(ctx));
     const unsigned int cpg = tail_group_ctas(t);
@@ -1356,7 +1364,16 @@ static int tail_start(zksc_tables* t, unsigned long long half, bool sharded) {
         a.tail = gt.base; a.tail_tab_stride = gt.tab_stride; a.tail_proof_stride = gt.proof_stride;
     }
     a.relay_cap = (unsigned int)ctx->tail_proofs_cap;
-    tail_post(t, seq0);
+    if (prelaunch) {
+        // nothing is posted before this launch, so whatever an earlier session left in the mailbox is what the kernel reads first: a
+        // "leave" mark of a session that was stopped half-way must not be there (sequence number 0 is never used)
+        for (uint32_t b = 0; b < t->B; b++) ctx->tail_mail[(size_t)b * kMailUnits] = 0;
+        t->tail_cur = seq0 - 1;
+        t->tail_posted = false;
+        t->tail_seen = std::chrono::steady_clock::now();
+    } else {
+        tail_post(t, seq0);
+    }
     cudaError_t le = zksc_launch_resident(tail_dsel(t), (unsigned int)(groups * cpg), ctx->stream, a);
     if (le != cudaSuccess) {
         // cannot be made resident (another context holds the SMs, MPS limits, ...): ordinary launches from now on
@@ -1650,6 +1667,12 @@ static int round_evals_impl(zksc_tables* t, uint64_t* out, uint32_t npts_cap) {
     if (fold) { t->where = to; t->cur_n /= 2; t->pending = false; }
 
     if (mapped) {
+        // The next round will be the resident kernel's first: queue it now, behind this round's launch (see tail_start).  Only where nothing
+        // else of this round is queued after this point (host-mapped results), on unsharded contexts, in the prover's call pattern.
+        if (ctx->tail_prelaunch && t->in_prove && full && ctx->n_ranks == 1 && !t->tail_running && t->cur_n >= 4 && tail_eligible(t, t->cur_n / 4, false)) {
+            const int rc = tail_start(t, t->cur_n / 4, false, true);
+            if (rc != ZKSC_OK && rc != kTailExpired) return rc;      // (expired: cannot be made resident; the context is on ordinary launches now)
+        }
         const auto w0 = std::chrono::steady_clock::now();
         ctx->prof_launch = std::chrono::duration<double, std::micro>(w0 - prof_t0).count();
         TRY(wait_flag(ctx, seq));
@@ -1717,8 +1740,12 @@ extern "C" int zksc_bind(zksc_tables* t, const uint64_t* challenges) {
         // that deadline could reach some and not others, so the host never posts later than half of it after it saw the results:
         // past that, the kernel is told to leave (nothing of the round has been folded) and ordinary launches carry on.
         const double waited_ns = std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - t->tail_seen).count();
-        if (waited_ns > 0.5 * (double)kTailTimeoutNs) TRY(tail_stop(t));
-        else post = true;
+        if (waited_ns > 0.5 * (double)kTailTimeoutNs) {
+            // (also what happens when launches are synchronous -- a profiler -- and the kernel was queued ahead of its first round: it has
+            // come and gone while the launch call blocked.  Either way this host cannot feed a resident kernel: ordinary launches for good.)
+            TRY(tail_stop(t));
+            ctx->tail_enabled = false;
+        } else post = true;
     }
     const unsigned int post_seq = t->tail_cur + 1;
     for_each_proof(ctx, t->B, [&](uint32_t b) {
@@ -2201,6 +2228,7 @@ static int prove_run(zksc_tables* t, int protocol, std::vector<host::FiatShamirT
         explicit PoolSession(zksc_ctx* ctx, bool on) : c(on ? ctx : nullptr) { if (c) { c->pool->begin(); c->pool_active = true; } }
         ~PoolSession() { if (c) { c->pool_active = false; c->pool->end(); } }
     } pool_session(ctx, ctx->pool != nullptr && B >= kPoolMinProofs);
+    struct InProve { zksc_tables* t; explicit InProve(zksc_tables* x) : t(x) { t->in_prove = true; } ~InProve() { t->in_prove = false; } } in_prove(t);
     for (uint32_t round = round0; round < round0 + t->n_vars; round++) {
         const auto p0 = std::chrono::steady_clock::now();
         TRY(round_evals_impl(t, ev.data(), ZKSC_MAX_DEGREE + 1));
