@@ -98,6 +98,35 @@ def test_gkr_c_driver_matches_layerwise_driver(depth):
             zk.GKRProtocol.verify(zc, inp, a)
 
 
+@pytest.mark.parametrize("linear_min", ["1", "3", "99"])
+def test_gkr_c_driver_two_phase_form_of_large_layers(built, linear_min):
+    """zksc_gkr_prove runs its large layers (default: 9 bits per input label and up) in the two-phase form of csrc/gkr_linear.cuh: with
+    every layer / the layers from 3 bits / no layer in that form the bytes must be the oracle's"""
+    import os
+    old = os.environ.get("ZKSC_GKR_LINEAR_MIN")
+    os.environ["ZKSC_GKR_LINEAR_MIN"] = linear_min
+    try:
+        c = zk.Context(0)
+        try:
+            for layers, inp in [(CIRCUIT_1, [2, 3, 4, 5]), (CIRCUIT_2, [2, 1, 3, 1, 4, 1, 2, 2, 3, 3, 4, 4, 2, 3, 3, 4])]:
+                zc, oc = both(layers)
+                ev = zc.evaluation(inp)
+                got, want = zk.GKRProtocol.prove(zc, ev, ctx=c), g.GKRProtocol.prove(oc, ev)
+                assert got.to_bytes() == want.to_bytes() and got.wb_s == want.wb_s and got.wc_s == want.wc_s
+            zc, oc = zk.Circuit.random(7), g.Circuit.random(7)
+            inp = [(0x9E3779B97F4A7C15 * (i + 1)) % R for i in range(1 << 7)]
+            ev = zc.evaluation(inp)
+            got = zk.GKRProtocol.prove(zc, ev, ctx=c)
+            assert got.to_bytes() == g.GKRProtocol.prove_sparse(oc, ev, layer_prover=g.c_layer_prover, evaluate=g.c_evaluate).to_bytes()
+        finally:
+            c.close()
+    finally:
+        if old is None:
+            os.environ.pop("ZKSC_GKR_LINEAR_MIN", None)
+        else:
+            os.environ["ZKSC_GKR_LINEAR_MIN"] = old
+
+
 def test_gkr_c_driver_reference_cases_layerwise_too():
     for layers, inp in [(CIRCUIT_1, [2, 3, 4, 5]), (CIRCUIT_2, [2, 1, 3, 1, 4, 1, 2, 2, 3, 3, 4, 4, 2, 3, 3, 4])]:
         zc, oc = both(layers)

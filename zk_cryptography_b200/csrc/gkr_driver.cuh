@@ -92,6 +92,18 @@ static std::vector<FrH> gkr_eq_vector(const std::vector<FrH>& r) {
     return v;
 }
 
+// Gate arrays and the two CSR orders (gates grouped by first / by second input) of one circuit layer, in HBM; gkr_linear.cuh has the
+// layer sumcheck that works from them in two phases on tables of 2^k entries instead of 2^(2k).
+struct GkrLayerDev {
+    unsigned char* type = nullptr;                               // [gates]
+    unsigned int *in0 = nullptr, *in1 = nullptr;                 // [gates]
+    unsigned int *row0 = nullptr, *gate0 = nullptr;              // gates grouped by first input: [wires + 1], [gates]
+    unsigned int *row1 = nullptr, *gate1 = nullptr;              // ... by second input
+};
+static int gkr_two_phase_layer(zksc_ctx* ctx, const GkrLayerDev& l, const Fr* d_w, uint32_t k, unsigned long long ng, const std::vector<FrH>& r_b,
+                               const std::vector<FrH>* r_c, const FrH& alpha, const FrH& beta, Fr* wgt, Fr* eq_half, size_t hsz, zksc_tables* t, const FrH& claimed,
+                               uint32_t stride, uint64_t* msgs, uint32_t* lens, uint64_t* chal, FrH* wu_out, FrH* wv_out, double* prof);
+
 extern "C" uint64_t zksc_gkr_total_rounds(uint32_t n_layers) { return (uint64_t)n_layers * (n_layers + 1); }
 
 extern "C" int zksc_gkr_prove(zksc_ctx* ctx, uint32_t n_layers, const uint32_t* n_gates, const uint8_t* gate_type, const uint32_t* gate_in0,
@@ -144,6 +156,78 @@ extern "C" int zksc_gkr_prove(zksc_ctx* ctx, uint32_t n_layers, const uint32_t* 
         const uint32_t k = li + 1, n = 2 * k;
         const uint64_t nw = 1ull << k;
         const auto p0 = std::chrono::steady_clock::now();
+        if (k >= ctx->gkr_linear_min) {
+            // Large layers: the two-phase form of gkr_linear.cuh -- 2k rounds on tables of 2^k entries built from the gate lists instead of four
+            // 2^(2k)-entry tables; the same round polynomials, hence the same bytes (tests/test_gpu_gkr.py compares both forms on every
+            // reference circuit).  Measured on Circuit::random(10): the two largest layers 760 + 400 us -> 300 + 280 us.
+            const size_t ng = n_gates[li];
+            const uint32_t* g_in0 = gate_in0 + gate_off;
+            const uint32_t* g_in1 = gate_in1 + gate_off;
+            // one staging buffer [W | row0 | gate0 | row1 | gate1 | in0 | in1 | type], one copy
+            const size_t n_u32 = 2 * (nw + 1) + 4 * ng, bytes_total = nw * sizeof(Fr) + n_u32 * 4 + ng;
+            const size_t hsz = (size_t)1 << ((k + 1) / 2), n_scratch = std::max<size_t>(ng, 2) + 6 * hsz;
+            if (ctx->gkr_stage_cap * sizeof(uint64_t) < bytes_total + 64) {
+                CK(cudaStreamSynchronize(ctx->stream));
+                if (ctx->gkr_stage) cudaFreeHost(ctx->gkr_stage);
+                ctx->gkr_stage = nullptr; ctx->gkr_stage_cap = 0;
+                CK(cudaHostAlloc((void**)&ctx->gkr_stage, 2 * (bytes_total + 64), cudaHostAllocDefault));
+                ctx->gkr_stage_cap = 2 * (bytes_total + 64) / sizeof(uint64_t);
+            }
+            uint8_t* stage = (uint8_t*)ctx->gkr_stage;       // free again: the previous layer ended with a stream synchronisation
+            memcpy(stage, layer_values[li + 1], nw * sizeof(Fr));
+            uint32_t* row0 = (uint32_t*)(stage + nw * sizeof(Fr));
+            uint32_t *gate0 = row0 + nw + 1, *row1 = gate0 + ng, *gate1 = row1 + nw + 1, *s_in0 = gate1 + ng, *s_in1 = s_in0 + ng;
+            uint8_t* s_type = (uint8_t*)(s_in1 + ng);
+            memset(row0, 0, (nw + 1) * 4);
+            memset(row1, 0, (nw + 1) * 4);
+            for (size_t g = 0; g < ng; g++) { row0[g_in0[g] + 1]++; row1[g_in1[g] + 1]++; }
+            for (size_t w = 0; w < nw; w++) { row0[w + 1] += row0[w]; row1[w + 1] += row1[w]; }
+            {
+                std::vector<uint32_t> q0(row0, row0 + nw), q1(row1, row1 + nw);
+                for (size_t g = 0; g < ng; g++) { gate0[q0[g_in0[g]]++] = (uint32_t)g; gate1[q1[g_in1[g]]++] = (uint32_t)g; }
+            }
+            memcpy(s_in0, g_in0, ng * 4);
+            memcpy(s_in1, g_in1, ng * 4);
+            memcpy(s_type, gate_type + gate_off, ng);
+            DevBuf dbuf(ctx), scratch(ctx);
+            CK(dev_alloc(ctx, (void**)&dbuf.p, bytes_total + 64));
+            CK(dev_alloc(ctx, (void**)&scratch.p, n_scratch * sizeof(Fr)));
+            CK(cudaMemcpyAsync(dbuf.p, stage, bytes_total, cudaMemcpyHostToDevice, ctx->stream));
+            GkrLayerDev l;
+            uint8_t* d = (uint8_t*)dbuf.p + nw * sizeof(Fr);
+            l.row0 = (unsigned int*)d; l.gate0 = l.row0 + nw + 1; l.row1 = l.gate0 + ng; l.gate1 = l.row1 + nw + 1; l.in0 = l.gate1 + ng; l.in1 = l.in0 + ng;
+            l.type = (unsigned char*)(l.in1 + ng);
+            zksc_tables* t = nullptr;
+            TRY(tables_alloc(ctx, k, 1, 2, degs, &t));
+            struct Guard { zksc_tables* t; ~Guard() { if (t) zksc_tables_free(t); } } guard{t};
+            store_h(sums + 4 * li, claimed);
+            uint64_t* msgs = round_msgs + round_off * stride * 4;
+            uint32_t* lens = round_len + round_off;
+            uint64_t* chal = challenges + round_off * 4;
+            FrH wu, wv;
+            TRY(gkr_two_phase_layer(ctx, l, dbuf.p, k, ng, r_b, li > 0 ? &r_c : nullptr, alpha, beta, scratch.p, scratch.p + std::max<size_t>(ng, 2), hsz, t, claimed, stride,
+                                    msgs, lens, chal, &wu, &wv, nullptr));
+            const auto p2 = std::chrono::steady_clock::now();
+            size_t blen = 0;
+            TRY(zksc_proof_to_bytes(ZKSC_PROTO_MULTI_PARTIAL, n, stride, msgs, lens, nullptr, &blen));
+            bytes.resize(blen);
+            TRY(zksc_proof_to_bytes(ZKSC_PROTO_MULTI_PARTIAL, n, stride, msgs, lens, bytes.data(), &blen));
+            transcript.commit(bytes);
+            r_b.clear(); r_c.clear();
+            for (uint32_t j = 0; j < k; j++) { r_b.push_back(load_h(chal + 4 * j)); r_c.push_back(load_h(chal + 4 * (k + j))); }
+            store_h(wb_s + 4 * li, wu);
+            store_h(wc_s + 4 * li, wv);
+            alpha = transcript.evaluate_challenge_into_field();
+            beta = transcript.evaluate_challenge_into_field();
+            claimed = host::add(host::mul(alpha, wu), host::mul(beta, wv));
+            round_off += n;
+            gate_off += n_gates[li];
+            if (ctx->profile) {
+                auto us = [](auto a, auto b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+                fprintf(stderr, "[zksc profile] gkr layer %2u (two-phase form): tables + prove %7.1f us  absorb %7.1f us\n", li, us(p0, p2), us(p2, std::chrono::steady_clock::now()));
+            }
+            continue;
+        }
         // wiring entries: layer one add(n_r, b, c) unscaled (utils.rs:23-24); later alpha add(r_b,.,.) + beta add(r_c,.,.) (protocol.rs:86-88)
         idx_add.clear(); idx_mul.clear(); val_add.clear(); val_mul.clear();
         {

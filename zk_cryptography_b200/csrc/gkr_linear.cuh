@@ -145,12 +145,7 @@ struct zksc_circuit {
     zksc_ctx* ctx = nullptr;
     uint32_t n_layers = 0;
     std::vector<uint32_t> lw;                 // [n_layers + 1] log2 of the layer widths; layer n_layers = the inputs
-    struct Layer {
-        unsigned char* type = nullptr;        // [gates]
-        unsigned int *in0 = nullptr, *in1 = nullptr;                 // [gates]
-        unsigned int *row0 = nullptr, *gate0 = nullptr;              // gates grouped by first input: [wires + 1], [gates]
-        unsigned int *row1 = nullptr, *gate1 = nullptr;              // ... by second input
-    };
+    typedef GkrLayerDev Layer;                // (gkr_driver.cuh: gate arrays and the two CSR orders of a layer, in HBM)
     std::vector<Layer> layers;
     std::vector<Fr*> values;                  // [n_layers + 1] layer values in HBM (zksc_circuit_evaluate)
     bool evaluated = false;
@@ -282,6 +277,67 @@ static zksc::EqPoint gkr_eq_point(const std::vector<FrH>& r) {
 // GKRProtocol::prove (gkr/src/protocol.rs:21-113) for the layered circuit `c` on the values of the latest zksc_circuit_evaluate.  Outputs as
 // zksc_gkr_prove's: w0 (max(2, width of layer 0) elements: the output layer, a single output padded with 0 as protocol.rs:31-34 does), and per layer
 // the claimed sum, W(b*), W(c*), and the rounds of its sumcheck (zksc_circuit_total_rounds in all; message stride zksc_msg_stride(MULTI_PARTIAL, 2, {2,2})).
+// One layer sumcheck in two phases (see the head of this file) on the handle `t` (k variables, two degree-2 products): 2k rounds on one
+// transcript, written to msgs / lens / chal like zksc_prove's; W(u) and W(v) come back as the residuals of the two phases.
+// r_c == nullptr: the output layer's single point (wgt = eq(r_b, .), utils.rs:23-24), else wgt = alpha eq(r_b, .) + beta eq(r_c, .).
+// wgt: ng elements of scratch; eq_half: six half tables of hsz elements each (hsz >= 2^ceil(max(k, |r_b|) / 2)).
+static int gkr_two_phase_layer(zksc_ctx* ctx, const GkrLayerDev& l, const Fr* d_w, uint32_t k, unsigned long long ng, const std::vector<FrH>& r_b,
+                               const std::vector<FrH>* r_c, const FrH& alpha, const FrH& beta, Fr* wgt, Fr* eq_half, size_t hsz, zksc_tables* t, const FrH& claimed,
+                               uint32_t stride, uint64_t* msgs, uint32_t* lens, uint64_t* chal, FrH* wu_out, FrH* wv_out, double* prof) {
+    const unsigned long long nw = 1ull << k;
+    const auto p0 = std::chrono::steady_clock::now();
+    auto us_since = [](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - a).count(); };
+    auto halves = [&](const std::vector<FrH>& r, const FrH& scale, int slot) {
+        const zksc::EqPoint p = gkr_eq_point(r);
+        Fr sc;
+        store_h((uint64_t*)sc.l, scale);
+        const unsigned int kl = p.k / 2, kh = p.k - kl;
+        zksc::gkr_eq_halves_kernel<<<((1u << kh) + 255) / 256, 256, 0, ctx->stream>>>(p, sc, eq_half + (2 * slot) * hsz, eq_half + (2 * slot + 1) * hsz);
+        ctx->launches++;
+        return zksc::EqHalves{eq_half + (2 * slot) * hsz, eq_half + (2 * slot + 1) * hsz, kl};
+    };
+    {
+        const zksc::EqHalves hb = halves(r_b, alpha, 0), hc = r_c ? halves(*r_c, beta, 1) : hb;
+        zksc::gkr_wgt_kernel<<<grid_for(ctx, ng, 256, 8), 256, 0, ctx->stream>>>(hb, hc, r_c ? 1 : 0, wgt, ng);
+    }
+    // ---- phase 1: the k rounds that bind b
+    TRY(zksc_tables_reset(t));
+    zksc::gkr_phase1_kernel<<<grid_for(ctx, nw, 256, 8), 256, 0, ctx->stream>>>(l.row0, l.gate0, l.type, l.in1, wgt, d_w, t->orig, nw);
+    ctx->launches += 2;
+    CK(cudaGetLastError());
+    t->r0_valid = false;
+    std::vector<host::FiatShamirTranscript> tr(1);
+    tr[0].commit_field(claimed);                                          // multi_composed_sumcheck.rs:70
+    // prove_run indexes its outputs by (proof * n + round) with the handle's own round count: this proof has 2k rounds, so the two runs
+    // are given the layer's slots directly
+    TRY(prove_run(t, ZKSC_PROTO_MULTI_PARTIAL, tr, k, 0, stride, msgs, lens, chal));
+    if (prof) prof[0] = us_since(p0);
+    uint64_t resid[16];
+    TRY(zksc_residual(t, resid));                                         // W(u), H1(u), H2(u), 1
+    if (prof) prof[1] = us_since(p0);
+    const FrH wu = load_h(resid);
+    std::vector<FrH> u(k);
+    for (uint32_t j = 0; j < k; j++) u[j] = load_h(chal + 4 * j);
+    // ---- phase 2: the k rounds that bind c
+    {
+        Fr wu_m;
+        store_h((uint64_t*)wu_m.l, wu);
+        const zksc::EqHalves hu = halves(u, host::kOne, 2);
+        TRY(zksc_tables_reset(t));
+        zksc::gkr_phase2_kernel<<<grid_for(ctx, nw, 256, 8), 256, 0, ctx->stream>>>(l.row1, l.gate1, l.type, l.in0, wgt, hu, d_w, wu_m, t->orig, nw);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        t->r0_valid = false;
+    }
+    TRY(prove_run(t, ZKSC_PROTO_MULTI_PARTIAL, tr, k, 0, stride, msgs + (size_t)k * stride * 4, lens + k, chal + (size_t)k * 4));
+    if (prof) prof[2] = us_since(p0);
+    TRY(zksc_residual(t, resid));                                         // A(v), W(u) + W(v), W(u) M(v), W(v)
+    if (prof) prof[3] = us_since(p0);
+    *wu_out = wu;
+    *wv_out = load_h(resid + 12);
+    return ZKSC_OK;
+}
+
 extern "C" int zksc_gkr_prove_linear(zksc_circuit* c, uint64_t* w0, uint64_t* sums, uint64_t* wb_s, uint64_t* wc_s, uint64_t* round_msgs, uint32_t* round_len,
                                      uint64_t* challenges) {
     if (!c) return ZKSC_ERR_STATE;
@@ -338,70 +394,26 @@ extern "C" int zksc_gkr_prove_linear(zksc_circuit* c, uint64_t* w0, uint64_t* su
     memset(round_msgs, 0, (size_t)zksc_circuit_total_rounds(c) * stride * 32);
     ctx->round_us.assign((size_t)zksc_circuit_total_rounds(c), 0.0);
     std::vector<uint8_t> bytes;
-    std::vector<host::FiatShamirTranscript> tr(1);
     size_t round_off = 0;
     for (uint32_t li = 0; li < L; li++) {
         const uint32_t ka = std::max(c->lw[li], 1u), k = c->lw[li + 1], n = 2 * k;
-        const unsigned long long ng = 1ull << c->lw[li], nw = 1ull << k;
+        const unsigned long long ng = 1ull << c->lw[li];
         const zksc_circuit::Layer& l = c->layers[li];
         if (r_b.size() != ka) FAIL(ZKSC_ERR_STATE, "challenge vector does not match the layer's gate-label bits");
         const auto p0 = std::chrono::steady_clock::now();
         zksc_tables*& t = c->handles[k];
         if (!t) TRY(tables_alloc(ctx, k, 1, 2, degs, &t));
-        // wgt(g) = alpha eq(r_b, g) + beta eq(r_c, g); the output layer: eq(n_r, g) (utils.rs:23-24, protocol.rs:86-88)
-        const size_t hsz = (size_t)1 << zksc::kEqHalfMax;
-        auto halves = [&](const std::vector<FrH>& r, const FrH& scale, int slot) {
-            const zksc::EqPoint p = gkr_eq_point(r);
-            Fr sc;
-            store_h((uint64_t*)sc.l, scale);
-            const unsigned int kl = p.k / 2, kh = p.k - kl;
-            zksc::gkr_eq_halves_kernel<<<((1u << kh) + 255) / 256, 256, 0, ctx->stream>>>(p, sc, c->eq_half + (2 * slot) * hsz, c->eq_half + (2 * slot + 1) * hsz);
-            ctx->launches++;
-            return zksc::EqHalves{c->eq_half + (2 * slot) * hsz, c->eq_half + (2 * slot + 1) * hsz, kl};
-        };
-        {
-            const zksc::EqHalves hb = halves(r_b, alpha, 0), hc = li > 0 ? halves(r_c, beta, 1) : hb;
-            zksc::gkr_wgt_kernel<<<grid_for(ctx, ng, 256, 8), 256, 0, ctx->stream>>>(hb, hc, li > 0 ? 1 : 0, c->wgt, ng);
-        }
-        // ---- phase 1: the k rounds that bind b
-        TRY(zksc_tables_reset(t));
-        zksc::gkr_phase1_kernel<<<grid_for(ctx, nw, 256, 8), 256, 0, ctx->stream>>>(l.row0, l.gate0, l.type, l.in1, c->wgt, c->values[li + 1], t->orig, nw);
-        ctx->launches += 2;
-        CK(cudaGetLastError());
-        t->r0_valid = false;
         store_h(sums + 4 * li, claimed);
         uint64_t* msgs = round_msgs + round_off * stride * 4;
         uint32_t* lens = round_len + round_off;
         uint64_t* chal = challenges + round_off * 4;
-        tr[0] = host::FiatShamirTranscript();
-        tr[0].commit_field(claimed);                                          // multi_composed_sumcheck.rs:70
-        // prove_run indexes its outputs by (proof * n + round) with the handle's own round count: this proof has n = 2k rounds, so the two runs
-        // are given the layer's slots directly
-        TRY(prove_run(t, ZKSC_PROTO_MULTI_PARTIAL, tr, k, 0, stride, msgs, lens, chal));
-        const double t_ph1 = us_since(p0);
-        uint64_t resid[16];
-        TRY(zksc_residual(t, resid));                                         // W(u), H1(u), H2(u), 1
-        const double t_res1 = us_since(p0);
-        const FrH wu = load_h(resid);
+        FrH wu, wv;
+        double prof[4] = {0, 0, 0, 0};
+        TRY(gkr_two_phase_layer(ctx, l, c->values[li + 1], k, ng, r_b, li > 0 ? &r_c : nullptr, alpha, beta, c->wgt, c->eq_half, (size_t)1 << zksc::kEqHalfMax, t, claimed,
+                                stride, msgs, lens, chal, &wu, &wv, prof));
+        const double t_ph1 = prof[0], t_res1 = prof[1], t_ph2 = prof[2], t_res2 = prof[3];
         std::vector<FrH> u(k), v(k);
-        for (uint32_t j = 0; j < k; j++) u[j] = load_h(chal + 4 * j);
-        // ---- phase 2: the k rounds that bind c
-        {
-            Fr wu_m;
-            store_h((uint64_t*)wu_m.l, wu);
-            const zksc::EqHalves hu = halves(u, host::kOne, 2);
-            TRY(zksc_tables_reset(t));
-            zksc::gkr_phase2_kernel<<<grid_for(ctx, nw, 256, 8), 256, 0, ctx->stream>>>(l.row1, l.gate1, l.type, l.in0, c->wgt, hu, c->values[li + 1], wu_m, t->orig, nw);
-            ctx->launches++;
-            CK(cudaGetLastError());
-            t->r0_valid = false;
-        }
-        TRY(prove_run(t, ZKSC_PROTO_MULTI_PARTIAL, tr, k, 0, stride, msgs + (size_t)k * stride * 4, lens + k, chal + (size_t)k * 4));
-        const double t_ph2 = us_since(p0);
-        TRY(zksc_residual(t, resid));                                         // A(v), W(u) + W(v), W(u) M(v), W(v)
-        const double t_res2 = us_since(p0);
-        const FrH wv = load_h(resid + 12);
-        for (uint32_t j = 0; j < k; j++) v[j] = load_h(chal + 4 * (k + j));
+        for (uint32_t j = 0; j < k; j++) { u[j] = load_h(chal + 4 * j); v[j] = load_h(chal + 4 * (k + j)); }
         // transcript.commit(&proof.to_bytes()); W(b*), W(c*); alpha, beta                                    protocol.rs:93-113
         size_t blen = 0;
         TRY(zksc_proof_to_bytes(ZKSC_PROTO_MULTI_PARTIAL, n, stride, msgs, lens, nullptr, &blen));

@@ -213,6 +213,7 @@ struct zksc_ctx {
     bool tail_enabled = true;            // ZKSC_NO_TAIL=1: every round is its own launch
     unsigned int dyn_max_groups = 8;     // ZKSC_DYN_MAX_GROUPS (<= kDynMaxGroups): most groups of a launch that takes its chunks from counters
     bool round_dynamic = true;           // ZKSC_ROUND_STATIC=1: the round kernels split a round by a fixed stride (kernels.cuh RoundBase::dynamic)
+    uint32_t gkr_linear_min = 9;         // ZKSC_GKR_LINEAR_MIN: zksc_gkr_prove's layers with at least this many bits per input label use the two-phase form
     bool tail_prelaunch = true;          // ZKSC_NO_PRELAUNCH=1: the resident kernel is launched in its first round, not behind the launch of the round before
     bool tail_dynamic = true;            // ZKSC_RES_STATIC=1: the resident kernel splits every round by a fixed stride (no work counter)
     unsigned long long tail_work = kTailWorkDefault;   // start threshold of the resident kernel (ZKSC_TAIL_WORK overrides, experiments)
@@ -404,6 +405,7 @@ extern "C" int zksc_ctx_create(int device, zksc_ctx** out) {
     { const char* e_ = getenv("ZKSC_NO_TAIL"); ctx->tail_enabled = !(e_ && e_[0] == '1'); }
     { const char* e_ = getenv("ZKSC_RES_STATIC"); ctx->tail_dynamic = !(e_ && e_[0] == '1'); }
     { const char* e_ = getenv("ZKSC_NO_PRELAUNCH"); ctx->tail_prelaunch = !(e_ && e_[0] == '1'); }
+    { const char* e_ = getenv("ZKSC_GKR_LINEAR_MIN"); if (e_) ctx->gkr_linear_min = (uint32_t)strtoul(e_, nullptr, 10); }
     { const char* e_ = getenv("ZKSC_ROUND_STATIC"); ctx->round_dynamic = !(e_ && e_[0] == '1'); }
     { const char* e_ = getenv("ZKSC_DYN_MAX_GROUPS"); if (e_) ctx->dyn_max_groups = std::min<unsigned int>(kDynMaxGroups, (unsigned int)strtoul(e_, nullptr, 10)); }
     { const char* e_ = getenv("ZKSC_NO_FUSE"); ctx->fuse_products = !(e_ && e_[0] == '1'); }
