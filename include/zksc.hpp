@@ -634,5 +634,101 @@ struct GKRProtocol {
     }
 };
 
+// ---- layered circuits of any power-of-two widths, proved in time linear in their gates (zksc_circuit_*, zksc_gkr_prove_linear) ----
+// BASELINE config 4 as written ("width 2^20, depth 8").  `Circuit` above, like the reference's, holds only the pyramid shape; on a
+// pyramid `LayeredCircuit::prove` returns the GKRProof of GKRProtocol::prove, byte for byte, and `verify` is GKRProtocol::verify
+// (protocol.rs:115-195) with the wiring polynomials taken from the gate lists on the device (zksc_circuit_wiring_eval).
+class LayeredCircuit {
+   public:
+    // log_width[i] = log2(gates of layer i), output layer first, last entry = log2(inputs); layers[i] = the gates of layer i
+    LayeredCircuit(std::vector<uint32_t> log_width, const std::vector<CircuitLayer>& layers) : lw_(std::move(log_width)) {
+        if (lw_.size() != layers.size() + 1) throw Error(ZKSC_ERR_SHAPE, "one width per layer plus the input layer");
+        std::vector<uint32_t> in0, in1;
+        std::vector<uint8_t> type;
+        for (size_t i = 0; i < layers.size(); i++) {
+            if (layers[i].layer.size() != (size_t(1) << lw_[i])) throw Error(ZKSC_ERR_SHAPE, "a layer must have 2^log_width gates");
+            for (const Gate& g : layers[i].layer) {
+                type.push_back(g.gate_type == GateType::Add ? 0 : 1);
+                in0.push_back((uint32_t)g.inputs[0]);
+                in1.push_back((uint32_t)g.inputs[1]);
+            }
+        }
+        Context::check(zksc_circuit_create(Context::get(), (uint32_t)layers.size(), lw_.data(), type.data(), in0.data(), in1.data(), &h_));
+    }
+    static LayeredCircuit from_circuit(const Circuit& c) {
+        std::vector<uint32_t> lw;
+        for (uint32_t i = 0; i <= c.layers.size(); i++) lw.push_back(i);
+        return LayeredCircuit(lw, c.layers);
+    }
+    LayeredCircuit(const LayeredCircuit&) = delete;
+    LayeredCircuit& operator=(const LayeredCircuit&) = delete;
+    LayeredCircuit(LayeredCircuit&& o) noexcept : lw_(std::move(o.lw_)), h_(o.h_) { o.h_ = nullptr; }
+    ~LayeredCircuit() { if (h_) zksc_circuit_free(h_); }
+
+    // Circuit::evaluation (circuit.rs:32-55) on the device: returns the output layer, every layer stays in HBM for prove()
+    std::vector<Fr> evaluate(const std::vector<Fr>& input) {
+        if (input.size() != (size_t(1) << lw_.back())) throw Error(ZKSC_ERR_SHAPE, "the input layer has 2^log_width values");
+        std::vector<Fr> out(size_t(1) << lw_[0]);
+        Context::check(zksc_circuit_evaluate(h_, raw(input), raw(out)));
+        return out;
+    }
+    GKRProof prove() {
+        const uint32_t L = (uint32_t)lw_.size() - 1;
+        const size_t rounds = zksc_circuit_total_rounds(h_);
+        std::vector<Fr> w0(std::max<size_t>(2, size_t(1) << lw_[0])), sums(L), wb(L), wc(L), msgs(rounds * 6 + 1), chal(rounds + 1);
+        std::vector<uint32_t> lens(rounds + 1);
+        Context::check(zksc_gkr_prove_linear(h_, raw(w0), raw(sums), raw(wb), raw(wc), raw(msgs), lens.data(), raw(chal)));
+        GKRProof proof;
+        proof.w_0_mle = Multilinear::new_(w0);
+        proof.wb_s = wb;
+        proof.wc_s = wc;
+        size_t off = 0;
+        for (uint32_t li = 0; li < L; li++) {
+            detail::Rounds r;
+            r.n = 2 * lw_[li + 1];
+            r.stride = 6;
+            r.msgs.assign(msgs.begin() + off * 6, msgs.begin() + (off + r.n) * 6);
+            r.lens.assign(lens.begin() + off, lens.begin() + off + r.n);
+            proof.sumcheck_proofs.push_back(detail::proof_of(r, sums[li]));
+            off += r.n;
+        }
+        return proof;
+    }
+    bool verify(const std::vector<Fr>& input, const GKRProof& proof) {
+        const size_t L = lw_.size() - 1;
+        if (proof.sumcheck_proofs.size() != L || proof.wb_s.size() != L || proof.wc_s.size() != L) return false;
+        FiatShamirTranscript transcript;
+        transcript.commit(proof.w_0_mle.to_bytes());
+        std::vector<Fr> r_b = transcript.evaluate_n_challenge_into_field(proof.w_0_mle.n_vars), r_c;
+        Fr claimed_sum = proof.w_0_mle.evaluation(r_b);
+        Fr alpha = Fr::one(), beta = Fr::zero();
+        for (size_t i = 0; i < L; i++) {
+            const ComposedSumcheckProof& p = proof.sumcheck_proofs[i];
+            if (claimed_sum != p.sum) return false;
+            transcript.commit(p.to_bytes());
+            auto sub = MultiComposedSumcheckVerifier::verify_partial(p);
+            if (!sub.is_ok()) return false;
+            const auto& ch = sub.unwrap().challenges;
+            if (ch.size() != 2 * (size_t)lw_[i + 1]) return false;
+            const std::vector<Fr> b(ch.begin(), ch.begin() + ch.size() / 2), c(ch.begin() + ch.size() / 2, ch.end());
+            Fr wiring[2];
+            Context::check(zksc_circuit_wiring_eval(h_, (uint32_t)i, raw(r_b), alpha.v, i ? raw(r_c) : nullptr, i ? beta.v : nullptr, raw(b), raw(c), wiring[0].v));
+            const Fr wb = proof.wb_s[i], wc = proof.wc_s[i];
+            if (wiring[0] * (wb + wc) + wiring[1] * (wb * wc) != sub.unwrap().sum) return false;
+            alpha = transcript.evaluate_challenge_into_field();
+            beta = transcript.evaluate_challenge_into_field();
+            claimed_sum = alpha * wb + beta * wc;
+            r_b = b;
+            r_c = c;
+        }
+        const Multilinear w_mle_input = Multilinear::new_(input);
+        return claimed_sum == alpha * w_mle_input.evaluation(r_b) + beta * w_mle_input.evaluation(r_c);
+    }
+
+   private:
+    std::vector<uint32_t> lw_;
+    zksc_circuit* h_ = nullptr;
+};
+
 }  // namespace zk
 #endif  // ZKSC_HPP

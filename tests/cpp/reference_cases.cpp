@@ -185,6 +185,37 @@ static void gkr_case(const char* name, const Circuit& circuit, const std::vector
     GKRProof bad = proof;
     bad.wb_s.back() = bad.wb_s.back() + Fr::one();
     CHECK(!GKRProtocol::verify(circuit, input, bad));
+    // the linear-time prover for layered circuits of any widths gives the same proof on the reference's pyramid circuits, and its
+    // verifier (wiring polynomials from the gate lists on the device) agrees with GKRProtocol::verify
+    LayeredCircuit lc = LayeredCircuit::from_circuit(circuit);
+    CHECK(lc.evaluate(input) == evaluation[0]);
+    GKRProof lin = lc.prove();
+    CHECK(lin.sumcheck_proofs.size() == proof.sumcheck_proofs.size());
+    for (size_t i = 0; i < lin.sumcheck_proofs.size() && i < proof.sumcheck_proofs.size(); i++) CHECK(lin.sumcheck_proofs[i].to_bytes() == proof.sumcheck_proofs[i].to_bytes());
+    CHECK(lin.wb_s == proof.wb_s && lin.wc_s == proof.wc_s);
+    CHECK(lc.verify(input, lin));
+    CHECK(!lc.verify(input, bad));
+}
+static void test_layered_uniform() {
+    // a uniform-width circuit (2^5 gates in every layer, 3 layers): the reference's Circuit cannot hold it
+    std::vector<CircuitLayer> layers;
+    uint64_t x = 88172645463325252ull;
+    auto next = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
+    for (int li = 0; li < 3; li++) {
+        CircuitLayer l;
+        for (int g = 0; g < 32; g++) l.layer.push_back(Gate{(next() & 1) ? GateType::Mul : GateType::Add, {size_t(next() % 32), size_t(next() % 32)}});
+        layers.push_back(l);
+    }
+    std::vector<Fr> input;
+    for (uint64_t i = 0; i < 32; i++) input.push_back(Fr::from(0xD1B54A32D192ED03ull * (i + 1)));
+    LayeredCircuit lc({5, 5, 5, 5}, layers);
+    std::vector<Fr> host = Circuit::new_(layers).evaluation(input)[0];
+    CHECK(lc.evaluate(input) == host);
+    GKRProof proof = lc.prove();
+    CHECK(proof.sumcheck_proofs.size() == 3 && proof.sumcheck_proofs[0].round_polys.size() == 10);
+    CHECK(lc.verify(input, proof));
+    proof.wc_s[1] = proof.wc_s[1] + Fr::one();
+    CHECK(!lc.verify(input, proof));
 }
 static void test_gkr() {
     using G = Gate;
@@ -217,7 +248,7 @@ int main() {
         test_composed_sumcheck();
         test_multi_composed_sumcheck();
         // (the GKR driver runs on single-device contexts: its layer tables are far below the size where sharding pays)
-        if (zksc_ctx_devices(Context::get()) == 1) test_gkr();
+        if (zksc_ctx_devices(Context::get()) == 1) { test_gkr(); test_layered_uniform(); }
     } catch (const Error& e) {
         std::fprintf(stderr, "zk::Error %d: %s\n", e.code, e.what());
         return 2;
