@@ -28,6 +28,16 @@ def test_reference_arm_line(built):
     assert d["config"]["workload"].startswith("c2")
 
 
+@pytest.mark.parametrize("workload", ["c4", "c4b"])
+def test_reference_arm_gkr_workloads(built, workload):
+    """the GKR workloads' reference arm: the oracle's (dense) GKR driver on a bounded sample of the same circuit family"""
+    r = run_bench(["--impl", "reference", "--workload", workload, "--steps", "1", "--warmup", "0"])
+    assert r.returncode == 0, r.stderr[-1500:]
+    d = json.loads([l for l in r.stdout.strip().splitlines() if l.startswith("{")][0])
+    assert d["impl"] == "reference" and d["unit"] == "evals/s" and d["value"] > 0
+    assert d["config"]["workload"].startswith(workload + ":") and d["cpu_baseline"]["kind"] == "port"
+
+
 def test_reference_arm_other_ranks_stay_silent(built):
     r = run_bench(["--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0", "--cpu-n", "12"], {"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
     assert r.returncode == 0 and r.stdout.strip() == ""
