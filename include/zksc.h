@@ -280,8 +280,16 @@ int zksc_ml_elementwise(zksc_ctx* ctx, int op, const uint64_t* a, const uint64_t
  *   evaluation_form.rs:86-96,112-119) is committed, and the polynomial is replaced by its remainder partial_evaluation(point, 0)
  *   (get_poly_remainder, utils.rs:5-10).  evals: 2^n_vars elements; points: n_vars elements; srs_g1: 2^n_vars x 18;
  *   out_evaluation: 1 element (= poly.evaluation(points)); out_proofs: n_vars x 18.
- * The pairing check of MultilinearKZG::verify is host-side work on n + 1 single points: a Rust caller keeps ark-ec's pairing; the Python
- * mirror carries its own (zk_cryptography_b200/pairing.py).  No C-ABI entry point: nothing of it runs on the device. */
+ * The pairing check of MultilinearKZG::verify is host-side work on n + 1 single points: zksc_pairing_check below (a Rust caller may as well
+ * keep ark-ec's pairing).  Nothing of it runs on the device. */
+/* The verifier's pairing equation on the host (csrc/host_pairing.hpp; no device work, no context): is prod_i e(P_i, Q_i) == 1 ?
+ * g1: n x 12 u64 = affine (x, y); g2: n x 24 u64 = affine (x.c0, x.c1, y.c0, y.c1); canonical little-endian limbs, all zero = the identity.
+ * MultilinearKZG::verify (multilinear_kzg.rs:90-116, sum_pairing_results kzg/src/utils.rs:42-61) is
+ *   e(C - v g1, -g2) * prod_i e(proof_i, tau_i g2 - z_i g2) == 1.
+ * ZKSC_ERR_SHAPE for a coordinate >= p or a point off its curve; subgroup membership is not checked (ark-ec's unchecked forms).
+ * zksc_pairing: e(P, Q) itself as 12 Fq coefficients (72 u64, canonical) in tower order -- for cross-checks. */
+int zksc_pairing_check(const uint64_t* g1, const uint64_t* g2, uint32_t n, int* is_one);
+int zksc_pairing(const uint64_t* g1, const uint64_t* g2, uint64_t* out);
 int zksc_g1_msm(zksc_ctx* ctx, const uint64_t* scalars, const uint64_t* points, uint64_t n, uint64_t* out);
 int zksc_kzg_open(zksc_ctx* ctx, const uint64_t* evals, uint32_t n_vars, const uint64_t* points, const uint64_t* srs_g1, uint64_t* out_evaluation,
                   uint64_t* out_proofs);

@@ -29,6 +29,23 @@ def test_generators_and_bilinearity():
     assert pr.pairing(None, pr.G2) == pr.F12_ONE
 
 
+def test_native_pairing_is_the_python_pairing(built):
+    """csrc/host_pairing.hpp through the C ABI (zksc_pairing, zksc_pairing_check; host code, no GPU) against pairing.py: the same
+    element of Fq12 coefficient by coefficient, the same decisions, identities, rejected inputs"""
+    a, b = 0x1234567890ABCDEF, 0x0FEDCBA987654321
+    pa, qb = pr.g1_mul(a, pr.G1), pr.g2_mul(b, pr.G2)
+    assert pr.native_pairing(pa, qb) == pr.pairing(pa, qb)
+    assert pr.native_pairing(pr.G1, pr.G2) == pr.pairing(pr.G1, pr.G2)
+    assert pr.native_pairing_check([(pa, qb), (pr.g1_neg(pr.g1_mul(a * b % R, pr.G1)), pr.G2)]) is True
+    assert pr.native_pairing_check([(pa, qb), (pr.g1_neg(pr.g1_mul((a * b + 1) % R, pr.G1)), pr.G2)]) is False
+    assert pr.native_pairing_check([(None, pr.G2), (pr.G1, None)]) is True and pr.native_pairing_check([]) is True
+    assert pr.native_pairing_check([(pr.G1, pr.G2)]) is False
+    from zk_cryptography_b200 import ZkscError
+    for bad in ([((1, 2), pr.G2)], [(pr.G1, ((1, 0), (2, 0)))], [((pr.P, 0), pr.G2)]):
+        with pytest.raises(ZkscError):
+            pr.native_pairing_check(bad)
+
+
 @pytest.mark.parametrize("prover,tampered,verifier,ev", [
     ([2, 3, 4], [2, 13, 4], [5, 9, 6], [0, 7, 0, 5, 0, 7, 4, 9]),                                                          # test_kzg_1
     ([12, 9, 28, 40], [12, 19, 28, 40], [54, 90, 76, 160], [0, 0, 0, 2, 0, 0, 10, 12, 0, -12, 4, -6, 0, -12, 14, 4]),      # test_kzg_2
@@ -40,6 +57,8 @@ def test_reference_kzg_verify(prover, tampered, verifier, ev):
     v, proofs = k.open_(ev, verifier, model)
     proof = MultilinearKZGProof(v, np.stack([k.to_ark(p) for p in proofs]))
     assert MultilinearKZG.verify(commit, verifier, proof, srs_for(model)) is True
+    assert MultilinearKZG.verify(commit, verifier, proof, srs_for(model), native=False) is True               # the same through pairing.py's integers
     assert MultilinearKZG.verify(commit, verifier, proof, srs_for(k.TrustedSetup(tampered))) is False         # tampered_tau_verify_status == false
+    assert MultilinearKZG.verify(commit, verifier, proof, srs_for(k.TrustedSetup(tampered)), native=False) is False
     assert MultilinearKZG.verify(commit, verifier, MultilinearKZGProof((v + 1) % R, proof.proofs), srs_for(model)) is False
     assert MultilinearKZG.verify(k.add(commit, k.G1), verifier, proof, srs_for(model)) is False

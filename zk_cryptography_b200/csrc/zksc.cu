@@ -26,6 +26,7 @@
 #include <vector>
 
 #include "host_field.hpp"
+#include "host_pairing.hpp"
 #include "aux_kernels.cuh"
 #include "kernels.cuh"
 #include "resident_kernel.cuh"
@@ -2701,4 +2702,70 @@ extern "C" void zksc_synth_entry(uint64_t seed, uint64_t table, uint64_t index, 
     uint64_t c[4];
     for (int limb = 0; limb < 4; limb++) c[limb] = h_splitmix64(base + (index * 4 + limb) * 0x9E3779B97F4A7C15ull);
     store_h(out, host::from_canonical(c));
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// BLS12-381 pairing check on the host (host_pairing.hpp): the verifier half of the multilinear KZG / succinct GKR
+// ------------------------------------------------------------------------------------------------
+namespace {
+namespace pr = zksc::pairing;
+bool load_fq(const uint64_t* c, pr::Fq* out) {
+    if (pr::geq_p(c)) return false;
+    *out = pr::from_canonical(c);
+    return true;
+}
+// affine points as canonical little-endian limbs; all-zero coordinates = the identity.  false: a coordinate >= p or a point off its curve.
+bool load_g1(const uint64_t* c, pr::G1Affine* p) {
+    bool zero = true;
+    for (int i = 0; i < 12; i++) zero = zero && c[i] == 0;
+    p->infinity = zero;
+    if (zero) return true;
+    if (!load_fq(c, &p->x) || !load_fq(c + 6, &p->y)) return false;
+    const pr::Fq rhs = pr::add(pr::mul(pr::mul(p->x, p->x), p->x), pr::from_u64(4));
+    return pr::eq(pr::mul(p->y, p->y), rhs);
+}
+bool load_g2(const uint64_t* c, pr::G2Affine* q) {
+    bool zero = true;
+    for (int i = 0; i < 24; i++) zero = zero && c[i] == 0;
+    q->infinity = zero;
+    if (zero) return true;
+    if (!load_fq(c, &q->x.c0) || !load_fq(c + 6, &q->x.c1) || !load_fq(c + 12, &q->y.c0) || !load_fq(c + 18, &q->y.c1)) return false;
+    const pr::Fq four = pr::from_u64(4);
+    const pr::Fq2 b = {four, four};                                   // 4 (1 + u)
+    return pr::eq(pr::mul(q->y, q->y), pr::add(pr::mul(pr::mul(q->x, q->x), q->x), b));
+}
+}  // namespace
+
+// prod_i e(P_i, Q_i) == 1 ?   g1: n x 12 u64 (x, y), g2: n x 24 u64 (x.c0, x.c1, y.c0, y.c1): canonical little-endian limbs, all zero = the
+// identity.  The pairing equation of MultilinearKZG::verify (multilinear_kzg.rs:90-116) in the form  e(C - v g1, -g2) prod_i e(pi_i, tau_i g2 - z_i g2) == 1.
+// Points must lie on their curves (ZKSC_ERR_SHAPE otherwise); subgroup membership is the caller's business, as with ark-ec's unchecked types.
+extern "C" int zksc_pairing_check(const uint64_t* g1, const uint64_t* g2, uint32_t n, int* is_one) {
+    if (!is_one || (n && (!g1 || !g2))) return ZKSC_ERR_SHAPE;
+    pr::Fq12 f = pr::kOne12;
+    for (uint32_t i = 0; i < n; i++) {
+        pr::G1Affine p;
+        pr::G2Affine q;
+        if (!load_g1(g1 + 12 * (size_t)i, &p) || !load_g2(g2 + 24 * (size_t)i, &q)) return ZKSC_ERR_SHAPE;
+        f = pr::mul(f, pr::miller_loop(p, q));
+    }
+    *is_one = pr::eq(pr::final_exponentiation(f), pr::kOne12) ? 1 : 0;
+    return ZKSC_OK;
+}
+// e(P, Q) itself: 12 Fq coefficients, canonical limbs, in the order ((c0.c0.c0, c0.c0.c1), (c0.c1.*), (c0.c2.*), (c1.c0.*), ...) of the tower above
+extern "C" int zksc_pairing(const uint64_t* g1, const uint64_t* g2, uint64_t* out) {
+    if (!g1 || !g2 || !out) return ZKSC_ERR_SHAPE;
+    pr::G1Affine p;
+    pr::G2Affine q;
+    if (!load_g1(g1, &p) || !load_g2(g2, &q)) return ZKSC_ERR_SHAPE;
+    const pr::Fq12 e = pr::final_exponentiation(pr::miller_loop(p, q));
+    const pr::Fq6* h[2] = {&e.c0, &e.c1};
+    for (int a = 0; a < 2; a++) {
+        const pr::Fq2* t[3] = {&h[a]->c0, &h[a]->c1, &h[a]->c2};
+        for (int b = 0; b < 3; b++) {
+            pr::to_canonical(t[b]->c0, out + ((a * 3 + b) * 2) * 6);
+            pr::to_canonical(t[b]->c1, out + ((a * 3 + b) * 2 + 1) * 6);
+        }
+    }
+    return ZKSC_OK;
 }

@@ -49,9 +49,10 @@ class MultilinearKZG:
         return MultilinearKZGProof(ev, proofs)
 
     @staticmethod
-    def verify(commit, verifier_points, proof: MultilinearKZGProof, srs: TrustedSetup):  # multilinear_kzg.rs:90-116
+    def verify(commit, verifier_points, proof: MultilinearKZGProof, srs: TrustedSetup, native=True):  # multilinear_kzg.rs:90-116
         """e(commit - evaluation g1, g2) == sum_i e(proof_i, tau_i g2 - z_i g2)   (sum_pairing_results, kzg/src/utils.rs:42-61), checked
-        as one product of n + 1 Miller loops and a single final exponentiation."""
+        as one product of n + 1 Miller loops and a single final exponentiation -- by the library's host code (zksc_pairing_check,
+        csrc/host_pairing.hpp) or, native=False, by the Python integers of pairing.py (the cross-check of the tests)."""
         if srs.powers_of_tau_in_g2 is None:
             raise ZkscError(-3, "the trusted setup carries no G2 powers: cannot verify")
         proofs = np.ascontiguousarray(proof.proofs, dtype=np.uint64).reshape(-1, 18)
@@ -63,4 +64,4 @@ class MultilinearKZG:
         pairs = [(lhs_point, pairing.g2_neg(pairing.G2))]
         for i, z in enumerate(verifier_points):
             pairs.append((pairing.g1_from_ark(proofs[i]), pairing.g2_add(srs.powers_of_tau_in_g2[i], pairing.g2_neg(pairing.g2_mul(int(z), pairing.G2)))))
-        return pairing.multi_pairing(pairs) == pairing.F12_ONE
+        return pairing.native_pairing_check(pairs) if native else pairing.multi_pairing(pairs) == pairing.F12_ONE
