@@ -289,6 +289,11 @@ int zksc_ml_elementwise(zksc_ctx* ctx, int op, const uint64_t* a, const uint64_t
  * ZKSC_ERR_SHAPE for a coordinate >= p or a point off its curve; subgroup membership is not checked (ark-ec's unchecked forms).
  * zksc_pairing: e(P, Q) itself as 12 Fq coefficients (72 u64, canonical) in tower order -- for cross-checks. */
 int zksc_pairing_check(const uint64_t* g1, const uint64_t* g2, uint32_t n, int* is_one);
+/* MultilinearKZG::verify (multilinear_kzg.rs:90-116) in one host call.  commitment, proofs: 18 u64 each (ark-ec G1Projective memory form, as
+ * zksc_g1_msm / zksc_kzg_open return them); points (n_vars), evaluation: Montgomery Fr elements; srs_g2: the trusted setup's n_vars G2 powers
+ * tau_i g2 (trusted_setup.rs:37-46), 24 u64 each as in zksc_pairing_check.  *ok = 1 (verified) / 0.  No context, no device work. */
+int zksc_kzg_verify(const uint64_t* commitment, const uint64_t* points, const uint64_t* evaluation, const uint64_t* proofs, const uint64_t* srs_g2,
+                    uint32_t n_vars, int* ok);
 int zksc_pairing(const uint64_t* g1, const uint64_t* g2, uint64_t* out);
 int zksc_g1_msm(zksc_ctx* ctx, const uint64_t* scalars, const uint64_t* points, uint64_t n, uint64_t* out);
 int zksc_kzg_open(zksc_ctx* ctx, const uint64_t* evals, uint32_t n_vars, const uint64_t* points, const uint64_t* srs_g1, uint64_t* out_evaluation,

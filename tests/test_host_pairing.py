@@ -60,5 +60,12 @@ def test_reference_kzg_verify(prover, tampered, verifier, ev):
     assert MultilinearKZG.verify(commit, verifier, proof, srs_for(model), native=False) is True               # the same through pairing.py's integers
     assert MultilinearKZG.verify(commit, verifier, proof, srs_for(k.TrustedSetup(tampered))) is False         # tampered_tau_verify_status == false
     assert MultilinearKZG.verify(commit, verifier, proof, srs_for(k.TrustedSetup(tampered)), native=False) is False
+    # ... and with the commitment in ark-ec's memory form, as the device returns it: the whole check inside the library (zksc_kzg_verify)
+    ca = k.to_ark(commit)
+    assert MultilinearKZG.verify(ca, verifier, proof, srs_for(model)) is True
+    assert MultilinearKZG.verify(ca, verifier, proof, srs_for(k.TrustedSetup(tampered))) is False
+    assert MultilinearKZG.verify(ca, verifier, MultilinearKZGProof((v + 1) % R, proof.proofs), srs_for(model)) is False
+    assert MultilinearKZG.verify(k.to_ark(k.add(commit, k.G1)), verifier, proof, srs_for(model)) is False
+    assert MultilinearKZG.verify(ca, [(z + 1) % R for z in verifier], proof, srs_for(model)) is False
     assert MultilinearKZG.verify(commit, verifier, MultilinearKZGProof((v + 1) % R, proof.proofs), srs_for(model)) is False
     assert MultilinearKZG.verify(k.add(commit, k.G1), verifier, proof, srs_for(model)) is False

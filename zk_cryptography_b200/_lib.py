@@ -89,6 +89,7 @@ def lib():
         "zksc_kzg_open": (ctypes.c_int, [vp, _u64p, ctypes.c_uint32, _u64p, _u64p, _u64p, _u64p]),
         "zksc_pairing_check": (ctypes.c_int, [_u64p, _u64p, ctypes.c_uint32, ctypes.POINTER(ctypes.c_int)]),
         "zksc_pairing": (ctypes.c_int, [_u64p, _u64p, _u64p]),
+        "zksc_kzg_verify": (ctypes.c_int, [_u64p, _u64p, _u64p, _u64p, _u64p, ctypes.c_uint32, ctypes.POINTER(ctypes.c_int)]),
         "zksc_circuit_create": (ctypes.c_int, [vp, ctypes.c_uint32, _u32p, _u8p, _u32p, _u32p, ctypes.POINTER(vp)]),
         "zksc_circuit_free": (ctypes.c_int, [vp]),
         "zksc_circuit_evaluate": (ctypes.c_int, [vp, _u64p, _u64p]),

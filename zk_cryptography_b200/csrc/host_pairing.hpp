@@ -174,6 +174,62 @@ inline Fq12 from_fq2(const Fq2& a) { return {{a, kZero2, kZero2}, kZero6}; }
 struct G1Affine { Fq x, y; bool infinity; };
 struct G2Affine { Fq2 x, y; bool infinity; };
 
+// ---- the groups, affine (what a verifier needs: a handful of additions and two scalar multiplications per opening) -------------------------
+// the generators ark-ec uses (canonical limbs)
+static const uint64_t kG1x[6] = {0xfb3af00adb22c6bbull, 0x6c55e83ff97a1aefull, 0xa14e3a3f171bac58ull, 0xc3688c4f9774b905ull, 0x2695638c4fa9ac0full, 0x17f1d3a73197d794ull}, kG1y[6] = {0x0caa232946c5e7e1ull, 0xd03cc744a2888ae4ull, 0x00db18cb2c04b3edull, 0xfcf5e095d5d00af6ull, 0xa09e30ed741d8ae4ull, 0x08b3f481e3aaa0f1ull};
+static const uint64_t kG2x0[6] = {0xd48056c8c121bdb8ull, 0x0bac0326a805bbefull, 0xb4510b647ae3d177ull, 0xc6e47ad4fa403b02ull, 0x260805272dc51051ull, 0x024aa2b2f08f0a91ull}, kG2x1[6] = {0xe5ac7d055d042b7eull, 0x334cf11213945d57ull, 0xb5da61bbdc7f5049ull, 0x596bd0d09920b61aull, 0x7dacd3a088274f65ull, 0x13e02b6052719f60ull}, kG2y0[6] = {0xe193548608b82801ull, 0x923ac9cc3baca289ull, 0x6d429a695160d12cull, 0xadfd9baa8cbdd3a7ull, 0x8cc9cdc6da2e351aull, 0x0ce5d527727d6e11ull}, kG2y1[6] = {0xaaa9075ff05f79beull, 0x3f370d275cec1da1ull, 0x267492ab572e99abull, 0xcb3e287e85a763afull, 0x32acd2b02bc28b99ull, 0x0606c4a02ea734ccull};
+inline G1Affine g1_generator() { return {from_canonical(kG1x), from_canonical(kG1y), false}; }
+inline G2Affine g2_generator() { return {{from_canonical(kG2x0), from_canonical(kG2x1)}, {from_canonical(kG2y0), from_canonical(kG2y1)}, false}; }
+inline Fq mul3(const Fq& a) { return add(add(a, a), a); }
+inline Fq2 mul3(const Fq2& a) { return add(add(a, a), a); }
+template <class P, class F>
+inline P ec_add(const P& a, const P& b) {
+    if (a.infinity) return b;
+    if (b.infinity) return a;
+    F lam;
+    if (eq(a.x, b.x)) {
+        if (is_zero(add(a.y, b.y))) { P o = a; o.infinity = true; return o; }
+        lam = mul(mul3(mul(a.x, a.x)), inv(add(a.y, a.y)));
+    } else {
+        lam = mul(sub(b.y, a.y), inv(sub(b.x, a.x)));
+    }
+    P r;
+    r.infinity = false;
+    r.x = sub(sub(mul(lam, lam), a.x), b.x);
+    r.y = sub(mul(lam, sub(a.x, r.x)), a.y);
+    return r;
+}
+inline G1Affine g1_add(const G1Affine& a, const G1Affine& b) { return ec_add<G1Affine, Fq>(a, b); }
+inline G2Affine g2_add(const G2Affine& a, const G2Affine& b) { return ec_add<G2Affine, Fq2>(a, b); }
+inline G1Affine g1_neg(const G1Affine& a) { return {a.x, neg(a.y), a.infinity}; }
+inline G2Affine g2_neg(const G2Affine& a) { return {a.x, neg(a.y), a.infinity}; }
+// k * P, k as four canonical 64-bit limbs (a scalar-field element)
+template <class P, class F>
+inline P ec_mul(const uint64_t k[4], P pt) {
+    P acc = pt;
+    acc.infinity = true;
+    for (int i = 0; i < 256; i++) {
+        if ((k[i / 64] >> (i % 64)) & 1) acc = ec_add<P, F>(acc, pt);
+        pt = ec_add<P, F>(pt, pt);
+    }
+    return acc;
+}
+inline G1Affine g1_mul(const uint64_t k[4], const G1Affine& p) { return ec_mul<G1Affine, Fq>(k, p); }
+inline G2Affine g2_mul(const uint64_t k[4], const G2Affine& p) { return ec_mul<G2Affine, Fq2>(k, p); }
+// ark-ec's G1Projective in memory: Jacobian (X, Y, Z), each coordinate 6 Montgomery limbs (the same R = 2^384): x = X / Z^2, y = Y / Z^3
+inline bool g1_from_ark(const uint64_t* a, G1Affine* out) {
+    for (int c = 0; c < 3; c++)
+        if (geq_p(a + 6 * c)) return false;
+    Fq X, Y, Z;
+    memcpy(X.v, a, 48); memcpy(Y.v, a + 6, 48); memcpy(Z.v, a + 12, 48);
+    if (is_zero(Z)) { out->infinity = true; out->x = kZero; out->y = kZero; return true; }
+    const Fq zi = inv(Z), zi2 = mul(zi, zi);
+    out->infinity = false;
+    out->x = mul(X, zi2);
+    out->y = mul(Y, mul(zi2, zi));
+    return eq(mul(out->y, out->y), add(mul(mul(out->x, out->x), out->x), from_u64(4)));
+}
+
 // f_{|x|, psi(Q)}(P), conjugated for x < 0; 1 when either point is the identity
 inline Fq12 miller_loop(const G1Affine& p, const G2Affine& q) {
     if (p.infinity || q.infinity) return kOne12;

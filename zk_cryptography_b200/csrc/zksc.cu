@@ -2769,3 +2769,29 @@ extern "C" int zksc_pairing(const uint64_t* g1, const uint64_t* g2, uint64_t* ou
     }
     return ZKSC_OK;
 }
+
+// MultilinearKZG::verify (kzg/src/multilinear_kzg.rs:90-116; sum_pairing_results, kzg/src/utils.rs:42-61) on the host:
+//   e(commitment - evaluation g1, g2) == sum_i e(proof_i, tau_i g2 - point_i g2),   checked as   e(C - v g1, -g2) prod_i e(pi_i, tau_i g2 - z_i g2) == 1.
+// commitment, proofs: ark-ec G1Projective memory form (18 u64 each, as zksc_g1_msm / zksc_kzg_open return them); points, evaluation: Montgomery
+// Fr elements; srs_g2: the n G2 powers tau_i g2 of the trusted setup (trusted_setup.rs:37-46), affine canonical limbs (24 u64 each).
+// *ok = 1 / 0.  ZKSC_ERR_SHAPE for malformed points.  No context, no device work.
+extern "C" int zksc_kzg_verify(const uint64_t* commitment, const uint64_t* points, const uint64_t* evaluation, const uint64_t* proofs, const uint64_t* srs_g2,
+                               uint32_t n_vars, int* ok) {
+    if (!commitment || !evaluation || !ok || (n_vars && (!points || !proofs || !srs_g2))) return ZKSC_ERR_SHAPE;
+    pr::G1Affine c;
+    if (!pr::g1_from_ark(commitment, &c)) return ZKSC_ERR_SHAPE;
+    const pr::G1Affine g1 = pr::g1_generator();
+    const pr::G2Affine g2 = pr::g2_generator();
+    uint64_t k[4];
+    host::to_canonical(load_h(evaluation), k);
+    pr::Fq12 f = pr::miller_loop(pr::g1_add(c, pr::g1_neg(pr::g1_mul(k, g1))), pr::g2_neg(g2));
+    for (uint32_t i = 0; i < n_vars; i++) {
+        pr::G1Affine pi;
+        pr::G2Affine tau;
+        if (!pr::g1_from_ark(proofs + 18 * (size_t)i, &pi) || !load_g2(srs_g2 + 24 * (size_t)i, &tau)) return ZKSC_ERR_SHAPE;
+        host::to_canonical(load_h(points + 4 * (size_t)i), k);
+        f = pr::mul(f, pr::miller_loop(pi, pr::g2_add(tau, pr::g2_neg(pr::g2_mul(k, g2)))));
+    }
+    *ok = pr::eq(pr::final_exponentiation(f), pr::kOne12) ? 1 : 0;
+    return ZKSC_OK;
+}

@@ -58,6 +58,17 @@ class MultilinearKZG:
         proofs = np.ascontiguousarray(proof.proofs, dtype=np.uint64).reshape(-1, 18)
         if not (len(verifier_points) == len(srs.powers_of_tau_in_g2) == proofs.shape[0]):      # assert_eq! "Length mismatch", utils.rs:49-50
             raise ZkscError(-3, "Length mismatch")
+        if native and isinstance(commit, np.ndarray):
+            # everything in the library's host code: zksc_kzg_verify (group arithmetic, Miller loops, final exponentiation)
+            import ctypes
+            ev = np.ascontiguousarray(proof.evaluation, dtype=np.uint64) if isinstance(proof.evaluation, np.ndarray) else to_mont([int(proof.evaluation)])
+            g2 = np.array([w for q in srs.powers_of_tau_in_g2 for w in pairing._pack_g2(q)], dtype=np.uint64)
+            ok = ctypes.c_int(0)
+            rc = lib().zksc_kzg_verify(p64(np.ascontiguousarray(commit, dtype=np.uint64)), p64(to_mont([int(z) for z in verifier_points])), p64(ev), p64(proofs), p64(g2),
+                                       proofs.shape[0], ctypes.byref(ok))
+            if rc != 0:
+                raise ZkscError(rc, "zksc_kzg_verify: malformed point")
+            return bool(ok.value)
         c = pairing.g1_from_ark(commit) if isinstance(commit, np.ndarray) else commit
         v = int(from_mont(np.ascontiguousarray(proof.evaluation, dtype=np.uint64))) if isinstance(proof.evaluation, np.ndarray) else int(proof.evaluation)
         lhs_point = pairing.g1_add(c, pairing.g1_neg(pairing.g1_mul(v, pairing.G1)))
